@@ -1,0 +1,174 @@
+"""Host-side mirror of the reference's operator interface for the dense-correspondence path.
+
+`EppmContext` is the batched context API (eppm_create / eppm_compute_batch_host / ...), and
+`BaoFlowPatchmatchMultiscaleCuda` mirrors the reference's C++ class
+(bao_flow_patchmatch_multiscale_cuda.h:33-45: init, set_data, compute_flow) for callers who think in those terms.
+Everything executes in libeppm_b200.so on the GPU; nothing here computes."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+PLANE_RGBA1, PLANE_RGBA2, PLANE_CENSUS1, PLANE_CENSUS2 = 0, 1, 2, 3
+PLANE_NNF_FWD, PLANE_NNF_BWD, PLANE_COST_FWD, PLANE_COST_BWD, PLANE_FLOW = 4, 5, 6, 7, 8
+
+
+class EppmError(RuntimeError):
+    pass
+
+
+def default_params():
+    p = _lib.EppmParams()
+    _lib.load().eppm_default_params(C.byref(p))
+    return p
+
+
+def _ptr(a):
+    """Raw address of a numpy array, a torch tensor (host or device) or an int."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+class EppmContext:
+    """One context per (device, h, w, params): owns all device memory (eppm_create)."""
+
+    def __init__(self, h, w, max_batch=1, device=0, params=None):
+        self.lib = _lib.load()
+        self.h, self.w, self.max_batch, self.device = h, w, max_batch, device
+        self._ctx = C.c_void_p()
+        rc = self.lib.eppm_create(C.byref(self._ctx), device, h, w, max_batch, C.byref(params) if params is not None else None)
+        if rc != 0:
+            raise EppmError(f"eppm_create failed ({rc}): {self.lib.eppm_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.eppm_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EppmError(f"{what} failed ({rc}): {self.lib.eppm_last_error().decode()}")
+
+    # --- geometry ---------------------------------------------------------------------------------
+    @property
+    def num_levels(self):
+        return self.lib.eppm_num_levels(self._ctx)
+
+    def level_dims(self, level):
+        h, w = C.c_int(), C.c_int()
+        self._check(self.lib.eppm_level_dims(self._ctx, level, C.byref(h), C.byref(w)), "eppm_level_dims")
+        return h.value, w.value
+
+    # --- whole pipeline ------------------------------------------------------------------------------
+    def compute_batch_host(self, img1, img2, out=None):
+        """img1, img2: uint8 [n,h,w,3] host arrays (numpy or pinned torch); returns float32 [n,h,w,2] (u,v)."""
+        n = int(img1.shape[0])
+        if out is None:
+            out = np.empty((n, self.h, self.w, 2), np.float32)
+        self._check(self.lib.eppm_compute_batch_host(self._ctx, _ptr(img1), _ptr(img2), n, _ptr(out)), "eppm_compute_batch_host")
+        return out
+
+    def compute_batch_device(self, d_img1, d_img2, n, d_flow):
+        """Device-resident tensors / raw device addresses; stream-ordered, returns without synchronising."""
+        self._check(self.lib.eppm_compute_batch_device(self._ctx, _ptr(d_img1), _ptr(d_img2), n, _ptr(d_flow)), "eppm_compute_batch_device")
+
+    def synchronize(self):
+        self._check(self.lib.eppm_synchronize(self._ctx), "eppm_synchronize")
+
+    # --- staged ---------------------------------------------------------------------------------------
+    def stage_prepare(self, d_img1, d_img2, n):
+        self._check(self.lib.eppm_stage_prepare(self._ctx, _ptr(d_img1), _ptr(d_img2), n), "eppm_stage_prepare")
+
+    def stage_patchmatch(self):
+        self._check(self.lib.eppm_stage_patchmatch(self._ctx), "eppm_stage_patchmatch")
+
+    def stage_patchmatch_partial(self, n_steps):
+        self._check(self.lib.eppm_stage_patchmatch_partial(self._ctx, n_steps), "eppm_stage_patchmatch_partial")
+
+    def write_plane(self, which, arr, level=0, pair=0):
+        arr = np.ascontiguousarray(arr)
+        n = self.lib.eppm_write_plane(self._ctx, which, level, pair, arr.ctypes.data)
+        if n != arr.nbytes:
+            raise EppmError(f"eppm_write_plane returned {n} for {arr.nbytes} bytes: {self.lib.eppm_last_error().decode()}")
+
+    def stage_consistency(self):
+        self._check(self.lib.eppm_stage_consistency(self._ctx), "eppm_stage_consistency")
+
+    def stage_c2f(self, d_flow=None):
+        self._check(self.lib.eppm_stage_c2f(self._ctx, _ptr(d_flow)), "eppm_stage_c2f")
+
+    def read_plane(self, which, level=0, pair=0):
+        h, w = self.level_dims(level)
+        if which in (PLANE_NNF_FWD, PLANE_NNF_BWD, PLANE_COST_FWD, PLANE_COST_BWD):
+            h, w = self.level_dims(self.num_levels - 1)
+        shape, dt = {
+            PLANE_RGBA1: ((h, w, 4), np.uint8), PLANE_RGBA2: ((h, w, 4), np.uint8),
+            PLANE_CENSUS1: ((h, w), np.uint8), PLANE_CENSUS2: ((h, w), np.uint8),
+            PLANE_NNF_FWD: ((h, w, 2), np.int16), PLANE_NNF_BWD: ((h, w, 2), np.int16),
+            PLANE_COST_FWD: ((h, w), np.float32), PLANE_COST_BWD: ((h, w), np.float32),
+            PLANE_FLOW: ((h, w, 2), np.float32),
+        }[which]
+        out = np.empty(shape, dt)
+        n = self.lib.eppm_read_plane(self._ctx, which, level, pair, out.ctypes.data)
+        if n != out.nbytes:
+            raise EppmError(f"eppm_read_plane returned {n}: {self.lib.eppm_last_error().decode()}")
+        return out
+
+    def last_stage_ms(self):
+        buf = (C.c_float * 5)()
+        self._check(self.lib.eppm_last_stage_ms(self._ctx, C.byref(buf)), "eppm_last_stage_ms")
+        return dict(zip(("prepare", "patchmatch", "consistency", "c2f", "total"), list(buf)))
+
+    def launch_count(self, reset=False):
+        return int(self.lib.eppm_launch_count(1 if reset else 0))
+
+
+class BaoFlowPatchmatchMultiscaleCuda:
+    """Python mirror of the reference's class: init(h,w) / init(img1,img2,h,w), set_data(img1,img2) -> True,
+    compute_flow() -> (u, v) float32 [h,w] arrays (the reference fills caller arrays disp1_x / disp1_y)."""
+
+    def __init__(self, device=0):
+        self._device = device
+        self._ctx = None
+        self._pair = None
+
+    def init(self, *args):
+        if len(args) == 2:
+            h, w = args
+            imgs = None
+        elif len(args) == 4:
+            img1, img2, h, w = args
+            imgs = (img1, img2)
+        else:
+            raise TypeError("init(h, w) or init(img1, img2, h, w)")
+        if self._ctx is not None:
+            self._ctx.close()
+        self._ctx = EppmContext(h, w, 1, self._device)
+        if imgs is not None:
+            self.set_data(*imgs)
+
+    def set_data(self, img1, img2):
+        if self._ctx is None:
+            raise EppmError("set_data before init")
+        a = np.ascontiguousarray(img1, np.uint8).reshape(1, self._ctx.h, self._ctx.w, 3)
+        b = np.ascontiguousarray(img2, np.uint8).reshape(1, self._ctx.h, self._ctx.w, 3)
+        self._pair = (a, b)
+        return True  # the reference always returns true (bao_flow_patchmatch_multiscale_cuda.cpp:159-168)
+
+    def compute_flow(self):
+        if self._ctx is None or self._pair is None:
+            raise EppmError("compute_flow before init/set_data")
+        flow = self._ctx.compute_batch_host(self._pair[0], self._pair[1])[0]
+        return np.ascontiguousarray(flow[..., 0]), np.ascontiguousarray(flow[..., 1])

@@ -1,0 +1,354 @@
+// Context, arena and the public eppm_* entry points (include/eppm.h).
+// Host sequencing restates bao_flow_patchmatch_multiscale_cuda::init/set_data/compute_flow
+// (bao_flow_patchmatch_multiscale_cuda.cpp:112-168,217-306) for a whole batch of pairs per call.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "eppm_internal.h"
+
+namespace eppm {
+
+unsigned long long g_launches = 0;
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+bool cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return false;
+}
+
+__global__ void k_extract_census(const float4* __restrict__ pix, int pw, unsigned char* __restrict__ out, int w, int h) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    out[(size_t)y * w + x] = (unsigned char)(__float_as_uint(pix[(size_t)(y + PAD) * pw + x + PAD].w) & 0xffu);
+}
+
+static void host_luts(eppm_context* c) {
+    // _initGaussianLookupTable (bao_pmflow_kernel.cu:670-687), evaluated with the host libm like the reference does.
+    // `volatile` keeps the compiler from folding expf at build time: the reference calls it at run time.
+    const eppm_params& p = c->prm;
+    volatile float sig_s = 0.5f * p.patch_r;  // PM_SIG_S (defs.h:45)
+    float G[10];
+    for (int i = 0; i <= 9; i++) G[i] = i <= p.patch_r ? expf(-(i * i) / (sig_s * sig_s)) : 0.f;
+    for (int i = 0; i < 10; i++)
+        for (int j = 0; j < 10; j++) c->cost_lut.gg[i][j] = G[j] * G[i];  // cSpatialGaussian[abs(j)] * cSpatialGaussian[abs(i)] (:293)
+    volatile float lc = p.lambda_census;
+    for (int i = 0; i <= 8; i++) c->cost_lut.census[i] = 1 - expf(-float(i * i) / (lc * 8 * lc * 8));  // :683
+    volatile float wmf_sig_s = p.wmf_radius * 1.0f;  // WMF_SIG_S (defs.h:59)
+    for (int i = 0; i < 8; i++) c->wmf_lut.g[i] = i <= p.wmf_radius ? expf(-float(i * i) / (wmf_sig_s * wmf_sig_s)) : 0.f;  // refine:273
+    volatile int bs = p.blf_sig_s;
+    for (int i = 0; i < 21; i++) c->smooth_lut.g[i] = i <= 2 * p.blf_sig_s ? expf(-float(i * i) / float(bs * bs)) : 0.f;  // refine:812
+}
+
+}  // namespace eppm
+
+using namespace eppm;
+
+extern "C" {
+
+const char* eppm_last_error(void) { return g_err.c_str(); }
+const char* eppm_version(void) { return "eppm-b200 0.1 (sm_100a)"; }
+
+void eppm_default_params(eppm_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->pyr_levels = 3;
+    p->num_iter = 10;
+    p->patch_r = 9;
+    p->patch_stride = 2;
+    p->search_range = 30;
+    p->search_radius_min = 1;
+    p->num_rand_guess = 6;
+    p->prop_seg_length = 10;
+    p->lambda_ad = 0.1f;
+    p->lambda_census = 0.3f;
+    p->pm_sig_r = 0.1f;
+    p->stat_radius = 6;
+    p->stat_sim_thresh = 2;
+    p->wmf_radius = 4;
+    p->wmf_sig_r = 0.02f;
+    p->wmf_iters = 20;
+    p->blf_sig_s = 5;
+    p->blf_sig_r = 0.02f;
+    p->rng_mode = EPPM_RNG_XORWOW;
+    p->seed = 1234ULL;
+}
+
+unsigned long long eppm_launch_count(int reset) {
+    unsigned long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, const eppm_params* params) {
+    if (!out || h < 32 || w < 32 || h > 16384 || w > 16384 || max_batch < 1) {
+        set_error("eppm_create: bad argument");
+        return EPPM_ERR_ARG;
+    }
+    int ndev = 0;
+    if (!cuda_ok(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount") || device < 0 || device >= ndev) {
+        if (g_err.empty()) set_error("eppm_create: no such CUDA device (this library has no CPU path)");
+        return EPPM_ERR_CUDA;
+    }
+    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return EPPM_ERR_CUDA;
+    eppm_context* c = new eppm_context;
+    c->device = device;
+    c->h = h; c->w = w; c->max_batch = max_batch;
+    if (params) c->prm = *params; else eppm_default_params(&c->prm);
+    const eppm_params& p = c->prm;
+    if (p.pyr_levels < 1 || p.pyr_levels > MAX_LEVELS || p.patch_r != 9 || p.patch_stride != 2 || p.wmf_radius != 4 || p.num_iter < 0 ||
+        p.num_rand_guess < 0 || p.num_rand_guess > 16 || p.prop_seg_length < 1 || p.blf_sig_s < 1 || p.blf_sig_s > 10 || p.stat_radius < 0 ||
+        p.stat_radius > 16 || p.rng_mode != EPPM_RNG_XORWOW || p.lambda_ad != 0.1f || p.pm_sig_r != 0.1f) {
+        set_error("eppm_create: parameter combination not supported by this build");
+        delete c;
+        return EPPM_ERR_ARG;
+    }
+    // bao_pyr_init_dim (basic/bao_basic.h:196-211): int(double(dim) * pow(double(0.5f), i))
+    c->n_levels = p.pyr_levels;
+    for (int i = 0; i < c->n_levels; i++) {
+        LevelGeom& g = c->lv[i];
+        g.h = i == 0 ? h : int(double(h) * pow((double)0.5f, i));
+        g.w = i == 0 ? w : int(double(w) * pow((double)0.5f, i));
+        g.pw = g.w + 2 * PAD;
+        g.ph = g.h + 2 * PAD;
+        g.plane = (size_t)g.pw * g.ph;
+    }
+    const LevelGeom& gc = c->lv[c->n_levels - 1];
+    if (gc.w < 20 || gc.h < 20 || (gc.w + p.prop_seg_length - 1) / p.prop_seg_length > 1024 || (gc.h + p.prop_seg_length - 1) / p.prop_seg_length > 1024) {
+        set_error("eppm_create: coarsest level out of range");
+        delete c;
+        return EPPM_ERR_ARG;
+    }
+    c->profile = getenv("EPPM_PROFILE") && atoi(getenv("EPPM_PROFILE")) != 0;
+    if (!cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return EPPM_ERR_CUDA; }
+    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
+
+    // ---- arena: two passes (measure, then carve) ----
+    const size_t B = max_batch;
+    for (int pass = 0; pass < 2; pass++) {
+        Arena& A = c->arena;
+        A.used = 0;
+        if (pass == 1) {
+            if (!cuda_ok(cudaMalloc((void**)&A.base, A.size), "cudaMalloc(arena)")) { eppm_destroy(c); return EPPM_ERR_CUDA; }
+        } else {
+            A.base = nullptr;
+        }
+        for (int img = 0; img < 2; img++) c->d_rgb[img] = A.take<uint8_t>(B * h * w * 3);
+        c->d_flow_out = A.take<float>(B * h * w * 2);
+        for (int i = 0; i < c->n_levels; i++)
+            for (int img = 0; img < 2; img++) {
+                c->rgba[img][i] = A.take<uchar4>(B * c->lv[i].w * c->lv[i].h);
+                c->pix[img][i] = A.take<float4>(B * c->lv[i].plane);
+            }
+        if (c->n_levels > 2)  // generic blur scratch: the largest source level it can be asked to blur is level 1
+            for (int img = 0; img < 2; img++) c->blur_tmp[img] = A.take<uchar4>(B * c->lv[1].w * c->lv[1].h);
+        for (int i = 0; i < c->n_levels; i++) c->gauss[i].d_w = A.take<float>(7 * 7 + 1);
+        const size_t nc = (size_t)gc.w * gc.h;
+        for (int d = 0; d < 2; d++) {
+            c->nnf[d] = A.take<short2>(B * nc);
+            c->cost[d] = A.take<float>(B * nc);
+        }
+        c->nnf_tmp = A.take<short2>(B * nc);
+        c->occl_list = A.take<int>(B * nc);
+        c->occl_count = A.take<int>(64);
+        c->rng_init = A.take<short2>(nc);
+        c->rng_search = A.take<short2>((size_t)(p.num_iter > 0 ? p.num_iter : 1) * (p.num_rand_guess > 0 ? p.num_rand_guess : 1) * nc);
+        for (int i = 0; i < c->n_levels; i++) c->flow[i] = A.take<float2>(B * c->lv[i].w * c->lv[i].h);
+        c->flow_tmp = A.take<float2>(B * c->lv[0].w * c->lv[0].h);
+        if (pass == 0) A.size = A.used;
+    }
+    host_luts(c);
+    build_gauss_tables(c);
+    build_rng_tables(c);
+    if (!cuda_ok(cudaStreamSynchronize(c->stream), "context setup kernels")) { eppm_destroy(c); return EPPM_ERR_CUDA; }
+    *out = c;
+    return EPPM_OK;
+}
+
+void eppm_destroy(eppm_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->arena.base) cudaFree(c->arena.base);
+    for (int i = 0; i < 2; i++)
+        if (c->h_pinned_in[i]) cudaFreeHost(c->h_pinned_in[i]);
+    if (c->h_pinned_out) cudaFreeHost(c->h_pinned_out);
+    for (int i = 0; i < 6; i++)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+int eppm_num_levels(const eppm_context* c) { return c ? c->n_levels : EPPM_ERR_ARG; }
+int eppm_level_dims(const eppm_context* c, int level, int* h, int* w) {
+    if (!c || level < 0 || level >= c->n_levels) return EPPM_ERR_ARG;
+    if (h) *h = c->lv[level].h;
+    if (w) *w = c->lv[level].w;
+    return EPPM_OK;
+}
+void* eppm_stream(eppm_context* c) { return c ? (void*)c->stream : nullptr; }
+int eppm_synchronize(eppm_context* c) {
+    if (!c) return EPPM_ERR_ARG;
+    cudaSetDevice(c->device);
+    return cuda_ok(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize") ? EPPM_OK : EPPM_ERR_CUDA;
+}
+
+static int check_batch(eppm_context* c, const void* a, const void* b, int n) {
+    if (!c || !a || !b || n < 1 || n > c->max_batch) {
+        set_error("bad argument (null pointer or batch size out of range)");
+        return EPPM_ERR_ARG;
+    }
+    cudaSetDevice(c->device);
+    return EPPM_OK;
+}
+
+int eppm_stage_prepare(eppm_context* c, const uint8_t* d_img1, const uint8_t* d_img2, int n) {
+    int rc = check_batch(c, d_img1, d_img2, n);
+    if (rc) return rc;
+    c->n_cur = n;
+    run_prepare(c, d_img1, d_img2, n);
+    return cuda_ok(cudaGetLastError(), "prepare") ? EPPM_OK : EPPM_ERR_CUDA;
+}
+int eppm_stage_patchmatch(eppm_context* c) {
+    if (!c || c->n_cur < 1) { set_error("patchmatch before prepare"); return EPPM_ERR_STATE; }
+    cudaSetDevice(c->device);
+    run_patchmatch(c);
+    return cuda_ok(cudaGetLastError(), "patchmatch") ? EPPM_OK : EPPM_ERR_CUDA;
+}
+int eppm_stage_patchmatch_partial(eppm_context* c, int n_steps) {
+    if (!c || c->n_cur < 1) { set_error("patchmatch before prepare"); return EPPM_ERR_STATE; }
+    cudaSetDevice(c->device);
+    run_patchmatch_dirs(c, 2, n_steps);
+    return cuda_ok(cudaGetLastError(), "patchmatch") ? EPPM_OK : EPPM_ERR_CUDA;
+}
+int eppm_stage_consistency(eppm_context* c) {
+    if (!c || c->n_cur < 1) { set_error("consistency before prepare"); return EPPM_ERR_STATE; }
+    cudaSetDevice(c->device);
+    run_consistency(c);
+    return cuda_ok(cudaGetLastError(), "consistency") ? EPPM_OK : EPPM_ERR_CUDA;
+}
+int eppm_stage_c2f(eppm_context* c, float* d_flow) {
+    if (!c || c->n_cur < 1) { set_error("c2f before prepare"); return EPPM_ERR_STATE; }
+    cudaSetDevice(c->device);
+    run_c2f(c, d_flow);
+    return cuda_ok(cudaGetLastError(), "c2f") ? EPPM_OK : EPPM_ERR_CUDA;
+}
+
+int eppm_compute_batch_device(eppm_context* c, const uint8_t* d_img1, const uint8_t* d_img2, int n, float* d_flow) {
+    int rc = check_batch(c, d_img1, d_img2, n);
+    if (rc) return rc;
+    if (!d_flow) { set_error("null output"); return EPPM_ERR_ARG; }
+    c->n_cur = n;
+    cudaStream_t s = c->stream;
+    if (c->profile) cudaEventRecord(c->ev[0], s);
+    run_prepare(c, d_img1, d_img2, n);
+    if (c->profile) cudaEventRecord(c->ev[1], s);
+    run_patchmatch(c);
+    if (c->profile) cudaEventRecord(c->ev[2], s);
+    run_consistency(c);
+    if (c->profile) cudaEventRecord(c->ev[3], s);
+    run_c2f(c, d_flow);
+    if (c->profile) cudaEventRecord(c->ev[4], s);
+    return cuda_ok(cudaGetLastError(), "compute_batch") ? EPPM_OK : EPPM_ERR_CUDA;
+}
+
+int eppm_last_stage_ms(eppm_context* c, float out[5]) {
+    if (!c || !c->profile) return EPPM_ERR_STATE;
+    cudaSetDevice(c->device);
+    if (!cuda_ok(cudaEventSynchronize(c->ev[4]), "event sync")) return EPPM_ERR_CUDA;
+    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&out[i], c->ev[i], c->ev[i + 1]);
+    cudaEventElapsedTime(&out[4], c->ev[0], c->ev[4]);
+    return EPPM_OK;
+}
+
+int eppm_compute_batch_host(eppm_context* c, const uint8_t* img1, const uint8_t* img2, int n, float* flow) {
+    int rc = check_batch(c, img1, img2, n);
+    if (rc) return rc;
+    if (!flow) { set_error("null output"); return EPPM_ERR_ARG; }
+    const size_t in_bytes = (size_t)n * c->h * c->w * 3, out_bytes = (size_t)n * c->h * c->w * 2 * sizeof(float);
+    cudaStream_t s = c->stream;
+    // Pageable or pinned host memory both work; pinned buffers make the copies truly asynchronous.
+    if (!cuda_ok(cudaMemcpyAsync(c->d_rgb[0], img1, in_bytes, cudaMemcpyHostToDevice, s), "H2D img1")) return EPPM_ERR_CUDA;
+    if (!cuda_ok(cudaMemcpyAsync(c->d_rgb[1], img2, in_bytes, cudaMemcpyHostToDevice, s), "H2D img2")) return EPPM_ERR_CUDA;
+    rc = eppm_compute_batch_device(c, c->d_rgb[0], c->d_rgb[1], n, c->d_flow_out);
+    if (rc) return rc;
+    if (!cuda_ok(cudaMemcpyAsync(flow, c->d_flow_out, out_bytes, cudaMemcpyDeviceToHost, s), "D2H flow")) return EPPM_ERR_CUDA;
+    return cuda_ok(cudaStreamSynchronize(s), "compute_batch_host") ? EPPM_OK : EPPM_ERR_CUDA;
+}
+
+long eppm_read_plane(eppm_context* c, int which, int level, int pair, void* host_out) {
+    if (!c || !host_out || level < 0 || level >= c->n_levels || pair < 0 || pair >= c->max_batch) return EPPM_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (!cuda_ok(cudaStreamSynchronize(c->stream), "read_plane sync")) return EPPM_ERR_CUDA;
+    const LevelGeom& g = c->lv[level];
+    const LevelGeom& gc = c->lv[c->n_levels - 1];
+    const size_t n = (size_t)g.w * g.h, nc = (size_t)gc.w * gc.h;
+    cudaError_t e = cudaSuccess;
+    long bytes = 0;
+    switch (which) {
+    case EPPM_PLANE_RGBA1: case EPPM_PLANE_RGBA2:
+        bytes = n * 4;
+        e = cudaMemcpy(host_out, c->rgba[which - EPPM_PLANE_RGBA1][level] + pair * n, bytes, cudaMemcpyDeviceToHost);
+        break;
+    case EPPM_PLANE_CENSUS1: case EPPM_PLANE_CENSUS2: {
+        unsigned char* tmp = nullptr;
+        bytes = n;
+        if (!cuda_ok(cudaMalloc((void**)&tmp, n), "cudaMalloc")) return EPPM_ERR_CUDA;
+        k_extract_census<<<dim3((g.w + 127) / 128, g.h), 128, 0, c->stream>>>(c->pix[which - EPPM_PLANE_CENSUS1][level] + pair * g.plane, g.pw, tmp, g.w, g.h);
+        cudaStreamSynchronize(c->stream);
+        e = cudaMemcpy(host_out, tmp, n, cudaMemcpyDeviceToHost);
+        cudaFree(tmp);
+        break;
+    }
+    case EPPM_PLANE_NNF_FWD: case EPPM_PLANE_NNF_BWD:
+        bytes = nc * 4;
+        e = cudaMemcpy(host_out, c->nnf[which - EPPM_PLANE_NNF_FWD] + pair * nc, bytes, cudaMemcpyDeviceToHost);
+        break;
+    case EPPM_PLANE_COST_FWD: case EPPM_PLANE_COST_BWD:
+        bytes = nc * 4;
+        e = cudaMemcpy(host_out, c->cost[which - EPPM_PLANE_COST_FWD] + pair * nc, bytes, cudaMemcpyDeviceToHost);
+        break;
+    case EPPM_PLANE_FLOW:
+        bytes = n * 8;
+        e = cudaMemcpy(host_out, c->flow[level] + pair * n, bytes, cudaMemcpyDeviceToHost);
+        break;
+    default:
+        return EPPM_ERR_ARG;
+    }
+    return cuda_ok(e, "read_plane copy") ? bytes : EPPM_ERR_CUDA;
+}
+
+long eppm_write_plane(eppm_context* c, int which, int level, int pair, const void* host_in) {
+    if (!c || !host_in || level < 0 || level >= c->n_levels || pair < 0 || pair >= c->max_batch) return EPPM_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (!cuda_ok(cudaStreamSynchronize(c->stream), "write_plane sync")) return EPPM_ERR_CUDA;
+    const LevelGeom& g = c->lv[level];
+    const LevelGeom& gc = c->lv[c->n_levels - 1];
+    const size_t n = (size_t)g.w * g.h, nc = (size_t)gc.w * gc.h;
+    cudaError_t e;
+    long bytes;
+    switch (which) {
+    case EPPM_PLANE_NNF_FWD: case EPPM_PLANE_NNF_BWD:
+        bytes = nc * 4;
+        e = cudaMemcpy(c->nnf[which - EPPM_PLANE_NNF_FWD] + pair * nc, host_in, bytes, cudaMemcpyHostToDevice);
+        break;
+    case EPPM_PLANE_COST_FWD: case EPPM_PLANE_COST_BWD:
+        bytes = nc * 4;
+        e = cudaMemcpy(c->cost[which - EPPM_PLANE_COST_FWD] + pair * nc, host_in, bytes, cudaMemcpyHostToDevice);
+        break;
+    case EPPM_PLANE_FLOW:
+        bytes = n * 8;
+        e = cudaMemcpy(c->flow[level] + pair * n, host_in, bytes, cudaMemcpyHostToDevice);
+        break;
+    default:
+        return EPPM_ERR_ARG;
+    }
+    return cuda_ok(e, "write_plane copy") ? bytes : EPPM_ERR_CUDA;
+}
+
+}  // extern "C"

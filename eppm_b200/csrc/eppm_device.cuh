@@ -1,0 +1,106 @@
+// Device-side arithmetic primitives shared by all kernels of libeppm_b200.
+//
+// Every floating-point step is written with explicit round-to-nearest intrinsics so that nvcc can
+// neither contract nor re-associate it.  The sequences restate, operation for operation, what
+// nvcc 12.9 generates for the reference's expressions at its default flags (-fmad=true, no fast-math);
+// the reference file:line each one follows is given beside it.  Results are therefore bit-identical
+// to the reference's kernels given identical inputs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace eppm {
+
+constexpr int PAD = 16;        // replicated border of the packed planes (>= 9 + plane-fitting reach 5.2, and >= 10 at the PatchMatch level)
+constexpr int PATCH_R = 9;     // defs.h:42
+constexpr int INVALID_LOCATION = -10000;  // bao_pmflow_refine_kernel.cu:46
+#define EPPM_UNKNOWN_FLOW 1e10f            // defs.h:89-91
+#define EPPM_UNKNOWN_FLOW_THRESH 1e9f      // defs.h:84-86
+
+// Packed pixel of a pyramid level: r,g,b as the floats a cudaReadModeNormalizedFloat fetch returns
+// (exactly RN(k/255), probed on B200) and the 3x3 census byte in the bits of .w.
+// One 16-byte load replaces the reference's two texture fetches (colour + census) per sample.
+struct PlaneRef {
+    const float4* p;   // points at logical pixel (0,0) of one image inside its padded plane
+    int pw;            // padded row pitch in pixels
+};
+
+__device__ __forceinline__ float4 ldpix(const float4* p) { return __ldg(p); }
+
+// LUTs the reference uploads to __constant__ memory on every call (bao_pmflow_kernel.cu:670-687);
+// here they ride in kernel parameter space (constant bank 0), so contexts never share mutable state.
+struct CostLut {
+    float gg[10][10];   // gg[|i|][|j|] = G[|j|]*G[|i|], G[k] = expf(-k^2/sigma_s^2)   (:293, :676)
+    float census[9];    // 1 - expf(-d^2/(lambda_census*8)^2)                              (:683)
+    float pad_[3];
+};
+
+// x / -(0.1f*0.1f), correctly rounded.  nvcc lowers the reference's `-(c*c)/(LAMBDA_AD*LAMBDA_AD)` and
+// `-(w+t)/(PM_SIG_R*PM_SIG_R)` (bao_pmflow_kernel.cu:282,288) to a division by the folded constant
+// -0.010000000707805157 whose fast path is q0=x*r, rem=fma(q0,0.01',x), q=fma(r,rem,q0) with r=-99.99999237
+// (FCHK guards only denormal/huge operands).  tools/probe_hw.cu verified on B200 that this equals div.rn for
+// EVERY float in [2^-20, 4); the operands here are 0 or in [1.5e-5, 2].
+__device__ __forceinline__ float div_neg_0p01(float x) {
+    const float r = -99.99999237060546875f;
+    const float d = 0.010000000707805156708f;
+    float q0 = __fmaf_rn(x, r, 0.0f);
+    float rem = __fmaf_rn(q0, d, x);
+    return __fmaf_rn(r, rem, q0);
+}
+
+// __expf as the reference calls it: ex2.approx(x*log2e) with the x*log2e < -126 half/square fix-up that
+// nvcc emits when -ftz=false.  Using the intrinsic itself keeps the instruction sequence identical.
+__device__ __forceinline__ float exp_ref(float x) { return __expf(x); }
+
+__device__ __forceinline__ float max3abs_diff(const float4& a, const float4& b) {
+    float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
+    return fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
+}
+
+// One sample of the bilateral-weighted AD+census patch cost (bao_pmflow_kernel.cu:274-296):
+//   cost   = 1 - exp(-c^2/lambda_ad^2) + LUT_census[popc(census1 ^ census2)],  c = max|rgb1-rgb2|
+//   weight = exp(-(d1^2 + d2^2)/sigma_r^2) * G[|j|]*G[|i|],                     dk = max|centre_k - p_k|
+// accumulated as cost_sum = fma(cost, weight, cost_sum); weight_sum += weight, in sample order.
+// d1 (image-1 side) is passed in so callers can hoist it across candidates.
+__device__ __forceinline__ void sample_term(const float4& p1, const float4& p2, const float4& c2, float d1,
+                                            float gg, const CostLut& lut, float& cost_sum, float& weight_sum) {
+    float c = max3abs_diff(p1, p2);
+    float e = exp_ref(div_neg_0p01(__fmul_rn(c, c)));
+    unsigned cx = (__float_as_uint(p1.w) ^ __float_as_uint(p2.w)) & 0xffu;
+    float cost = __fadd_rn(__fadd_rn(1.0f, -e), lut.census[__popc(cx)]);
+    float d2 = max3abs_diff(c2, p2);
+    float arg = __fmaf_rn(d1, d1, __fmul_rn(d2, d2));
+    float w = __fmul_rn(exp_ref(div_neg_0p01(arg)), gg);
+    cost_sum = __fmaf_rn(cost, w, cost_sum);
+    weight_sum = __fadd_rn(weight_sum, w);
+}
+
+// _d_compute_patch_dist (bao_pmflow_kernel.cu:255-301): 100 samples at stride 2 over a 19x19 patch.
+// A/B point at logical (0,0) of the source / target packed planes (same padded pitch pw).
+// Texture clamp addressing is realised by the replicated PAD border: |x2+j| never leaves it because
+// targets lie in [0,w]x[0,h] and |j| <= 9 < PAD.
+template <int STRIDE>
+__device__ __forceinline__ float patch_cost(const float4* __restrict__ A, const float4* __restrict__ B, int pw,
+                                            int x1, int y1, int x2, int y2, const CostLut& lut) {
+    const float4* a0 = A + (size_t)y1 * pw + x1;
+    const float4* b0 = B + (size_t)y2 * pw + x2;
+    const float4 c1 = ldpix(a0);
+    const float4 c2 = ldpix(b0);
+    float cost_sum = 0.f, weight_sum = 0.f;
+#pragma unroll 1
+    for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
+        const float4* ar = a0 + i * pw;
+        const float4* br = b0 + i * pw;
+        const int ai = i < 0 ? -i : i;
+#pragma unroll
+        for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE) {
+            const float4 p1 = ldpix(ar + j);
+            const float4 p2 = ldpix(br + j);
+            const float d1 = max3abs_diff(c1, p1);
+            sample_term(p1, p2, c2, d1, lut.gg[ai][j < 0 ? -j : j], lut, cost_sum, weight_sum);
+        }
+    }
+    return __fdiv_rn(cost_sum, weight_sum);
+}
+
+}  // namespace eppm

@@ -1,0 +1,120 @@
+// Host-side context of libeppm_b200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/eppm.h"
+#include "eppm_device.cuh"
+
+namespace eppm {
+
+constexpr int MAX_LEVELS = 6;
+
+struct LevelGeom {
+    int w, h;     // bao_pyr_init_dim: int(double(dim) * pow(0.5, level))  (basic/bao_basic.h:196-211)
+    int pw, ph;   // padded plane dims: w + 2*PAD, h + 2*PAD
+    size_t plane; // pw*ph
+};
+
+struct GaussTab {   // tap weights of one pyramid blur, computed on the device with the reference's expression
+    float* d_w;     // [(2r+1)^2]
+    int r;
+};
+
+struct Arena {
+    char* base = nullptr;
+    size_t size = 0, used = 0;
+    template <class T>
+    T* take(size_t n) {
+        size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+        T* p = reinterpret_cast<T*>(base + used);
+        used += bytes;
+        return p;
+    }
+};
+
+struct SmoothLut {
+    float g[21];     // expf(-i^2 / sig_s^2), i = 0..2*sig_s  (bao_pmflow_refine_kernel.cu:809-813)
+    float pad_[3];
+};
+struct WmfLut {
+    float g[8];      // expf(-i^2 / (WMF_SIG_S^2)), i = 0..WMF_RADIUS (:270-275)
+};
+
+}  // namespace eppm
+
+struct eppm_context {
+    int device = 0;
+    int h = 0, w = 0, max_batch = 0;
+    int n_cur = 0;                 // pairs of the batch currently resident
+    eppm_params prm;
+    int n_levels = 0;
+    eppm::LevelGeom lv[eppm::MAX_LEVELS];
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    bool profile = false;
+    cudaEvent_t ev[6] = {};
+    float stage_ms[5] = {};
+
+    eppm::Arena arena;
+    // inputs staged on the device for the host-buffer API
+    uint8_t* d_rgb[2] = {nullptr, nullptr};      // [B][h][w][3]
+    float* d_flow_out = nullptr;                 // [B][h][w][2]
+    uint8_t* h_pinned_in[2] = {nullptr, nullptr};
+    float* h_pinned_out = nullptr;
+    // pyramid
+    uchar4* rgba[2][eppm::MAX_LEVELS] = {};      // [B][h_l][w_l] dense
+    uchar4* blur_tmp[2] = {nullptr, nullptr};    // scratch for pyramid levels beyond the 2-octave fast path
+    float4* pix[2][eppm::MAX_LEVELS] = {};       // [B][ph_l][pw_l] packed float rgb + census
+    eppm::GaussTab gauss[eppm::MAX_LEVELS];      // [0] pre-blur, [i] blur feeding level i
+    // PatchMatch state at the coarsest level: index = dir (0 fwd, 1 bwd)
+    short2* nnf[2] = {nullptr, nullptr};         // [B][h_c][w_c]
+    float* cost[2] = {nullptr, nullptr};
+    short2* nnf_tmp = nullptr;                   // snapshot buffer for the in-place filters
+    int* occl_list = nullptr;                    // compacted occluded pixels for WMF: [B*h_c*w_c]
+    int* occl_count = nullptr;                   // [2] device counters
+    short2* rng_init = nullptr;                  // [h_c][w_c] initial targets (same for every pair/direction)
+    short2* rng_search = nullptr;                // [num_iter][num_guess][h_c][w_c] raw (short(r1), short(r2))
+    // flow pyramid (+ snapshot buffer)
+    float2* flow[eppm::MAX_LEVELS] = {};
+    float2* flow_tmp = nullptr;                  // level-0 sized
+    eppm::CostLut cost_lut;
+    eppm::SmoothLut smooth_lut;
+    eppm::WmfLut wmf_lut;
+};
+
+namespace eppm {
+void set_error(const std::string& s);
+bool cuda_ok(cudaError_t e, const char* what);
+extern unsigned long long g_launches;
+#define EPPM_LAUNCH_COUNT(n) (eppm::g_launches += (n))
+
+// stage drivers (each enqueues on ctx->stream)
+void run_prepare(eppm_context* c, const uint8_t* d_img1, const uint8_t* d_img2, int n);
+void run_patchmatch(eppm_context* c);
+void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps = 1 << 30);
+void run_consistency(eppm_context* c);
+void run_c2f(eppm_context* c, float* d_flow_out);
+void build_rng_tables(eppm_context* c);
+void build_gauss_tables(eppm_context* c);
+
+// building blocks reused by the legacy stage ABI (foreign buffers)
+void op_lr_check(cudaStream_t s, short2* nnf, float* cost, const short2* nnf2, int w, int h, int n);
+void op_outlier_removal(cudaStream_t s, const short2* src, short2* dst, float* cost, int w, int h, int n, int R, int sim);
+void wmf_sweeps(eppm_context* c, short2*& cur, short2*& other, const float4* pix, size_t plane, int pw, int w, int h, int n, int iters,
+                bool only_occlusion);
+void op_fill_holes(cudaStream_t s, const short2* src, short2* dst, const float4* pix, size_t plane, int pw, int w, int h, int n);
+void op_nnf_to_flow(cudaStream_t s, const short2* nnf, float2* flow, int w, int h, int n);
+void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const LevelGeom& g, const float2* coarse, int ws, int hs, int upsample,
+               float2* out, int n);
+void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pix1, const LevelGeom& g, int n);
+void op_preblur_rgba(eppm_context* c, const uchar4* src1, const uchar4* src2, size_t pitch_bytes);
+void op_pyramid_and_pack(eppm_context* c, int n);
+void op_pack_foreign(cudaStream_t s, const uchar4* rgba, size_t rgba_pitch_bytes, const unsigned char* census, size_t census_pitch_bytes, float4* pix,
+                     const LevelGeom& g);
+void op_extract_census(cudaStream_t s, const float4* pix, const LevelGeom& g, unsigned char* out, size_t out_pitch_bytes);
+void k_pack_planes(cudaStream_t s, const uchar4* rgba, size_t rgba_pitch_bytes, size_t rgba_img_stride_bytes, float4* pix,
+                   const LevelGeom& g, int n_img);
+}  // namespace eppm

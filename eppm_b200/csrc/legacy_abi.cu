@@ -1,0 +1,208 @@
+// The reference's stage functions (include/eppm_legacy_abi.h) on FOREIGN buffers in the reference's layouts:
+// uchar4 / u8 planes with a byte pitch, dense short2 / float / float2 planes.  Each entry point converts the foreign
+// image planes into this library's packed planes (one small kernel), runs the same kernels the eppm_* API runs, and
+// writes the result back in the foreign layout.  A context per (h, w) is created on first use and cached.
+#include <stdio.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
+
+#include "../../include/eppm_legacy_abi.h"
+#include "eppm_internal.h"
+
+using namespace eppm;
+
+namespace {
+
+std::mutex g_mu;
+std::map<std::pair<int, int>, eppm_context*> g_single;   // single-level contexts keyed by (h, w)
+std::map<std::pair<int, int>, eppm_context*> g_pyramid;  // full-pyramid contexts keyed by (h, w) of level 0
+
+void complain(const char* where) { fprintf(stderr, "EPPM(b200) %s: %s\n", where, eppm_last_error()); }
+
+eppm_context* get_ctx(std::map<std::pair<int, int>, eppm_context*>& cache, int h, int w, int levels) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = cache.find({h, w});
+    if (it != cache.end() && it->second->n_levels == levels) return it->second;
+    if (it != cache.end()) { eppm_destroy(it->second); cache.erase(it); }
+    eppm_params p;
+    eppm_default_params(&p);
+    p.pyr_levels = levels;
+    eppm_context* c = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (eppm_create(&c, dev, h, w, 1, &p) != EPPM_OK) { complain("context"); return nullptr; }
+    c->n_cur = 1;
+    cache[{h, w}] = c;
+    return c;
+}
+
+// entry: make work queued on the legacy default stream visible; exit: our stream is drained
+struct Scope {
+    eppm_context* c;
+    const char* name;
+    Scope(eppm_context* c_, const char* n) : c(c_), name(n) { cudaStreamSynchronize(0); }
+    ~Scope() {
+        if (c && !cuda_ok(cudaStreamSynchronize(c->stream), name)) complain(name);
+    }
+};
+
+template <class T>
+void copy_in(eppm_context* c, T* dense, const T* foreign, size_t pitch, int w, int h) {
+    cudaMemcpy2DAsync(dense, (size_t)w * sizeof(T), foreign, pitch, (size_t)w * sizeof(T), h, cudaMemcpyDeviceToDevice, c->stream);
+}
+template <class T>
+void copy_out(eppm_context* c, T* foreign, size_t pitch, const T* dense, int w, int h) {
+    cudaMemcpy2DAsync(foreign, pitch, dense, (size_t)w * sizeof(T), (size_t)w * sizeof(T), h, cudaMemcpyDeviceToDevice, c->stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+void baoCudaPatchMatchMultiscalePrepare(uchar4** pImgPyr1, uchar4** pImgPyr2, unsigned char** pCensusPyr1, unsigned char** pCensusPyr2,
+                                        uchar4** pTempPyr1, uchar4** pTempPyr2, int* arrH, int* arrW, size_t* arrPitchUchar4,
+                                        size_t* arrPitchUchar1, int nLevels, uchar4* d_img1, uchar4* d_img2, int h, int w) {
+    (void)pTempPyr1; (void)pTempPyr2;
+    eppm_context* c = get_ctx(g_pyramid, h, w, nLevels);
+    if (!c) return;
+    Scope sc(c, "baoCudaPatchMatchMultiscalePrepare");
+    op_preblur_rgba(c, d_img1, d_img2, arrPitchUchar4[0]);
+    op_pyramid_and_pack(c, 1);
+    for (int i = 0; i < nLevels; i++) {
+        const LevelGeom& g = c->lv[i];
+        if (g.w != arrW[i] || g.h != arrH[i]) { fprintf(stderr, "EPPM(b200): level %d geometry mismatch\n", i); return; }
+        copy_out(c, pImgPyr1[i], arrPitchUchar4[i], c->rgba[0][i], g.w, g.h);
+        copy_out(c, pImgPyr2[i], arrPitchUchar4[i], c->rgba[1][i], g.w, g.h);
+        op_extract_census(c->stream, c->pix[0][i], g, pCensusPyr1[i], arrPitchUchar1[i]);
+        op_extract_census(c->stream, c->pix[1][i], g, pCensusPyr2[i], arrPitchUchar1[i]);
+    }
+}
+
+void baoCudaCensusTransform(unsigned char* d_census1, unsigned char* d_census2, uchar4* d_img1, uchar4* d_img2, int w, int h, size_t img_pitch,
+                            size_t census_pitch) {
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaCensusTransform");
+    const LevelGeom& g = c->lv[0];
+    k_pack_planes(c->stream, d_img1, img_pitch, 0, c->pix[0][0], g, 1);
+    k_pack_planes(c->stream, d_img2, img_pitch, 0, c->pix[1][0], g, 1);
+    op_extract_census(c->stream, c->pix[0][0], g, d_census1, census_pitch);
+    op_extract_census(c->stream, c->pix[1][0], g, d_census2, census_pitch);
+}
+
+void baoCudaPatchMatch(short2* d_disp_vec, float* d_cost, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1, unsigned char* d_census2,
+                       int w, int h, size_t img_pitch, size_t cost_pitch, size_t disp_pitch, size_t census_pitch) {
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaPatchMatch");
+    const LevelGeom& g = c->lv[0];
+    op_pack_foreign(c->stream, d_img1, img_pitch, d_census1, census_pitch, c->pix[0][0], g);
+    op_pack_foreign(c->stream, d_img2, img_pitch, d_census2, census_pitch, c->pix[1][0], g);
+    run_patchmatch_dirs(c, 1);
+    copy_out(c, d_disp_vec, disp_pitch, c->nnf[0], w, h);
+    copy_out(c, d_cost, cost_pitch, c->cost[0], w, h);
+}
+
+void baoCudaLeftRightCheck(short2* d_disp_vec, float* d_cost, short2* d_disp_vec2, float* d_cost2, int w, int h, size_t cost_pitch,
+                           size_t disp_pitch) {
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaLeftRightCheck");
+    copy_in(c, c->nnf[0], d_disp_vec, disp_pitch, w, h);
+    copy_in(c, c->nnf[1], d_disp_vec2, disp_pitch, w, h);
+    copy_in(c, c->cost[0], d_cost, cost_pitch, w, h);
+    copy_in(c, c->cost[1], d_cost2, cost_pitch, w, h);
+    op_lr_check(c->stream, c->nnf[0], c->cost[0], c->nnf[1], w, h, 1);
+    op_lr_check(c->stream, c->nnf[1], c->cost[1], c->nnf[0], w, h, 1);
+    copy_out(c, d_disp_vec, disp_pitch, c->nnf[0], w, h);
+    copy_out(c, d_disp_vec2, disp_pitch, c->nnf[1], w, h);
+    copy_out(c, d_cost, cost_pitch, c->cost[0], w, h);
+    copy_out(c, d_cost2, cost_pitch, c->cost[1], w, h);
+}
+
+void baoCudaOutlierRemoval(short2* d_disp_vec, float* d_cost, int w, int h, size_t cost_pitch, size_t disp_pitch) {
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaOutlierRemoval");
+    copy_in(c, c->nnf[0], d_disp_vec, disp_pitch, w, h);
+    copy_in(c, c->cost[0], d_cost, cost_pitch, w, h);
+    op_outlier_removal(c->stream, c->nnf[0], c->nnf_tmp, c->cost[0], w, h, 1, c->prm.stat_radius, c->prm.stat_sim_thresh);
+    copy_out(c, d_disp_vec, disp_pitch, c->nnf_tmp, w, h);
+    copy_out(c, d_cost, cost_pitch, c->cost[0], w, h);
+}
+
+void baoCudaWeightedMedianFilter(short2* d_disp_vec, float* d_cost, uchar4* d_img, int w, int h, size_t img_pitch, size_t cost_pitch,
+                                 size_t disp_pitch, int num_iter, bool is_only_occlusion) {
+    (void)d_cost; (void)cost_pitch;
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaWeightedMedianFilter");
+    const LevelGeom& g = c->lv[0];
+    op_pack_foreign(c->stream, d_img, img_pitch, nullptr, 0, c->pix[0][0], g);
+    copy_in(c, c->nnf[0], d_disp_vec, disp_pitch, w, h);
+    short2* cur = c->nnf[0];
+    short2* other = c->nnf_tmp;
+    wmf_sweeps(c, cur, other, c->pix[0][0], g.plane, g.pw, w, h, 1, num_iter, is_only_occlusion);
+    copy_out(c, d_disp_vec, disp_pitch, cur, w, h);
+}
+
+void baoCudaFillHole(short2* d_disp_vec, float* d_cost, uchar4* d_img, int w, int h, size_t img_pitch, size_t cost_pitch, size_t disp_pitch) {
+    (void)d_cost; (void)cost_pitch;
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaFillHole");
+    const LevelGeom& g = c->lv[0];
+    op_pack_foreign(c->stream, d_img, img_pitch, nullptr, 0, c->pix[0][0], g);
+    copy_in(c, c->nnf[0], d_disp_vec, disp_pitch, w, h);
+    op_fill_holes(c->stream, c->nnf[0], c->nnf_tmp, c->pix[0][0], g.plane, g.pw, w, h, 1);
+    copy_out(c, d_disp_vec, disp_pitch, c->nnf_tmp, w, h);
+}
+
+void baoCudaNNF2Flow(float2* d_flow, short2* d_disp_vec, int w, int h, size_t disp_pitch, size_t flow_pitch) {
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaNNF2Flow");
+    copy_in(c, c->nnf[0], d_disp_vec, disp_pitch, w, h);
+    op_nnf_to_flow(c->stream, c->nnf[0], c->flow[0], w, h, 1);
+    copy_out(c, d_flow, flow_pitch, c->flow[0], w, h);
+}
+
+void baoCudaBLFCostFilterRefine(float2* d_flow_vec, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1, unsigned char* d_census2, int w,
+                                int h, size_t img_pitch, size_t census_pitch) {
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaBLFCostFilterRefine");
+    const LevelGeom& g = c->lv[0];
+    op_pack_foreign(c->stream, d_img1, img_pitch, d_census1, census_pitch, c->pix[0][0], g);
+    op_pack_foreign(c->stream, d_img2, img_pitch, d_census2, census_pitch, c->pix[1][0], g);
+    op_refine(c, c->pix[0][0], c->pix[1][0], g, d_flow_vec, w, h, 0, c->flow_tmp, 1);
+    cudaMemcpyAsync(d_flow_vec, c->flow_tmp, (size_t)w * h * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream);
+}
+
+void baoCudaBLF_C2F(float2** pFlowPyr, uchar4** pImgPyr1, uchar4** pImgPyr2, unsigned char** pCensusPyr1, unsigned char** pCensusPyr2,
+                    float2** pTempPyr1, float2** pTempPyr2, int* arrH, int* arrW, size_t* arrPitchUchar4, size_t* arrPitchUchar1, int nLayerIdx) {
+    (void)pTempPyr1; (void)pTempPyr2;
+    const int l = nLayerIdx, w = arrW[l], h = arrH[l];
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaBLF_C2F");
+    const LevelGeom& g = c->lv[0];
+    op_pack_foreign(c->stream, pImgPyr1[l], arrPitchUchar4[l], pCensusPyr1[l], arrPitchUchar1[l], c->pix[0][0], g);
+    op_pack_foreign(c->stream, pImgPyr2[l], arrPitchUchar4[l], pCensusPyr2[l], arrPitchUchar1[l], c->pix[1][0], g);
+    op_refine(c, c->pix[0][0], c->pix[1][0], g, pFlowPyr[l + 1], arrW[l + 1], arrH[l + 1], 1, pFlowPyr[l], 1);
+}
+
+void baoCudaFlowSmoothing(float2* d_flow, uchar4* d_img, int w, int h, size_t img_pitch, size_t flow_pitch) {
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaFlowSmoothing");
+    const LevelGeom& g = c->lv[0];
+    op_pack_foreign(c->stream, d_img, img_pitch, nullptr, 0, c->pix[0][0], g);
+    copy_in(c, c->flow[0], d_flow, flow_pitch, w, h);
+    op_smooth(c, c->flow[0], c->flow_tmp, c->pix[0][0], g, 1);
+    copy_out(c, d_flow, flow_pitch, c->flow_tmp, w, h);
+}
+
+}  // extern "C"

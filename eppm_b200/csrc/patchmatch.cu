@@ -1,0 +1,218 @@
+// Stage "patchmatch": randomised NNF at the coarsest pyramid level, both directions, whole batch per launch.
+// Restates baoCudaPatchMatch (bao_pmflow_kernel.cu:1760-1826): baoGenerateRandomField (:50-109,153-165),
+// baoComputeCostField (:636-645,689-696), baoSegPropagate (:1049-1181) and baoRandomSearch (:1519-1594).
+//
+// B200 design
+//  * grid.z = pair*2 + direction: forward and backward fields of every pair of the batch advance in the same launch
+//    (the reference runs 53 dependent launches per direction per pair on a 480x270 plane, i.e. ~5 warps per SM).
+//  * RNG: the reference seeds XORWOW with 1234 and sub-sequence = 16x16-block id in both directions of every pair
+//    (:68), so the random stream is a function of the level geometry alone.  It is expanded ONCE per context into
+//    `rng_init` (initial targets) and `rng_search` (raw 16-bit draws per iteration/guess/pixel) by one thread per
+//    sub-sequence; the per-pair kernels read it coalesced instead of serialising 3072 draws on one thread per block.
+//  * propagation: all segments of a scan line live in one CTA and advance in lock-step with a CTA barrier per step,
+//    which fixes the two orderings the reference leaves to warp scheduling (segment-start read before the
+//    neighbour's last write; segment 1's first write to pixel 10 before segment 0's last) -- see DESIGN.md.
+#include <curand_kernel.h>
+
+#include "eppm_internal.h"
+
+namespace eppm {
+
+constexpr int RB = 16;  // RNG block edge: BLOCK_DIM_X/Y of the reference (bao_pmflow_kernel.cu:42-43)
+
+// One thread per 16x16 block id = per XORWOW sub-sequence.  Draw order follows d_gen_rand_field (:88-99: rows i, cols j,
+// x then y) and d_update_random_guess (:1537-1551: per guess k, rows i, cols j, x then y), one search per iteration.
+__global__ void k_rng_tables(short2* __restrict__ init, short2* __restrict__ search, int w, int h, int gx, int gy, int num_iter, int num_guess,
+                             unsigned long long seed) {
+    const int bid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bid >= gx * gy) return;
+    const int bx = bid % gx, by = bid / gx;
+    curandState st;
+    curand_init(seed, bid, 0, &st);  // :68
+    for (int i = 0; i < RB; i++)
+        for (int j = 0; j < RB; j++) {
+            const unsigned r1 = curand(&st), r2 = curand(&st);
+            const int x = bx * RB + j, y = by * RB + i;
+            if (x < w && y < h) init[(size_t)y * w + x] = make_short2((short)(r1 % (unsigned)(w + 1)), (short)(r2 % (unsigned)(h + 1)));  // :97-98
+        }
+    for (int it = 0; it < num_iter; it++)
+        for (int k = 0; k < num_guess; k++)
+            for (int i = 0; i < RB; i++)
+                for (int j = 0; j < RB; j++) {
+                    const unsigned r1 = curand(&st), r2 = curand(&st);
+                    const int x = bx * RB + j, y = by * RB + i;
+                    if (x < w && y < h) search[((size_t)(it * num_guess + k) * h + y) * w + x] = make_short2((short)r1, (short)r2);  // :1549-1550
+                }
+}
+
+void build_rng_tables(eppm_context* c) {
+    const LevelGeom& g = c->lv[c->n_levels - 1];
+    const int gx = (g.w + RB - 1) / RB, gy = (g.h + RB - 1) / RB;
+    k_rng_tables<<<(gx * gy + 63) / 64, 64, 0, c->stream>>>(c->rng_init, c->rng_search, g.w, g.h, gx, gy, c->prm.num_iter, c->prm.num_rand_guess,
+                                                          c->prm.seed);
+    EPPM_LAUNCH_COUNT(1);
+}
+
+struct PmArgs {
+    const float4* pix[2];  // packed planes of image 1 / image 2 at the PatchMatch level, logical (0,0) of pair 0
+    size_t plane;          // pixels per padded plane
+    int pw;
+    short2* nnf[2];        // per direction, [B][h][w]
+    float* cost[2];
+    int w, h;
+    int n_dirs;            // 2: grid.z = pair*2 + direction; 1: forward only (legacy single-direction entry point)
+};
+
+__device__ __forceinline__ void pm_select(const PmArgs& a, int z, const float4*& A, const float4*& B, short2*& nnf, float*& cost) {
+    const int dir = a.n_dirs == 2 ? (z & 1) : 0, b = a.n_dirs == 2 ? (z >> 1) : z;
+    A = a.pix[dir] + (size_t)b * a.plane;       // direction 1 swaps the images (…cuda.cpp:223-224)
+    B = a.pix[dir ^ 1] + (size_t)b * a.plane;
+    nnf = a.nnf[dir] + (size_t)b * a.w * a.h;
+    cost = a.cost[dir] + (size_t)b * a.w * a.h;
+}
+
+// Random field + initial cost (d_gen_rand_field + d_compute_cost_field).
+__global__ void __launch_bounds__(128) k_pm_init(PmArgs a, const short2* __restrict__ rng_init, const __grid_constant__ CostLut lut) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.w) return;
+    const float4 *A, *B; short2* nnf; float* cost;
+    pm_select(a, blockIdx.z, A, B, nnf, cost);
+    const short2 t = rng_init[(size_t)y * a.w + x];
+    nnf[(size_t)y * a.w + x] = t;
+    cost[(size_t)y * a.w + x] = patch_cost<2>(A, B, a.pw, x, y, t.x, t.y, lut);
+}
+
+// Segment propagation, the four passes of baoSegPropagate.  DIR: 0 row forward, 1 column forward, 2 row reverse,
+// 3 column reverse.  blockDim = (lines per CTA, segments per line); every thread owns one (line, segment).
+template <int DIR>
+__global__ void k_pm_propagate(PmArgs a, int seg_len, const __grid_constant__ CostLut lut) {
+    constexpr bool ROW = (DIR == 0 || DIR == 2), FWD = (DIR < 2);
+    const int line = blockIdx.x * blockDim.x + threadIdx.x;
+    const int seg = threadIdx.y;
+    const int n_line = ROW ? a.h : a.w;   // number of scan lines
+    const int len = ROW ? a.w : a.h;      // pixels along a line
+    const float4 *A, *B; short2* nnf; float* cost;
+    pm_select(a, blockIdx.z, A, B, nnf, cost);
+    const bool active = line < n_line;
+    int start, end, steps;
+    if (FWD) {
+        // :1055-1058  seg 0 starts at pixel 0 and covers one pixel more; others start one before their segment
+        start = seg == 0 ? 0 : seg * seg_len - 1;
+        end = min(len - 1, start + seg_len);
+        steps = end - start;
+    } else {
+        // :1085-1088
+        start = (seg + 1) * seg_len;
+        if (start >= len) start = len - 1;
+        end = seg * seg_len;
+        steps = start - end;
+    }
+    if (!active) steps = 0;
+    auto idx = [&](int i) -> size_t { return ROW ? (size_t)line * a.w + i : (size_t)i * a.w + line; };
+    short2 prev = make_short2(0, 0);
+    if (steps > 0) prev = nnf[idx(start)];
+    __syncthreads();  // every segment has read its start pixel before any pixel is written
+    for (int t = 1; t <= seg_len; t++) {
+        if (t <= steps) {
+            const int i = FWD ? start + t : start - t;
+            const size_t id = idx(i);
+            const float cur_best = cost[id];
+            // :1065/:1095/:1125/:1155  shift the predecessor's target one step along the scan axis, clamped
+            if (DIR == 0) prev.x = min(prev.x + 1, a.w - 1);
+            if (DIR == 1) prev.y = min(prev.y + 1, a.h - 1);
+            if (DIR == 2) prev.x = max(prev.x - 1, 0);
+            if (DIR == 3) prev.y = max(prev.y - 1, 0);
+            const int x1 = ROW ? i : line, y1 = ROW ? line : i;
+            const float cv = patch_cost<2>(A, B, a.pw, x1, y1, prev.x, prev.y, lut);
+            if (cv < cur_best) {
+                nnf[id] = prev;
+                cost[id] = cv;
+            } else {
+                prev = nnf[id];
+            }
+        }
+        __syncthreads();  // lock-step: step t of every segment completes before step t+1 starts
+    }
+}
+
+// Random search (d_update_random_guess): num_guess candidates drawn in windows of radius 30,15,7,3,1,1 around the
+// ENTRY best target, evaluated in order with strict '<'.
+__global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __restrict__ rng, int num_guess, int search_range, int radius_min,
+                                                   const __grid_constant__ CostLut lut) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.w) return;
+    const float4 *A, *B; short2* nnf; float* cost;
+    pm_select(a, blockIdx.z, A, B, nnf, cost);
+    const size_t id = (size_t)y * a.w + x;
+    short2 best = nnf[id];
+    float best_cost = cost[id];
+    const short2 entry = best;
+    int mag = search_range;
+    for (int k = 0; k < num_guess; k++) {
+        const short2 rr = rng[(size_t)k * a.w * a.h + id];
+        // :1557-1563: short sign-extended into the unsigned draw, window clipped to [0,w] x [0,h], unsigned modulo
+        const unsigned r1 = (unsigned)(int)rr.x, r2 = (unsigned)(int)rr.y;
+        const short xmin = (short)max(entry.x - mag, 0), xmax = (short)min(entry.x + mag + 1, a.w + 1);
+        const short ymin = (short)max(entry.y - mag, 0), ymax = (short)min(entry.y + mag + 1, a.h + 1);
+        const short gx = (short)(xmin + r1 % (unsigned)(xmax - xmin));
+        const short gy = (short)(ymin + r2 % (unsigned)(ymax - ymin));
+        if (mag / 2 >= radius_min) mag /= 2;
+        const float cv = patch_cost<2>(A, B, a.pw, x, y, gx, gy, lut);
+        if (cv < best_cost) {
+            best = make_short2(gx, gy);
+            best_cost = cv;
+        }
+    }
+    nnf[id] = best;
+    cost[id] = best_cost;
+}
+
+template <int DIR>
+static void launch_propagate(eppm_context* c, const PmArgs& a, int n) {
+    const bool row = (DIR == 0 || DIR == 2);
+    const int len = row ? a.w : a.h, n_line = row ? a.h : a.w;
+    const int n_seg = (len + c->prm.prop_seg_length - 1) / c->prm.prop_seg_length;
+    int lines = 256 / n_seg;
+    if (lines < 1) lines = 1;
+    if (lines > 32) lines = 32;
+    dim3 blk(lines, n_seg), grd((n_line + lines - 1) / lines, 1, a.n_dirs * n);
+    k_pm_propagate<DIR><<<grd, blk, 0, c->stream>>>(a, c->prm.prop_seg_length, c->cost_lut);
+    EPPM_LAUNCH_COUNT(1);
+}
+
+void run_patchmatch(eppm_context* c) { run_patchmatch_dirs(c, 2); }
+
+void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps) {
+    const int L = c->n_levels - 1, n = c->n_cur;
+    const LevelGeom& g = c->lv[L];
+    PmArgs a;
+    a.pix[0] = c->pix[0][L] + (size_t)PAD * g.pw + PAD;
+    a.pix[1] = c->pix[1][L] + (size_t)PAD * g.pw + PAD;
+    a.plane = g.plane;
+    a.pw = g.pw;
+    a.nnf[0] = c->nnf[0]; a.nnf[1] = c->nnf[1];
+    a.cost[0] = c->cost[0]; a.cost[1] = c->cost[1];
+    a.w = g.w; a.h = g.h;
+    a.n_dirs = n_dirs;
+    dim3 blk(128), grd((g.w + 127) / 128, g.h, n_dirs * n);
+    int step = 0;
+    if (step++ >= n_steps) return;
+    k_pm_init<<<grd, blk, 0, c->stream>>>(a, c->rng_init, c->cost_lut);
+    EPPM_LAUNCH_COUNT(1);
+    for (int it = 0; it < c->prm.num_iter; it++) {
+        if (step++ >= n_steps) return;
+        launch_propagate<0>(c, a, n);
+        if (step++ >= n_steps) return;
+        launch_propagate<1>(c, a, n);
+        if (step++ >= n_steps) return;
+        launch_propagate<2>(c, a, n);
+        if (step++ >= n_steps) return;
+        launch_propagate<3>(c, a, n);
+        if (step++ >= n_steps) return;
+        k_pm_search<<<grd, blk, 0, c->stream>>>(a, c->rng_search + (size_t)it * c->prm.num_rand_guess * g.w * g.h, c->prm.num_rand_guess,
+                                               c->prm.search_range, c->prm.search_radius_min, c->cost_lut);
+        EPPM_LAUNCH_COUNT(1);
+    }
+}
+
+}  // namespace eppm

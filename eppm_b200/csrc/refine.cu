@@ -1,0 +1,290 @@
+// Stage "c2f": per finer level  x2 bilinear upsample (x2.0)  ->  3x3-candidate x 4-affine-model plane-fitting refine
+// ->  21x21 joint-bilateral flow smoothing; one more smoothing at level 0.
+// Restates baoCudaBLF_C2F (bao_pmflow_refine_kernel.cu:1076-1087), _d_bao_bilinear_resize<float2> and
+// _d_bao_multiply_scalar (basic/bao_basic_cuda.cuh:511-537,135-149), d_bilateral_refine_flow_planefitting and
+// _d_compute_patch_dist_planefitting (bao_pmflow_kernel.cu:2005-2041,319-513), d_flow_bilateral_filtering
+// (bao_pmflow_refine_kernel.cu:752-826) and the level loop of compute_flow (…cuda.cpp:275-289).
+// The weighted-median call inside that loop (…cuda.cpp:281) filters a buffer nothing reads and is not executed.
+//
+// B200 design
+//  * upsample, x2 scale and refine are ONE kernel: a refine thread only needs the upsampled flow of its own pixel.
+//  * refine: one thread per (pixel, candidate column m); its 3 candidates x 4 models accumulate side by side while the
+//    image-1 side of every sample (colour, census, range distance d1, spatial weight) is computed once and reused by
+//    all 12 (candidate, model) pairs.  Each pair still adds its 100 samples in the reference's order, so its cost is
+//    the bit pattern the reference gets.  The three column results of a pixel meet through warp shuffles and keep
+//    the reference's m-outer / n-inner first-minimum order.
+//  * smoothing reads a snapshot and writes a second buffer (the reference filters in place).
+#include <float.h>
+
+#include "eppm_internal.h"
+
+namespace eppm {
+
+// plane-fitting coefficient sets (bao_pmflow_kernel.cu:319-332); model 0 is the identity
+__constant__ float c_pf[3][4] = {
+    {0.177f, -0.011f, -0.003f, 0.301f},   // COEF_FL_{U_X,U_Y,V_X,V_Y}
+    {0.125f, -0.357f, 0.009f, 0.308f},    // COEF_LEFT_*
+    {0.205f, 0.370f, 0.011f, 0.296f},     // COEF_RIGHT_*
+};
+
+// _d_bao_bilinear_resize<float2> at ratio 2 followed by x2.0 (basic/bao_basic_cuda.cuh:511-537, 135-149)
+__device__ __forceinline__ float2 upsample2(const float2* __restrict__ src, int ws, int hs, int x, int y) {
+    const float div_scale = 0.5f;  // 1.f/ratio with ratio = PYR_RATIO_UP = 2
+    const float fx = __fmaf_rn((float)(x + 1), div_scale, -1.f), fy = __fmaf_rn((float)(y + 1), div_scale, -1.f);
+    const int xx = (int)fx, yy = (int)fy;
+    const float dx = fmaxf(fminf(__fsub_rn(fx, (float)xx), 1.f), 0.f), dy = fmaxf(fminf(__fsub_rn(fy, (float)yy), 1.f), 0.f);
+    float rx = 0.f, ry = 0.f;
+#pragma unroll
+    for (int m = 0; m <= 1; m++)
+#pragma unroll
+        for (int n = 0; n <= 1; n++) {
+            const int u = max(0, min(ws - 1, xx + m)), v = max(0, min(hs - 1, yy + n));
+            const float s = __fmul_rn(fabsf(__fsub_rn((float)(1 - m), dx)), fabsf(__fsub_rn((float)(1 - n), dy)));
+            const float2 p = src[(size_t)v * ws + u];
+            rx = __fmaf_rn(s, p.x, rx);
+            ry = __fmaf_rn(s, p.y, ry);
+        }
+    return make_float2(__fmul_rn(rx, 2.0f), __fmul_rn(ry, 2.0f));
+}
+
+struct RefineArgs {
+    const float4* pix1;   // logical (0,0) of pair 0, image 1 / image 2 at this level
+    const float4* pix2;
+    size_t plane;
+    int pw, w, h;
+    const float2* coarse; // [B][hs][ws]
+    int ws, hs;
+    float2* flow;         // [B][h][w] out
+    int upsample;         // 1: coarse is the next-coarser level (x2 upsample fused); 0: coarse is already at this level
+};
+
+// CTA = 3 warps x 32 pixels: warp m evaluates candidate column m of 32 consecutive pixels of one row (coalesced plane
+// reads); the three column minima of a pixel meet in shared memory.
+constexpr int RF_PIX = 32;
+__device__ __forceinline__ float min_ref(float a, float b) { return a < b ? a : b; }  // the reference's __min macro
+__global__ void __launch_bounds__(RF_PIX * 3) k_c2f_refine(RefineArgs a, const __grid_constant__ CostLut lut) {
+    __shared__ float s_best[3][RF_PIX];
+    __shared__ int s_bn[3][RF_PIX];
+    const int m = threadIdx.x >> 5, pl = threadIdx.x & 31;
+    const int x = blockIdx.x * RF_PIX + pl, y = blockIdx.y;
+    const bool in = x < a.w;
+    const int b = blockIdx.z;
+    const float4* I1 = a.pix1 + (size_t)b * a.plane;
+    const float4* I2 = a.pix2 + (size_t)b * a.plane;
+    float2 fl = make_float2(0.f, 0.f);
+    if (in) fl = a.upsample ? upsample2(a.coarse + (size_t)b * a.ws * a.hs, a.ws, a.hs, x, y) : a.coarse[(size_t)b * a.w * a.h + (size_t)y * a.w + x];
+    // :2011 unknown flow -> 0 and done
+    const bool unknown = fl.x > EPPM_UNKNOWN_FLOW_THRESH || fl.y > EPPM_UNKNOWN_FLOW_THRESH;
+    // :2014-2019 candidates: short(flow)+pos, -1/+0/+1 (16-bit arithmetic as in the reference)
+    const short cxc = (short)((short)(int)fl.x + x), cyc = (short)((short)(int)fl.y + y);
+    const short cx = (short)(cxc + (m - 1));
+    float cost[3] = {FLT_MAX, FLT_MAX, FLT_MAX};  // best-of-4-models cost of candidate rows n = 0..2
+    bool valid[3];
+#pragma unroll
+    for (int n = 0; n < 3; n++) {
+        const short cy = (short)(cyc + (n - 1));
+        valid[n] = in && !unknown && !(cx < 0 || cy < 0 || cx >= a.w || cy >= a.h);  // :2029
+    }
+    if (valid[0] || valid[1] || valid[2]) {
+        // accumulators: [n][model]
+        float cs[3][4], ws[3][4];
+#pragma unroll
+        for (int n = 0; n < 3; n++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) cs[n][q] = ws[n][q] = 0.f;
+        const float4* a0 = I1 + (size_t)y * a.pw + x;
+        const float4 c1 = ldpix(a0);
+        float4 c2[3];
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+            const int cy = max(-PAD, min(a.h - 1 + PAD, (int)cyc + n - 1));  // invalid rows are never used; clamp keeps the load in-plane
+            const int cxs = max(-PAD, min(a.w - 1 + PAD, (int)cx));
+            c2[n] = ldpix(I2 + (size_t)cy * a.pw + cxs);
+        }
+        const float uu = (float)((int)cx - x);  // :350 float uu = x2 - x1
+#pragma unroll 1
+        for (int i = -PATCH_R; i <= PATCH_R; i += 2) {
+            const float fi = (float)i;
+            const int ai = i < 0 ? -i : i;
+#pragma unroll 2
+            for (int j = -PATCH_R; j <= PATCH_R; j += 2) {
+                const float fj = (float)j;
+                const float4 p1 = ldpix(a0 + i * a.pw + j);
+                const float d1 = max3abs_diff(c1, p1);
+                const float gg = lut.gg[ai][j < 0 ? -j : j];
+                // x coordinates of the 4 models: cx2 = fma(i, C_uy, fma(j, C_ux, float(x1+j) + uu))   (:402, :440, :478 as contracted)
+                const float bx = __fadd_rn(uu, (float)(x + j));
+                int sx[4];
+                sx[0] = __float2int_rd(bx);
+#pragma unroll
+                for (int q = 0; q < 3; q++) sx[q + 1] = __float2int_rd(__fmaf_rn(fi, c_pf[q][1], __fmaf_rn(fj, c_pf[q][0], bx)));
+#pragma unroll
+                for (int n = 0; n < 3; n++) {
+                    if (!valid[n]) continue;
+                    const int cy = (int)cyc + n - 1;
+                    const float vv = (float)(cy - y);
+                    const float by = __fadd_rn((float)(y + i), vv);
+                    int sy[4];
+                    sy[0] = __float2int_rd(by);
+#pragma unroll
+                    for (int q = 0; q < 3; q++) sy[q + 1] = __float2int_rd(__fmaf_rn(fi, c_pf[q][3], __fmaf_rn(fj, c_pf[q][2], by)));
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const float4 p2 = ldpix(I2 + (size_t)sy[q] * a.pw + sx[q]);
+                        sample_term(p1, p2, c2[n], d1, gg, lut, cs[n][q], ws[n][q]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+            if (!valid[n]) continue;
+            const float k1 = __fdiv_rn(cs[n][0], ws[n][0]), k2 = __fdiv_rn(cs[n][1], ws[n][1]);
+            const float k3 = __fdiv_rn(cs[n][2], ws[n][2]), k4 = __fdiv_rn(cs[n][3], ws[n][3]);
+            cost[n] = min_ref(k1, min_ref(k2, min_ref(k3, k4)));  // :512 __min(cost1,__min(cost2,__min(cost3,cost4)))
+        }
+    }
+    // arg-min in the reference's order: m outer, n inner, strict '<' against 999999 (:2024,:2031)
+    float best = 999999.f;
+    int best_n = -1;
+#pragma unroll
+    for (int n = 0; n < 3; n++)
+        if (valid[n] && cost[n] < best) { best = cost[n]; best_n = n; }
+    s_best[m][pl] = best;
+    s_bn[m][pl] = best_n;
+    __syncthreads();
+    float bcost = 999999.f;
+    int bm = -1, bn = -1;
+#pragma unroll
+    for (int mm = 0; mm < 3; mm++) {
+        const float oc = s_best[mm][pl];
+        const int on = s_bn[mm][pl];
+        if (on >= 0 && oc < bcost) { bcost = oc; bm = mm; bn = on; }
+    }
+    if (in && m == 0) {
+        float2 out;
+        if (unknown) out = make_float2(0.f, 0.f);
+        else {
+            short bx = cxc, by = cyc;  // :2020-2022 default = centre candidate
+            if (bm >= 0) { bx = (short)(cxc + (bm - 1)); by = (short)(cyc + (bn - 1)); }
+            out = make_float2((float)(bx - x), (float)(by - y));  // :2038-2039
+        }
+        a.flow[(size_t)b * a.w * a.h + (size_t)y * a.w + x] = out;
+    }
+}
+
+// d_flow_bilateral_filtering (bao_pmflow_refine_kernel.cu:764-799): (2R+1)^2 joint bilateral, R = 2*sig_s, skipping unknown
+// flow, snapshot semantics.  Tile of flow + image-1 colours with R halo in shared memory.
+struct SmoothArgs {
+    const float2* src;
+    float2* dst;
+    const float4* pix;  // logical (0,0), image 1
+    size_t plane;
+    int pw, w, h;
+    int R;
+    float neg_sig_r2;
+};
+
+constexpr int SM_T = 16;
+__global__ void __launch_bounds__(SM_T* SM_T) k_flow_smooth(SmoothArgs a, const __grid_constant__ SmoothLut lut) {
+    extern __shared__ float4 smem[];  // [TW*TW] colours, then float2 [TW*TW] flows
+    const int R = a.R, TW = SM_T + 2 * R;
+    float4* s_pix = smem;
+    float2* s_flow = reinterpret_cast<float2*>(smem + TW * TW);
+    const int b = blockIdx.z;
+    const float2* f = a.src + (size_t)b * a.w * a.h;
+    const float4* img = a.pix + (size_t)b * a.plane;
+    const int x0 = blockIdx.x * SM_T - R, y0 = blockIdx.y * SM_T - R;
+    for (int i = threadIdx.y * SM_T + threadIdx.x; i < TW * TW; i += SM_T * SM_T) {
+        const int ty = i / TW, tx = i % TW;
+        const int cx = x0 + tx, cy = y0 + ty;
+        float2 fl = make_float2(EPPM_UNKNOWN_FLOW, EPPM_UNKNOWN_FLOW);  // outside the image: skipped like unknown flow (:776,:778)
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cx >= 0 && cy >= 0 && cx < a.w && cy < a.h) {
+            fl = f[(size_t)cy * a.w + cx];
+            p = ldpix(img + (size_t)cy * a.pw + cx);
+        }
+        s_flow[i] = fl;
+        s_pix[i] = p;
+    }
+    __syncthreads();
+    const int x = blockIdx.x * SM_T + threadIdx.x, y = blockIdx.y * SM_T + threadIdx.y;
+    if (x >= a.w || y >= a.h) return;
+    const float4 c = s_pix[(threadIdx.y + R) * TW + threadIdx.x + R];
+    float nx = 0.f, ny = 0.f, wsum = 0.f;
+    for (int dy = -R; dy <= R; dy++) {
+        const float gy = lut.g[abs(dy)];
+        const int rowb = (threadIdx.y + R + dy) * TW + threadIdx.x + R;
+        for (int dx = -R; dx <= R; dx++) {
+            const float2 fl = s_flow[rowb + dx];
+            if (fl.x > EPPM_UNKNOWN_FLOW_THRESH || fl.y > EPPM_UNKNOWN_FLOW_THRESH) continue;
+            const float4 p = s_pix[rowb + dx];
+            const float dr = max3abs_diff(p, c);                                              // :757
+            const float coef_r = __expf(__fdiv_rn(__fmul_rn(dr, dr), a.neg_sig_r2));          // :758
+            const float wgt = __fmul_rn(coef_r, __fmul_rn(lut.g[abs(dx)], gy));               // :759-760
+            nx = __fmaf_rn(wgt, fl.x, nx);                                                    // :782-783
+            ny = __fmaf_rn(wgt, fl.y, ny);
+            wsum = __fadd_rn(wsum, wgt);
+        }
+    }
+    float2 out = s_flow[(threadIdx.y + R) * TW + threadIdx.x + R];
+    if (wsum != 0.f) out = make_float2(__fdiv_rn(nx, wsum), __fdiv_rn(ny, wsum));  // :790-796 (untouched otherwise)
+    a.dst[(size_t)b * a.w * a.h + (size_t)y * a.w + x] = out;
+}
+
+void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const LevelGeom& g, const float2* coarse, int ws, int hs, int upsample,
+               float2* out, int n) {
+    RefineArgs a;
+    a.pix1 = pix1 + (size_t)PAD * g.pw + PAD;
+    a.pix2 = pix2 + (size_t)PAD * g.pw + PAD;
+    a.plane = g.plane; a.pw = g.pw; a.w = g.w; a.h = g.h;
+    a.coarse = coarse; a.ws = ws; a.hs = hs;
+    a.flow = out;
+    a.upsample = upsample;
+    dim3 blk(RF_PIX * 3), grd((g.w + RF_PIX - 1) / RF_PIX, g.h, n);
+    k_c2f_refine<<<grd, blk, 0, c->stream>>>(a, c->cost_lut);
+    EPPM_LAUNCH_COUNT(1);
+}
+
+void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pix1, const LevelGeom& g, int n) {
+    SmoothArgs a;
+    a.src = src; a.dst = dst;
+    a.pix = pix1 + (size_t)PAD * g.pw + PAD;
+    a.plane = g.plane; a.pw = g.pw; a.w = g.w; a.h = g.h;
+    a.R = 2 * c->prm.blf_sig_s;
+    a.neg_sig_r2 = -(c->prm.blf_sig_r * c->prm.blf_sig_r);
+    const int TW = SM_T + 2 * a.R;
+    const size_t smem = (size_t)TW * TW * (sizeof(float4) + sizeof(float2));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_flow_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    dim3 blk(SM_T, SM_T), grd((g.w + SM_T - 1) / SM_T, (g.h + SM_T - 1) / SM_T, n);
+    k_flow_smooth<<<grd, blk, smem, c->stream>>>(a, c->smooth_lut);
+    EPPM_LAUNCH_COUNT(1);
+}
+
+static void launch_smooth(eppm_context* c, const float2* src, float2* dst, int level, int n) {
+    op_smooth(c, src, dst, c->pix[0][level], c->lv[level], n);
+}
+
+void run_c2f(eppm_context* c, float* d_flow_out) {
+    const int n = c->n_cur;
+    for (int level = c->n_levels - 2; level >= 0; level--) {
+        const LevelGeom& g = c->lv[level];
+        const LevelGeom& gs = c->lv[level + 1];
+        op_refine(c, c->pix[0][level], c->pix[1][level], g, c->flow[level + 1], gs.w, gs.h, 1, c->flow_tmp, n);
+        launch_smooth(c, c->flow_tmp, c->flow[level], level, n);
+    }
+    // final smoothing at level 0 (…cuda.cpp:289); with a single level the loop above did not run
+    float2* out = reinterpret_cast<float2*>(d_flow_out);
+    if (c->n_levels >= 2) {
+        launch_smooth(c, c->flow[0], out ? out : c->flow_tmp, 0, n);
+        if (!out) cudaMemcpyAsync(c->flow[0], c->flow_tmp, (size_t)n * c->lv[0].w * c->lv[0].h * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream);
+    } else {
+        launch_smooth(c, c->flow[0], out ? out : c->flow_tmp, 0, n);
+    }
+}
+
+}  // namespace eppm

@@ -1,0 +1,133 @@
+/* eppm.h — C ABI of libeppm_b200.so: the B200-native (sm_100a) implementation of EPPM's
+ * dense-correspondence hot path (census -> pyramid -> coarse-level PatchMatch -> consistency pass ->
+ * coarse-to-fine plane-fitting refine + joint-bilateral smoothing).
+ *
+ * Two layers are exported, both `extern "C"`, plain pointers and sizes only:
+ *
+ *  (1) the batched, stream-ordered context API `eppm_*` declared below — what a new caller binds
+ *      (ctypes / cgo / JNI stubs are shown in INTEGRATION.md);
+ *  (2) the reference's own stage functions `baoCuda*` with the reference's signatures and buffer
+ *      layouts (declared in include/eppm_legacy_abi.h), so that the reference's host class
+ *      (bao_flow_patchmatch_multiscale_cuda.cpp:40-62 of linchaobao/EPPM) links against this
+ *      library unchanged.
+ *
+ * There is no CPU fallback: every entry point fails with EPPM_ERR_CUDA when no sm_100 device is present.
+ * All citations `file:line` refer to the upstream reference linchaobao/EPPM.
+ */
+#ifndef EPPM_H_
+#define EPPM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPPM_OK 0
+#define EPPM_ERR_ARG (-1)     /* bad argument (null pointer, size out of range, batch > max_batch) */
+#define EPPM_ERR_CUDA (-2)    /* CUDA runtime error; text via eppm_last_error() */
+#define EPPM_ERR_STATE (-3)   /* call sequence error (e.g. compute before set) */
+
+#define EPPM_RNG_XORWOW 0 /* the reference's stream: curand XORWOW, seed 1234, one subsequence per 16x16
+                             block (bao_pmflow_kernel.cu:50-109,1519-1586) -> bit-exact NNF */
+#define EPPM_RNG_PHILOX 1 /* counter-based Philox4x32-10 keyed by (seed, iteration, guess, pixel) */
+
+/* Algorithm parameters. The reference fixes all of them as macros (defs.h:31-76, and
+ * PROP_SEG_LENGTH bao_pmflow_kernel.cu:979, DIFF_THRESH/STAT_SIM_THRESH/POSTPROC_BLF_SIG_R
+ * bao_pmflow_refine_kernel.cu:51,147,752); eppm_default_params() returns exactly those values. */
+typedef struct eppm_params {
+    int pyr_levels;          /* PYR_MAX_DEPTH 3 */
+    int num_iter;            /* NUM_ITER 10 */
+    int patch_r;             /* PATCH_R 9        (kernels are specialised for 9) */
+    int patch_stride;        /* 2  (pixel skipping, bao_pmflow_kernel.cu:269,272); 1..3 supported */
+    int search_range;        /* SEARCH_RANGE 30 */
+    int search_radius_min;   /* SEARCH_RADIUS_MIN 1 */
+    int num_rand_guess;      /* NUM_RAND_GUESS 6 */
+    int prop_seg_length;     /* PROP_SEG_LENGTH 10 */
+    float lambda_ad;         /* LAMBDA_AD 0.1 */
+    float lambda_census;     /* LAMBDA_CENSUS 0.3 */
+    float pm_sig_r;          /* PM_SIG_R 0.1 */
+    int stat_radius;         /* STAT_RADIUS 6 */
+    int stat_sim_thresh;     /* STAT_SIM_THRESH 2 */
+    int wmf_radius;          /* WMF_RADIUS 4 */
+    float wmf_sig_r;         /* WMF_SIG_R 0.02 */
+    int wmf_iters;           /* 20 (bao_flow_patchmatch_multiscale_cuda.cpp:239) */
+    int blf_sig_s;           /* POSTPROC_BLF_SIG_S 5 (radius = 2*sig_s) */
+    float blf_sig_r;         /* POSTPROC_BLF_SIG_R 0.02 */
+    int rng_mode;            /* EPPM_RNG_XORWOW */
+    unsigned long long seed; /* 1234 (bao_pmflow_kernel.cu:68) */
+    int reserved[8];
+} eppm_params;
+
+typedef struct eppm_context eppm_context; /* opaque; one per (device, h, w, params) */
+
+void eppm_default_params(eppm_params* p);
+
+/* Create a context on `device` for frames of h x w (RGB u8) and up to `max_batch` pairs per call.
+ * Replaces bao_flow_patchmatch_multiscale_cuda::init(h,w) (…cuda.cpp:112-157): all device memory
+ * (one arena), the RNG tables and LUTs are set up here, nothing is allocated per pair. */
+int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, const eppm_params* params);
+void eppm_destroy(eppm_context* ctx);
+const char* eppm_last_error(void);
+const char* eppm_version(void);
+
+/* Level geometry, identical to bao_pyr_init_dim (basic/bao_basic.h:196-211). */
+int eppm_num_levels(const eppm_context* ctx);
+int eppm_level_dims(const eppm_context* ctx, int level, int* h, int* w);
+
+/* One batch, HOST buffers (the call a user of the reference's class makes, batched):
+ *   img1,img2 : [n][h][w][3] u8 interleaved RGB (bao_alloc layout, main.cpp:42-57)
+ *   flow      : [n][h][w][2] f32 interleaved (u,v) — what compute_flow returns as u[][] / v[][]
+ * H2D, all stages, D2H; returns after the result is in `flow`.
+ * Replaces set_data + compute_flow (…cuda.cpp:159-168,217-306). */
+int eppm_compute_batch_host(eppm_context* ctx, const uint8_t* img1, const uint8_t* img2, int n, float* flow);
+
+/* Same with DEVICE-resident inputs/outputs (same layouts), stream-ordered on the context's stream;
+ * returns without synchronising. */
+int eppm_compute_batch_device(eppm_context* ctx, const uint8_t* d_img1, const uint8_t* d_img2, int n, float* d_flow);
+int eppm_synchronize(eppm_context* ctx);
+void* eppm_stream(eppm_context* ctx); /* cudaStream_t */
+
+/* Staged execution for stage-level parity tests and profiling (device-resident):
+ *   eppm_stage_prepare     : RGB -> pre-blur, pyramid, census, packed planes      (…refine_kernel.cu:1060-1071)
+ *   eppm_stage_patchmatch  : both directions at the coarsest level                (…pmflow_kernel.cu:1760-1826)
+ *   eppm_stage_consistency : LR check, outlier removal, WMF, hole filling, NNF->flow (…cuda.cpp:233-258)
+ *   eppm_stage_c2f         : for each finer level: upsample x2, plane-fitting refine, smoothing; final smoothing
+ * Call in this order after eppm_stage_prepare. */
+int eppm_stage_prepare(eppm_context* ctx, const uint8_t* d_img1, const uint8_t* d_img2, int n);
+int eppm_stage_patchmatch(eppm_context* ctx);
+int eppm_stage_consistency(eppm_context* ctx);
+int eppm_stage_c2f(eppm_context* ctx, float* d_flow);
+
+/* Read-outs of intermediate planes of pair `pair` (dense host copies; synchronises):
+ *   EPPM_PLANE_RGBA1/2   uchar4 [h_l][w_l]      pyramid level image
+ *   EPPM_PLANE_CENSUS1/2 u8     [h_l][w_l]
+ *   EPPM_PLANE_NNF_FWD/BWD short2 [h_c][w_c]    absolute targets at the coarsest level
+ *   EPPM_PLANE_COST_FWD/BWD f32 [h_c][w_c]
+ *   EPPM_PLANE_FLOW      float2 [h_l][w_l]
+ * Returns bytes written or a negative error. */
+enum {
+    EPPM_PLANE_RGBA1 = 0, EPPM_PLANE_RGBA2 = 1, EPPM_PLANE_CENSUS1 = 2, EPPM_PLANE_CENSUS2 = 3,
+    EPPM_PLANE_NNF_FWD = 4, EPPM_PLANE_NNF_BWD = 5, EPPM_PLANE_COST_FWD = 6, EPPM_PLANE_COST_BWD = 7,
+    EPPM_PLANE_FLOW = 8
+};
+long eppm_read_plane(eppm_context* ctx, int which, int level, int pair, void* host_out);
+
+/* Test hooks: overwrite an NNF / COST / FLOW plane of pair `pair` from a dense host array (same shapes as
+ * eppm_read_plane), and run only the first `n_steps` launch groups of the PatchMatch stage
+ * (1 = random field + initial cost, then per iteration 4 propagation passes and 1 random search). */
+long eppm_write_plane(eppm_context* ctx, int which, int level, int pair, const void* host_in);
+int eppm_stage_patchmatch_partial(eppm_context* ctx, int n_steps);
+
+/* Number of kernel launches issued by this library since the counter was last reset (bench.py's gpu_launches). */
+unsigned long long eppm_launch_count(int reset);
+
+/* Per-stage device time of the last eppm_compute_batch_* call in ms (prepare, patchmatch, consistency, c2f, total);
+ * valid only when the context was created with EPPM_PROFILE=1 in the environment. */
+int eppm_last_stage_ms(eppm_context* ctx, float out[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPPM_H_ */

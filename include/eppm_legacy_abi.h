@@ -1,0 +1,54 @@
+/* eppm_legacy_abi.h — the reference's own stage functions, re-exported by libeppm_b200.so with the reference's
+ * signatures and buffer layouts, so that linchaobao/EPPM's host class (bao_flow_patchmatch_multiscale_cuda.cpp)
+ * links against this library unchanged.  Declarations follow bao_flow_patchmatch_multiscale_cuda.cpp:40-62.
+ *
+ * All pointers are DEVICE pointers; pyramids are host arrays of device pointers (basic/bao_basic_cuda.h:209-229);
+ * pitches are in bytes; images are uchar4 (alpha ignored) and census planes u8, both possibly pitched;
+ * NNF = short2 absolute target (x,y), cost = float, flow = float2.  Every function returns void like the reference:
+ * CUDA errors are printed to stderr (helper_cuda.h:682-712 behaviour) and can be read with eppm_last_error().
+ * The functions synchronise with the legacy default stream on entry and are complete on return.
+ */
+#ifndef EPPM_LEGACY_ABI_H_
+#define EPPM_LEGACY_ABI_H_
+#include <stddef.h>
+#include <cuda_runtime.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* bao_pmflow_refine_kernel.cu:1060-1071 */
+void baoCudaPatchMatchMultiscalePrepare(uchar4** pImgPyr1, uchar4** pImgPyr2, unsigned char** pCensusPyr1, unsigned char** pCensusPyr2,
+                                        uchar4** pTempPyr1, uchar4** pTempPyr2, int* arrH, int* arrW, size_t* arrPitchUchar4,
+                                        size_t* arrPitchUchar1, int nLevels, uchar4* d_img1, uchar4* d_img2, int h, int w);
+/* bao_pmflow_census_kernel.cu:93-112 */
+void baoCudaCensusTransform(unsigned char* d_census1, unsigned char* d_census2, uchar4* d_img1, uchar4* d_img2, int w, int h, size_t img_pitch,
+                            size_t census_pitch);
+/* bao_pmflow_kernel.cu:1760-1826 */
+void baoCudaPatchMatch(short2* d_disp_vec, float* d_cost, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1, unsigned char* d_census2,
+                       int w, int h, size_t img_pitch, size_t cost_pitch, size_t disp_pitch, size_t census_pitch);
+/* bao_pmflow_refine_kernel.cu:78-92 */
+void baoCudaLeftRightCheck(short2* d_disp_vec, float* d_cost, short2* d_disp_vec2, float* d_cost2, int w, int h, size_t cost_pitch,
+                           size_t disp_pitch);
+/* :185-193 */
+void baoCudaOutlierRemoval(short2* d_disp_vec, float* d_cost, int w, int h, size_t cost_pitch, size_t disp_pitch);
+/* :261-286 */
+void baoCudaWeightedMedianFilter(short2* d_disp_vec, float* d_cost, uchar4* d_img, int w, int h, size_t img_pitch, size_t cost_pitch,
+                                 size_t disp_pitch, int num_iter, bool is_only_occlusion);
+/* :373-390 */
+void baoCudaFillHole(short2* d_disp_vec, float* d_cost, uchar4* d_img, int w, int h, size_t img_pitch, size_t cost_pitch, size_t disp_pitch);
+/* :724-734 */
+void baoCudaNNF2Flow(float2* d_flow, short2* d_disp_vec, int w, int h, size_t disp_pitch, size_t flow_pitch);
+/* :1076-1087 */
+void baoCudaBLF_C2F(float2** pFlowPyr, uchar4** pImgPyr1, uchar4** pImgPyr2, unsigned char** pCensusPyr1, unsigned char** pCensusPyr2,
+                    float2** pTempPyr1, float2** pTempPyr2, int* arrH, int* arrW, size_t* arrPitchUchar4, size_t* arrPitchUchar1, int nLayerIdx);
+/* bao_pmflow_kernel.cu:2042-2069 (plane-fitting refine alone, on an already upsampled dense flow plane) */
+void baoCudaBLFCostFilterRefine(float2* d_flow_vec, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1, unsigned char* d_census2, int w,
+                                int h, size_t img_pitch, size_t census_pitch);
+/* bao_pmflow_refine_kernel.cu:801-826 */
+void baoCudaFlowSmoothing(float2* d_flow, uchar4* d_img, int w, int h, size_t img_pitch, size_t flow_pitch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
