@@ -41,6 +41,7 @@ EPPM_SYMBOLS = {
     "eppm_stage_patchmatch_partial": (C.c_int, [C.c_void_p, C.c_int]),
     "eppm_launch_count": (C.c_ulonglong, [C.c_int]),
     "eppm_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 5)]),
+    "eppm_last_kernel_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
 }
 
 # the reference's stage functions re-exported with the reference's signatures (include/eppm_legacy_abi.h)

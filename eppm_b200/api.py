@@ -131,6 +131,11 @@ class EppmContext:
         self._check(self.lib.eppm_last_stage_ms(self._ctx, C.byref(buf)), "eppm_last_stage_ms")
         return dict(zip(("prepare", "patchmatch", "consistency", "c2f", "total"), list(buf)))
 
+    def last_kernel_ms(self, which=0):
+        ms = C.c_float()
+        self._check(self.lib.eppm_last_kernel_ms(self._ctx, which, C.byref(ms)), "eppm_last_kernel_ms")
+        return float(ms.value)
+
     def launch_count(self, reset=False):
         return int(self.lib.eppm_launch_count(1 if reset else 0))
 

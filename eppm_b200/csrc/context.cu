@@ -84,7 +84,7 @@ unsigned long long eppm_launch_count(int reset) {
 }
 
 int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, const eppm_params* params) {
-    if (!out || h < 32 || w < 32 || h > 16384 || w > 16384 || max_batch < 1) {
+    if (!out || h < 1 || w < 1 || h > 16384 || w > 16384 || max_batch < 1) {
         set_error("eppm_create: bad argument");
         return EPPM_ERR_ARG;
     }
@@ -117,7 +117,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         g.plane = (size_t)g.pw * g.ph;
     }
     const LevelGeom& gc = c->lv[c->n_levels - 1];
-    if (gc.w < 20 || gc.h < 20 || (gc.w + p.prop_seg_length - 1) / p.prop_seg_length > 1024 || (gc.h + p.prop_seg_length - 1) / p.prop_seg_length > 1024) {
+    if (gc.w < 1 || gc.h < 1 || (gc.w + p.prop_seg_length - 1) / p.prop_seg_length > 896 || (gc.h + p.prop_seg_length - 1) / p.prop_seg_length > 896) {
         set_error("eppm_create: coarsest level out of range");
         delete c;
         return EPPM_ERR_ARG;
@@ -126,6 +126,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
     if (!cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return EPPM_ERR_CUDA; }
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev_k[i]);
 
     // ---- arena: two passes (measure, then carve) ----
     const size_t B = max_batch;
@@ -148,6 +149,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
             for (int img = 0; img < 2; img++) c->blur_tmp[img] = A.take<uchar4>(B * c->lv[1].w * c->lv[1].h);
         for (int i = 0; i < c->n_levels; i++) c->gauss[i].d_w = A.take<float>(7 * 7 + 1);
         const size_t nc = (size_t)gc.w * gc.h;
+        for (int img = 0; img < 2; img++) c->pixT[img] = A.take<float4>(B * gc.plane);
         for (int d = 0; d < 2; d++) {
             c->nnf[d] = A.take<short2>(B * nc);
             c->cost[d] = A.take<float>(B * nc);
@@ -179,6 +181,8 @@ void eppm_destroy(eppm_context* c) {
     if (c->h_pinned_out) cudaFreeHost(c->h_pinned_out);
     for (int i = 0; i < 6; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 4; i++)
+        if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -264,6 +268,13 @@ int eppm_last_stage_ms(eppm_context* c, float out[5]) {
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&out[i], c->ev[i], c->ev[i + 1]);
     cudaEventElapsedTime(&out[4], c->ev[0], c->ev[4]);
     return EPPM_OK;
+}
+
+int eppm_last_kernel_ms(eppm_context* c, int which, float* ms) {
+    if (!c || !c->profile || !ms || which < 0 || which > 1) return EPPM_ERR_STATE;
+    cudaSetDevice(c->device);
+    if (!cuda_ok(cudaEventSynchronize(c->ev_k[2 * which + 1]), "event sync")) return EPPM_ERR_CUDA;
+    return cuda_ok(cudaEventElapsedTime(ms, c->ev_k[2 * which], c->ev_k[2 * which + 1]), "event elapsed") ? EPPM_OK : EPPM_ERR_CUDA;
 }
 
 int eppm_compute_batch_host(eppm_context* c, const uint8_t* img1, const uint8_t* img2, int n, float* flow) {

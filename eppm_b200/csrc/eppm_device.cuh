@@ -48,13 +48,45 @@ __device__ __forceinline__ float div_neg_0p01(float x) {
     return __fmaf_rn(r, rem, q0);
 }
 
-// __expf as the reference calls it: ex2.approx(x*log2e) with the x*log2e < -126 half/square fix-up that
-// nvcc emits when -ftz=false.  Using the intrinsic itself keeps the instruction sequence identical.
-__device__ __forceinline__ float exp_ref(float x) { return __expf(x); }
+// ex2.approx on the MUFU pipe.  The .ftz form is the bare MUFU.EX2; results in the normal range are the same bits the
+// reference's non-ftz __expf path gets from the same instruction.
+__device__ __forceinline__ float ex2_mufu(float t) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return r;
+}
+
+// __expf(x) exactly as nvcc lowers it without -ftz (reference SASS): t = x*log2e; if (t < -126) { t *= .5; r = ex2(t); r *= r } else r = ex2(t).
+__device__ __forceinline__ float exp_ref(float x) {
+    float t = __fmul_rn(x, 1.4426950216293334961f);
+    const bool tiny = t < -126.0f;
+    if (tiny) t = __fmul_rn(t, 0.5f);
+    float r = ex2_mufu(t);
+    if (tiny) r = __fmul_rn(r, r);
+    return r;
+}
+
+// 1 - __expf(x) for x <= 0.  When x*log2e < -126 the reference's fix-up yields e < 2^-126, and 1 - e rounds to exactly
+// 1.0f whatever e is, so the fix-up (3 issue slots) can be dropped without changing a bit: MUFU.EX2 returns 0 there.
+__device__ __forceinline__ float one_minus_exp_ref(float x) {
+    return __fadd_rn(1.0f, -ex2_mufu(__fmul_rn(x, 1.4426950216293334961f)));
+}
 
 __device__ __forceinline__ float max3abs_diff(const float4& a, const float4& b) {
     float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
     return fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
+}
+
+// Census-distance LUT in shared memory, addressed by BYTE offset: the packed planes keep the census byte replicated in
+// all four bytes of .w, so popc(w1 ^ w2) = 4 * hamming distance = the byte offset of the LUT entry (no mask, no shift).
+// (A register-indexed constant-bank read would serialise on the up to 9 distinct indices of a warp.)
+__device__ __forceinline__ float census_lut(const float* s_census, const float4& p1, const float4& p2) {
+    const unsigned off = __popc(__float_as_uint(p1.w) ^ __float_as_uint(p2.w));
+    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_census) + off);
+}
+__device__ __forceinline__ void load_census_lut(float* s_census, const CostLut& lut) {
+    if (threadIdx.x + threadIdx.y * blockDim.x < 9) s_census[threadIdx.x + threadIdx.y * blockDim.x] = lut.census[threadIdx.x + threadIdx.y * blockDim.x];
+    __syncthreads();
 }
 
 // One sample of the bilateral-weighted AD+census patch cost (bao_pmflow_kernel.cu:274-296):
@@ -62,42 +94,56 @@ __device__ __forceinline__ float max3abs_diff(const float4& a, const float4& b) 
 //   weight = exp(-(d1^2 + d2^2)/sigma_r^2) * G[|j|]*G[|i|],                     dk = max|centre_k - p_k|
 // accumulated as cost_sum = fma(cost, weight, cost_sum); weight_sum += weight, in sample order.
 // d1 (image-1 side) is passed in so callers can hoist it across candidates.
-__device__ __forceinline__ void sample_term(const float4& p1, const float4& p2, const float4& c2, float d1,
-                                            float gg, const CostLut& lut, float& cost_sum, float& weight_sum) {
-    float c = max3abs_diff(p1, p2);
-    float e = exp_ref(div_neg_0p01(__fmul_rn(c, c)));
-    unsigned cx = (__float_as_uint(p1.w) ^ __float_as_uint(p2.w)) & 0xffu;
-    float cost = __fadd_rn(__fadd_rn(1.0f, -e), lut.census[__popc(cx)]);
-    float d2 = max3abs_diff(c2, p2);
-    float arg = __fmaf_rn(d1, d1, __fmul_rn(d2, d2));
-    float w = __fmul_rn(exp_ref(div_neg_0p01(arg)), gg);
+__device__ __forceinline__ void sample_term(const float4& p1, const float4& p2, const float4& c2, float d1, float gg, const float* s_census,
+                                            float& cost_sum, float& weight_sum) {
+    const float c = max3abs_diff(p1, p2);
+    const float cost = __fadd_rn(one_minus_exp_ref(div_neg_0p01(__fmul_rn(c, c))), census_lut(s_census, p1, p2));
+    const float d2 = max3abs_diff(c2, p2);
+    const float arg = __fmaf_rn(d1, d1, __fmul_rn(d2, d2));
+    const float w = __fmul_rn(exp_ref(div_neg_0p01(arg)), gg);
     cost_sum = __fmaf_rn(cost, w, cost_sum);
     weight_sum = __fadd_rn(weight_sum, w);
 }
 
 // _d_compute_patch_dist (bao_pmflow_kernel.cu:255-301): 100 samples at stride 2 over a 19x19 patch.
-// A/B point at logical (0,0) of the source / target packed planes (same padded pitch pw).
+// A/B point at the PADDED origin of the source / target packed planes (same pitch).  TRANSPOSED = false: row-major planes
+// (pixel (x,y) at y*pitch + x); true: column-major copies (pixel (x,y) at x*pitch + y) used by the row propagation
+// passes so that lanes walking adjacent ROWS read adjacent addresses.  Sample order is i (rows) outer, j inner in both.
 // Texture clamp addressing is realised by the replicated PAD border: |x2+j| never leaves it because
 // targets lie in [0,w]x[0,h] and |j| <= 9 < PAD.
-template <int STRIDE>
-__device__ __forceinline__ float patch_cost(const float4* __restrict__ A, const float4* __restrict__ B, int pw,
-                                            int x1, int y1, int x2, int y2, const CostLut& lut) {
-    const float4* a0 = A + (size_t)y1 * pw + x1;
-    const float4* b0 = B + (size_t)y2 * pw + x2;
-    const float4 c1 = ldpix(a0);
-    const float4 c2 = ldpix(b0);
+template <int STRIDE, bool TRANSPOSED>
+__device__ __forceinline__ float patch_cost(const float4* __restrict__ A, const float4* __restrict__ B, int pitch, int x1, int y1, int x2, int y2,
+                                            const CostLut& lut, const float* s_census) {
+    // A/B: PADDED origin of the planes (pixel (-PAD,-PAD)); all offsets below are non-negative 32-bit element indices, so every
+    // load address is one IMAD.WIDE.U32 away from a register-resident base pointer.
+    const unsigned sj = TRANSPOSED ? pitch : 1, si = TRANSPOSED ? 1 : pitch;
+    const unsigned oa = (unsigned)(x1 + PAD) * sj + (unsigned)(y1 + PAD) * si;
+    const unsigned ob = (unsigned)(x2 + PAD) * sj + (unsigned)(y2 + PAD) * si;
+    const float4 c1 = ldpix(A + oa);
+    const float4 c2 = ldpix(B + ob);
     float cost_sum = 0.f, weight_sum = 0.f;
 #pragma unroll 1
     for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
-        const float4* ar = a0 + i * pw;
-        const float4* br = b0 + i * pw;
         const int ai = i < 0 ? -i : i;
+        if (TRANSPOSED) {
+            const unsigned ra = oa + (unsigned)i, rb = ob + (unsigned)i;
 #pragma unroll
-        for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE) {
-            const float4 p1 = ldpix(ar + j);
-            const float4 p2 = ldpix(br + j);
-            const float d1 = max3abs_diff(c1, p1);
-            sample_term(p1, p2, c2, d1, lut.gg[ai][j < 0 ? -j : j], lut, cost_sum, weight_sum);
+            for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE) {
+                const float4 p1 = ldpix(A + (ra + (unsigned)(j * (int)sj)));
+                const float4 p2 = ldpix(B + (rb + (unsigned)(j * (int)sj)));
+                const float d1 = max3abs_diff(c1, p1);
+                sample_term(p1, p2, c2, d1, lut.gg[ai][j < 0 ? -j : j], s_census, cost_sum, weight_sum);
+            }
+        } else {
+            const float4* ar = A + (oa + (unsigned)(i * (int)si));
+            const float4* br = B + (ob + (unsigned)(i * (int)si));
+#pragma unroll
+            for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE) {
+                const float4 p1 = ldpix(ar + j);
+                const float4 p2 = ldpix(br + j);
+                const float d1 = max3abs_diff(c1, p1);
+                sample_term(p1, p2, c2, d1, lut.gg[ai][j < 0 ? -j : j], s_census, cost_sum, weight_sum);
+            }
         }
     }
     return __fdiv_rn(cost_sum, weight_sum);

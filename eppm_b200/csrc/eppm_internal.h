@@ -56,6 +56,7 @@ struct eppm_context {
     cudaStream_t copy_stream = nullptr;
     bool profile = false;
     cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_k[4] = {};      // [0],[1] bracket k_c2f_refine at level 0; [2],[3] k_flow_smooth of the final pass
     float stage_ms[5] = {};
 
     eppm::Arena arena;
@@ -68,6 +69,7 @@ struct eppm_context {
     uchar4* rgba[2][eppm::MAX_LEVELS] = {};      // [B][h_l][w_l] dense
     uchar4* blur_tmp[2] = {nullptr, nullptr};    // scratch for pyramid levels beyond the 2-octave fast path
     float4* pix[2][eppm::MAX_LEVELS] = {};       // [B][ph_l][pw_l] packed float rgb + census
+    float4* pixT[2] = {nullptr, nullptr};        // column-major copies of the coarsest level ([B][pw][ph]) for row propagation
     eppm::GaussTab gauss[eppm::MAX_LEVELS];      // [0] pre-blur, [i] blur feeding level i
     // PatchMatch state at the coarsest level: index = dir (0 fwd, 1 bwd)
     short2* nnf[2] = {nullptr, nullptr};         // [B][h_c][w_c]
@@ -114,6 +116,7 @@ void op_preblur_rgba(eppm_context* c, const uchar4* src1, const uchar4* src2, si
 void op_pyramid_and_pack(eppm_context* c, int n);
 void op_pack_foreign(cudaStream_t s, const uchar4* rgba, size_t rgba_pitch_bytes, const unsigned char* census, size_t census_pitch_bytes, float4* pix,
                      const LevelGeom& g);
+void op_transpose_plane(cudaStream_t s, const float4* src, float4* dst, const LevelGeom& g, int n_img);
 void op_extract_census(cudaStream_t s, const float4* pix, const LevelGeom& g, unsigned char* out, size_t out_pitch_bytes);
 void k_pack_planes(cudaStream_t s, const uchar4* rgba, size_t rgba_pitch_bytes, size_t rgba_img_stride_bytes, float4* pix,
                    const LevelGeom& g, int n_img);

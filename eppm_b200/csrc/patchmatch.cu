@@ -54,45 +54,55 @@ void build_rng_tables(eppm_context* c) {
 }
 
 struct PmArgs {
-    const float4* pix[2];  // packed planes of image 1 / image 2 at the PatchMatch level, logical (0,0) of pair 0
-    size_t plane;          // pixels per padded plane
-    int pw;
-    short2* nnf[2];        // per direction, [B][h][w]
+    const float4* pix[2];   // packed planes of image 1 / image 2 at the PatchMatch level, padded origin of pair 0
+    const float4* pixT[2];  // column-major copies (pixel (x,y) at (x+PAD)*ph + (y+PAD)), padded origin of pair 0
+    unsigned plane;         // pixels per padded plane
+    int pw, ph;
+    short2* nnf[2];         // per direction, [B][h][w]
     float* cost[2];
     int w, h;
-    int n_dirs;            // 2: grid.z = pair*2 + direction; 1: forward only (legacy single-direction entry point)
+    int n_dirs;             // 2: grid.z = pair*2 + direction; 1: forward only (legacy single-direction entry point)
 };
 
+template <bool T>
 __device__ __forceinline__ void pm_select(const PmArgs& a, int z, const float4*& A, const float4*& B, short2*& nnf, float*& cost) {
     const int dir = a.n_dirs == 2 ? (z & 1) : 0, b = a.n_dirs == 2 ? (z >> 1) : z;
-    A = a.pix[dir] + (size_t)b * a.plane;       // direction 1 swaps the images (…cuda.cpp:223-224)
-    B = a.pix[dir ^ 1] + (size_t)b * a.plane;
+    A = (T ? a.pixT[dir] : a.pix[dir]) + (size_t)b * a.plane;  // direction 1 swaps the images (…cuda.cpp:223-224)
+    B = (T ? a.pixT[dir ^ 1] : a.pix[dir ^ 1]) + (size_t)b * a.plane;
     nnf = a.nnf[dir] + (size_t)b * a.w * a.h;
     cost = a.cost[dir] + (size_t)b * a.w * a.h;
+    asm volatile("" : "+l"(A), "+l"(B));  // keep the plane bases in registers: every load is then base + u32 offset
 }
 
 // Random field + initial cost (d_gen_rand_field + d_compute_cost_field).
 __global__ void __launch_bounds__(128) k_pm_init(PmArgs a, const short2* __restrict__ rng_init, const __grid_constant__ CostLut lut) {
+    __shared__ float s_census[9];
+    load_census_lut(s_census, lut);
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= a.w) return;
     const float4 *A, *B; short2* nnf; float* cost;
-    pm_select(a, blockIdx.z, A, B, nnf, cost);
-    const short2 t = rng_init[(size_t)y * a.w + x];
-    nnf[(size_t)y * a.w + x] = t;
-    cost[(size_t)y * a.w + x] = patch_cost<2>(A, B, a.pw, x, y, t.x, t.y, lut);
+    pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
+    const short2 t = rng_init[y * a.w + x];
+    nnf[y * a.w + x] = t;
+    cost[y * a.w + x] = patch_cost<2, false>(A, B, a.pw, x, y, t.x, t.y, lut, s_census);
 }
 
 // Segment propagation, the four passes of baoSegPropagate.  DIR: 0 row forward, 1 column forward, 2 row reverse,
-// 3 column reverse.  blockDim = (lines per CTA, segments per line); every thread owns one (line, segment).
+// 3 column reverse.  blockDim = (lines per CTA, all segments of a line); every thread owns one (line, segment).
+// Lanes of a warp are ADJACENT scan lines working on the same position along the line: column passes read the
+// row-major planes, row passes the column-major copies, so both sides of every sample are coalesced.
 template <int DIR>
-__global__ void k_pm_propagate(PmArgs a, int seg_len, const __grid_constant__ CostLut lut) {
+__global__ void __launch_bounds__(896) k_pm_propagate(PmArgs a, int seg_len, const __grid_constant__ CostLut lut) {
     constexpr bool ROW = (DIR == 0 || DIR == 2), FWD = (DIR < 2);
+    __shared__ float s_census[9];
+    load_census_lut(s_census, lut);
     const int line = blockIdx.x * blockDim.x + threadIdx.x;
     const int seg = threadIdx.y;
     const int n_line = ROW ? a.h : a.w;   // number of scan lines
     const int len = ROW ? a.w : a.h;      // pixels along a line
     const float4 *A, *B; short2* nnf; float* cost;
-    pm_select(a, blockIdx.z, A, B, nnf, cost);
+    pm_select<ROW>(a, blockIdx.z, A, B, nnf, cost);
+    const int pitch = ROW ? a.ph : a.pw;
     const bool active = line < n_line;
     int start, end, steps;
     if (FWD) {
@@ -108,14 +118,14 @@ __global__ void k_pm_propagate(PmArgs a, int seg_len, const __grid_constant__ Co
         steps = start - end;
     }
     if (!active) steps = 0;
-    auto idx = [&](int i) -> size_t { return ROW ? (size_t)line * a.w + i : (size_t)i * a.w + line; };
+    auto idx = [&](int i) -> int { return ROW ? line * a.w + i : i * a.w + line; };
     short2 prev = make_short2(0, 0);
     if (steps > 0) prev = nnf[idx(start)];
     __syncthreads();  // every segment has read its start pixel before any pixel is written
     for (int t = 1; t <= seg_len; t++) {
         if (t <= steps) {
             const int i = FWD ? start + t : start - t;
-            const size_t id = idx(i);
+            const int id = idx(i);
             const float cur_best = cost[id];
             // :1065/:1095/:1125/:1155  shift the predecessor's target one step along the scan axis, clamped
             if (DIR == 0) prev.x = min(prev.x + 1, a.w - 1);
@@ -123,7 +133,7 @@ __global__ void k_pm_propagate(PmArgs a, int seg_len, const __grid_constant__ Co
             if (DIR == 2) prev.x = max(prev.x - 1, 0);
             if (DIR == 3) prev.y = max(prev.y - 1, 0);
             const int x1 = ROW ? i : line, y1 = ROW ? line : i;
-            const float cv = patch_cost<2>(A, B, a.pw, x1, y1, prev.x, prev.y, lut);
+            const float cv = patch_cost<2, ROW>(A, B, pitch, x1, y1, prev.x, prev.y, lut, s_census);
             if (cv < cur_best) {
                 nnf[id] = prev;
                 cost[id] = cv;
@@ -139,11 +149,13 @@ __global__ void k_pm_propagate(PmArgs a, int seg_len, const __grid_constant__ Co
 // ENTRY best target, evaluated in order with strict '<'.
 __global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __restrict__ rng, int num_guess, int search_range, int radius_min,
                                                    const __grid_constant__ CostLut lut) {
+    __shared__ float s_census[9];
+    load_census_lut(s_census, lut);
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= a.w) return;
     const float4 *A, *B; short2* nnf; float* cost;
-    pm_select(a, blockIdx.z, A, B, nnf, cost);
-    const size_t id = (size_t)y * a.w + x;
+    pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
+    const int id = y * a.w + x;
     short2 best = nnf[id];
     float best_cost = cost[id];
     const short2 entry = best;
@@ -157,7 +169,7 @@ __global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __res
         const short gx = (short)(xmin + r1 % (unsigned)(xmax - xmin));
         const short gy = (short)(ymin + r2 % (unsigned)(ymax - ymin));
         if (mag / 2 >= radius_min) mag /= 2;
-        const float cv = patch_cost<2>(A, B, a.pw, x, y, gx, gy, lut);
+        const float cv = patch_cost<2, false>(A, B, a.pw, x, y, gx, gy, lut, s_census);
         if (cv < best_cost) {
             best = make_short2(gx, gy);
             best_cost = cv;
@@ -172,9 +184,8 @@ static void launch_propagate(eppm_context* c, const PmArgs& a, int n) {
     const bool row = (DIR == 0 || DIR == 2);
     const int len = row ? a.w : a.h, n_line = row ? a.h : a.w;
     const int n_seg = (len + c->prm.prop_seg_length - 1) / c->prm.prop_seg_length;
-    int lines = 256 / n_seg;
-    if (lines < 1) lines = 1;
-    if (lines > 32) lines = 32;
+    int lines = 32;  // adjacent scan lines per CTA = coalescing width; all segments of a line stay in one CTA (lock-step barrier)
+    while (lines > 1 && lines * n_seg > 896) lines >>= 1;
     dim3 blk(lines, n_seg), grd((n_line + lines - 1) / lines, 1, a.n_dirs * n);
     k_pm_propagate<DIR><<<grd, blk, 0, c->stream>>>(a, c->prm.prop_seg_length, c->cost_lut);
     EPPM_LAUNCH_COUNT(1);
@@ -186,10 +197,12 @@ void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps) {
     const int L = c->n_levels - 1, n = c->n_cur;
     const LevelGeom& g = c->lv[L];
     PmArgs a;
-    a.pix[0] = c->pix[0][L] + (size_t)PAD * g.pw + PAD;
-    a.pix[1] = c->pix[1][L] + (size_t)PAD * g.pw + PAD;
-    a.plane = g.plane;
-    a.pw = g.pw;
+    a.pix[0] = c->pix[0][L];
+    a.pix[1] = c->pix[1][L];
+    a.pixT[0] = c->pixT[0];
+    a.pixT[1] = c->pixT[1];
+    a.plane = (unsigned)g.plane;
+    a.pw = g.pw; a.ph = g.ph;
     a.nnf[0] = c->nnf[0]; a.nnf[1] = c->nnf[1];
     a.cost[0] = c->cost[0]; a.cost[1] = c->cost[1];
     a.w = g.w; a.h = g.h;

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) k_census_pack(const uchar4* __restrict__ 
     o.x = __fdiv_rn((float)c.x, 255.f);
     o.y = __fdiv_rn((float)c.y, 255.f);
     o.z = __fdiv_rn((float)c.z, 255.f);
-    o.w = __uint_as_float(cen);
+    o.w = __uint_as_float(cen * 0x01010101u);  // census byte replicated: popc(w1^w2) = 4*hamming (see census_lut)
     pix[(size_t)blockIdx.z * pw * ph + (size_t)py * pw + px] = o;
 }
 
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) k_pack_foreign(const uchar4* __restrict__
     o.x = __fdiv_rn((float)c.x, 255.f);
     o.y = __fdiv_rn((float)c.y, 255.f);
     o.z = __fdiv_rn((float)c.z, 255.f);
-    o.w = __uint_as_float(cen);
+    o.w = __uint_as_float(cen * 0x01010101u);
     pix[(size_t)py * pw + px] = o;
 }
 
@@ -254,6 +254,24 @@ __global__ void k_extract_census_pitched(const float4* __restrict__ pix, int pw,
 
 void op_extract_census(cudaStream_t s, const float4* pix, const LevelGeom& g, unsigned char* out, size_t out_pitch_bytes) {
     k_extract_census_pitched<<<dim3((g.w + 127) / 128, g.h), 128, 0, s>>>(pix, g.pw, out, out_pitch_bytes, g.w, g.h);
+    EPPM_LAUNCH_COUNT(1);
+}
+
+// Column-major copy of a packed plane (pixel (x,y) at x*ph + y) for the row propagation passes of PatchMatch.
+__global__ void __launch_bounds__(256) k_transpose_plane(const float4* __restrict__ src, float4* __restrict__ dst, int pw, int ph) {
+    __shared__ float4 tile[16][17];
+    const size_t off = (size_t)blockIdx.z * pw * ph;
+    int x = blockIdx.x * 16 + threadIdx.x, y = blockIdx.y * 16 + threadIdx.y;
+    if (x < pw && y < ph) tile[threadIdx.y][threadIdx.x] = src[off + (size_t)y * pw + x];
+    __syncthreads();
+    x = blockIdx.x * 16 + threadIdx.y;
+    y = blockIdx.y * 16 + threadIdx.x;
+    if (x < pw && y < ph) dst[off + (size_t)x * ph + y] = tile[threadIdx.x][threadIdx.y];
+}
+
+void op_transpose_plane(cudaStream_t s, const float4* src, float4* dst, const LevelGeom& g, int n_img) {
+    dim3 blk(16, 16), grd((g.pw + 15) / 16, (g.ph + 15) / 16, n_img);
+    k_transpose_plane<<<grd, blk, 0, s>>>(src, dst, g.pw, g.ph);
     EPPM_LAUNCH_COUNT(1);
 }
 
@@ -306,6 +324,8 @@ void op_pyramid_and_pack(eppm_context* c, int n) {
         for (int img = 0; img < 2; img++)
             k_pack_planes(s, c->rgba[img][i], (size_t)g.w * 4, (size_t)g.w * g.h * 4, c->pix[img][i], g, n);
     }
+    const int L = c->n_levels - 1;
+    for (int img = 0; img < 2; img++) op_transpose_plane(s, c->pix[img][L], c->pixT[img], c->lv[L], n);
 }
 
 }  // namespace eppm

@@ -48,7 +48,7 @@ __device__ __forceinline__ float2 upsample2(const float2* __restrict__ src, int 
 }
 
 struct RefineArgs {
-    const float4* pix1;   // logical (0,0) of pair 0, image 1 / image 2 at this level
+    const float4* pix1;   // PADDED origin of pair 0, image 1 / image 2 at this level
     const float4* pix2;
     size_t plane;
     int pw, w, h;
@@ -65,12 +65,15 @@ __device__ __forceinline__ float min_ref(float a, float b) { return a < b ? a : 
 __global__ void __launch_bounds__(RF_PIX * 3) k_c2f_refine(RefineArgs a, const __grid_constant__ CostLut lut) {
     __shared__ float s_best[3][RF_PIX];
     __shared__ int s_bn[3][RF_PIX];
+    __shared__ float s_census[9];
+    load_census_lut(s_census, lut);
     const int m = threadIdx.x >> 5, pl = threadIdx.x & 31;
     const int x = blockIdx.x * RF_PIX + pl, y = blockIdx.y;
     const bool in = x < a.w;
     const int b = blockIdx.z;
     const float4* I1 = a.pix1 + (size_t)b * a.plane;
     const float4* I2 = a.pix2 + (size_t)b * a.plane;
+    asm volatile("" : "+l"(I1), "+l"(I2));  // keep the per-pair plane bases in registers: every load is then base + u32 offset
     float2 fl = make_float2(0.f, 0.f);
     if (in) fl = a.upsample ? upsample2(a.coarse + (size_t)b * a.ws * a.hs, a.ws, a.hs, x, y) : a.coarse[(size_t)b * a.w * a.h + (size_t)y * a.w + x];
     // :2011 unknown flow -> 0 and done
@@ -92,14 +95,14 @@ __global__ void __launch_bounds__(RF_PIX * 3) k_c2f_refine(RefineArgs a, const _
         for (int n = 0; n < 3; n++)
 #pragma unroll
             for (int q = 0; q < 4; q++) cs[n][q] = ws[n][q] = 0.f;
-        const float4* a0 = I1 + (size_t)y * a.pw + x;
+        const float4* a0 = I1 + (unsigned)((y + PAD) * a.pw + x + PAD);
         const float4 c1 = ldpix(a0);
         float4 c2[3];
 #pragma unroll
         for (int n = 0; n < 3; n++) {
             const int cy = max(-PAD, min(a.h - 1 + PAD, (int)cyc + n - 1));  // invalid rows are never used; clamp keeps the load in-plane
             const int cxs = max(-PAD, min(a.w - 1 + PAD, (int)cx));
-            c2[n] = ldpix(I2 + (size_t)cy * a.pw + cxs);
+            c2[n] = ldpix(I2 + (unsigned)((cy + PAD) * a.pw + cxs + PAD));
         }
         const float uu = (float)((int)cx - x);  // :350 float uu = x2 - x1
 #pragma unroll 1
@@ -115,9 +118,9 @@ __global__ void __launch_bounds__(RF_PIX * 3) k_c2f_refine(RefineArgs a, const _
                 // x coordinates of the 4 models: cx2 = fma(i, C_uy, fma(j, C_ux, float(x1+j) + uu))   (:402, :440, :478 as contracted)
                 const float bx = __fadd_rn(uu, (float)(x + j));
                 int sx[4];
-                sx[0] = __float2int_rd(bx);
+                sx[0] = __float2int_rd(bx) + PAD;
 #pragma unroll
-                for (int q = 0; q < 3; q++) sx[q + 1] = __float2int_rd(__fmaf_rn(fi, c_pf[q][1], __fmaf_rn(fj, c_pf[q][0], bx)));
+                for (int q = 0; q < 3; q++) sx[q + 1] = __float2int_rd(__fmaf_rn(fi, c_pf[q][1], __fmaf_rn(fj, c_pf[q][0], bx))) + PAD;
 #pragma unroll
                 for (int n = 0; n < 3; n++) {
                     if (!valid[n]) continue;
@@ -125,13 +128,13 @@ __global__ void __launch_bounds__(RF_PIX * 3) k_c2f_refine(RefineArgs a, const _
                     const float vv = (float)(cy - y);
                     const float by = __fadd_rn((float)(y + i), vv);
                     int sy[4];
-                    sy[0] = __float2int_rd(by);
+                    sy[0] = __float2int_rd(by) + PAD;
 #pragma unroll
-                    for (int q = 0; q < 3; q++) sy[q + 1] = __float2int_rd(__fmaf_rn(fi, c_pf[q][3], __fmaf_rn(fj, c_pf[q][2], by)));
+                    for (int q = 0; q < 3; q++) sy[q + 1] = __float2int_rd(__fmaf_rn(fi, c_pf[q][3], __fmaf_rn(fj, c_pf[q][2], by))) + PAD;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        const float4 p2 = ldpix(I2 + (size_t)sy[q] * a.pw + sx[q]);
-                        sample_term(p1, p2, c2[n], d1, gg, lut, cs[n][q], ws[n][q]);
+                        const float4 p2 = ldpix(I2 + (unsigned)(sy[q] * a.pw + sx[q]));
+                        sample_term(p1, p2, c2[n], d1, gg, s_census, cs[n][q], ws[n][q]);
                     }
                 }
             }
@@ -235,8 +238,8 @@ __global__ void __launch_bounds__(SM_T* SM_T) k_flow_smooth(SmoothArgs a, const 
 void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const LevelGeom& g, const float2* coarse, int ws, int hs, int upsample,
                float2* out, int n) {
     RefineArgs a;
-    a.pix1 = pix1 + (size_t)PAD * g.pw + PAD;
-    a.pix2 = pix2 + (size_t)PAD * g.pw + PAD;
+    a.pix1 = pix1;
+    a.pix2 = pix2;
     a.plane = g.plane; a.pw = g.pw; a.w = g.w; a.h = g.h;
     a.coarse = coarse; a.ws = ws; a.hs = hs;
     a.flow = out;
@@ -274,17 +277,21 @@ void run_c2f(eppm_context* c, float* d_flow_out) {
     for (int level = c->n_levels - 2; level >= 0; level--) {
         const LevelGeom& g = c->lv[level];
         const LevelGeom& gs = c->lv[level + 1];
+        if (c->profile && level == 0) cudaEventRecord(c->ev_k[0], c->stream);
         op_refine(c, c->pix[0][level], c->pix[1][level], g, c->flow[level + 1], gs.w, gs.h, 1, c->flow_tmp, n);
+        if (c->profile && level == 0) cudaEventRecord(c->ev_k[1], c->stream);
         launch_smooth(c, c->flow_tmp, c->flow[level], level, n);
     }
     // final smoothing at level 0 (…cuda.cpp:289); with a single level the loop above did not run
     float2* out = reinterpret_cast<float2*>(d_flow_out);
+    if (c->profile) cudaEventRecord(c->ev_k[2], c->stream);
     if (c->n_levels >= 2) {
         launch_smooth(c, c->flow[0], out ? out : c->flow_tmp, 0, n);
         if (!out) cudaMemcpyAsync(c->flow[0], c->flow_tmp, (size_t)n * c->lv[0].w * c->lv[0].h * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream);
     } else {
         launch_smooth(c, c->flow[0], out ? out : c->flow_tmp, 0, n);
     }
+    if (c->profile) cudaEventRecord(c->ev_k[3], c->stream);
 }
 
 }  // namespace eppm

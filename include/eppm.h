@@ -126,6 +126,9 @@ unsigned long long eppm_launch_count(int reset);
 /* Per-stage device time of the last eppm_compute_batch_* call in ms (prepare, patchmatch, consistency, c2f, total);
  * valid only when the context was created with EPPM_PROFILE=1 in the environment. */
 int eppm_last_stage_ms(eppm_context* ctx, float out[5]);
+/* Device time of one kernel of the last call, measured with CUDA events on the stream it was launched on
+ * (EPPM_PROFILE=1): which = 0 plane-fitting refine at level 0 (the dominant kernel), 1 = final flow smoothing. */
+int eppm_last_kernel_ms(eppm_context* ctx, int which, float* ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,113 @@
+"""ctypes wrapper of oracle/libeppm_golden.so (the single-threaded CPU oracle, oracle/golden.cpp).
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg — never by eppm_b200."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libeppm_golden.so")
+_lib = None
+
+PLANES = {"rgba1": 0, "rgba2": 1, "census1": 2, "census2": 3, "nnf_fwd": 4, "nnf_bwd": 5, "cost_fwd": 6, "cost_bwd": 7, "flow": 8}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            raise OSError(f"{_LIB} missing: run `make -C oracle golden`")
+        l = C.CDLL(_LIB)
+        P, I = C.c_void_p, C.c_int
+        l.golden_create.restype = P; l.golden_create.argtypes = [I, I, I, I]
+        l.golden_destroy.argtypes = [P]
+        l.golden_num_levels.argtypes = [P]
+        l.golden_level_dims.argtypes = [P, I, C.POINTER(I), C.POINTER(I)]
+        l.golden_prepare.argtypes = [P, P, P]
+        l.golden_patchmatch.argtypes = [P, I]
+        l.golden_consistency.argtypes = [P]
+        l.golden_c2f.argtypes = [P, P]
+        l.golden_compute.argtypes = [P, P, P, P]
+        l.golden_read_plane.restype = C.c_long; l.golden_read_plane.argtypes = [P, I, I, P]
+        l.golden_write_plane.restype = C.c_long; l.golden_write_plane.argtypes = [P, I, I, P]
+        l.golden_xorwow.argtypes = [C.c_ulonglong, C.c_ulonglong, I, P]
+        l.golden_level_dims_for.argtypes = [I, I, I, C.POINTER(I), C.POINTER(I)]
+        l.golden_patch_cost.restype = C.c_float; l.golden_patch_cost.argtypes = [P, I, I, I, I, I]
+        _lib = l
+    return _lib
+
+
+def xorwow(seed, subsequence, n):
+    out = np.zeros(n, np.uint32)
+    lib().golden_xorwow(seed, subsequence, n, out.ctypes.data)
+    return out
+
+
+def level_dims_for(h, w, level):
+    oh, ow = C.c_int(), C.c_int()
+    lib().golden_level_dims_for(h, w, level, C.byref(oh), C.byref(ow))
+    return oh.value, ow.value
+
+
+class Golden:
+    def __init__(self, h, w, levels=3, num_iter=10):
+        self.l = lib()
+        self.h, self.w = h, w
+        self.ctx = self.l.golden_create(h, w, levels, num_iter)
+        self.num_levels = levels
+
+    def __del__(self):
+        if getattr(self, "ctx", None):
+            self.l.golden_destroy(self.ctx)
+            self.ctx = None
+
+    def level_dims(self, level):
+        h, w = C.c_int(), C.c_int()
+        self.l.golden_level_dims(self.ctx, level, C.byref(h), C.byref(w))
+        return h.value, w.value
+
+    def prepare(self, img1, img2):
+        a = np.ascontiguousarray(img1, np.uint8); b = np.ascontiguousarray(img2, np.uint8)
+        self.l.golden_prepare(self.ctx, a.ctypes.data, b.ctypes.data)
+
+    def patchmatch(self, n_steps=-1):
+        self.l.golden_patchmatch(self.ctx, n_steps)
+
+    def consistency(self):
+        self.l.golden_consistency(self.ctx)
+
+    def c2f(self):
+        out = np.zeros((self.h, self.w, 2), np.float32)
+        self.l.golden_c2f(self.ctx, out.ctypes.data)
+        return out
+
+    def compute(self, img1, img2):
+        a = np.ascontiguousarray(img1, np.uint8); b = np.ascontiguousarray(img2, np.uint8)
+        out = np.zeros((self.h, self.w, 2), np.float32)
+        self.l.golden_compute(self.ctx, a.ctypes.data, b.ctypes.data, out.ctypes.data)
+        return out
+
+    def _shape(self, which, level):
+        h, w = self.level_dims(level)
+        if 4 <= which <= 7:
+            h, w = self.level_dims(self.num_levels - 1)
+        return {0: ((h, w, 4), np.uint8), 1: ((h, w, 4), np.uint8), 2: ((h, w), np.uint8), 3: ((h, w), np.uint8), 4: ((h, w, 2), np.int16),
+                5: ((h, w, 2), np.int16), 6: ((h, w), np.float32), 7: ((h, w), np.float32), 8: ((h, w, 2), np.float32)}[which]
+
+    def plane(self, name, level=0):
+        which = PLANES[name]
+        shape, dt = self._shape(which, level)
+        out = np.zeros(shape, dt)
+        n = self.l.golden_read_plane(self.ctx, which, level, out.ctypes.data)
+        if n != out.nbytes:
+            raise RuntimeError(f"golden_read_plane({name}, {level}) -> {n}")
+        return out
+
+    def set_plane(self, name, arr, level=0):
+        arr = np.ascontiguousarray(arr)
+        n = self.l.golden_write_plane(self.ctx, PLANES[name], level, arr.ctypes.data)
+        if n != arr.nbytes:
+            raise RuntimeError(f"golden_write_plane({name}, {level}) -> {n}")
+
+    def patch_cost(self, direction, x1, y1, x2, y2):
+        return float(self.l.golden_patch_cost(self.ctx, direction, x1, y1, x2, y2))
