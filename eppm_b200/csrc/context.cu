@@ -24,7 +24,7 @@ bool cuda_ok(cudaError_t e, const char* what) {
 __global__ void k_extract_census(const float4* __restrict__ pix, int pw, unsigned char* __restrict__ out, int w, int h) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
-    out[(size_t)y * w + x] = (unsigned char)(__float_as_uint(pix[(size_t)(y + PAD) * pw + x + PAD].w) & 0xffu);
+    out[(size_t)y * w + x] = (unsigned char)unpack_census(pix[(size_t)(y + PAD) * pw + x + PAD].w);
 }
 
 static void host_luts(eppm_context* c) {
@@ -164,6 +164,23 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         if (pass == 0) A.size = A.used;
     }
     host_luts(c);
+    {
+        // The smoothing kernel divides by the constant -(sig_r^2).  Its 3-instruction form is used only if it reproduces div.rn
+        // for EVERY float the kernel can feed it: dr^2 with dr in {0} U [2^-9, 1] -> [2^-18, 1]; checked once per process and divisor.
+        static std::mutex mu;
+        static float checked_d = 0.f;
+        static int checked_ok = 0;
+        std::lock_guard<std::mutex> lk(mu);
+        const float d = -(p.blf_sig_r * p.blf_sig_r);
+        if (checked_d != d) {
+            const float lo = 1.0f / (1 << 20), hi = 2.0f;
+            unsigned lob, hib;
+            memcpy(&lob, &lo, 4); memcpy(&hib, &hi, 4);
+            checked_ok = selftest_const_div(d, lob, hib) == 0;
+            checked_d = d;
+        }
+        c->smooth_fast_div = checked_ok;
+    }
     build_gauss_tables(c);
     build_rng_tables(c);
     if (!cuda_ok(cudaStreamSynchronize(c->stream), "context setup kernels")) { eppm_destroy(c); return EPPM_ERR_CUDA; }
@@ -333,6 +350,9 @@ long eppm_read_plane(eppm_context* c, int which, int level, int pair, void* host
     }
     return cuda_ok(e, "read_plane copy") ? bytes : EPPM_ERR_CUDA;
 }
+
+long long eppm_selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits) { return selftest_const_div(d, lo_bits, hi_bits); }
+int eppm_smooth_uses_fast_div(eppm_context* c) { return c ? c->smooth_fast_div : EPPM_ERR_ARG; }
 
 long eppm_write_plane(eppm_context* c, int which, int level, int pair, const void* host_in) {
     if (!c || !host_in || level < 0 || level >= c->n_levels || pair < 0 || pair >= c->max_batch) return EPPM_ERR_ARG;

@@ -79,28 +79,74 @@ __device__ __forceinline__ float max3abs_diff(const float4& a, const float4& b) 
 
 // Census-distance LUT in shared memory, addressed by BYTE offset: the packed planes keep the census byte replicated in
 // all four bytes of .w, so popc(w1 ^ w2) = 4 * hamming distance = the byte offset of the LUT entry (no mask, no shift).
-// (A register-indexed constant-bank read would serialise on the up to 9 distinct indices of a warp.)
+// (A register-indexed constant-bank read would serialise on the up to 9 distinct indices of a warp; a 256-entry table
+// indexed by the XOR itself avoids POPC but was measured slower: its bank conflicts cost more L1 wavefronts than POPC costs XU slots.)
+constexpr int CENSUS_LUT_N = 9;
 __device__ __forceinline__ float census_lut(const float* s_census, const float4& p1, const float4& p2) {
     const unsigned off = __popc(__float_as_uint(p1.w) ^ __float_as_uint(p2.w));
     return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_census) + off);
 }
 __device__ __forceinline__ void load_census_lut(float* s_census, const CostLut& lut) {
-    if (threadIdx.x + threadIdx.y * blockDim.x < 9) s_census[threadIdx.x + threadIdx.y * blockDim.x] = lut.census[threadIdx.x + threadIdx.y * blockDim.x];
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    if (tid < CENSUS_LUT_N) s_census[tid] = lut.census[tid];
     __syncthreads();
+}
+__device__ __forceinline__ unsigned pack_census(unsigned census_byte) { return census_byte * 0x01010101u; }
+__device__ __forceinline__ unsigned unpack_census(float w) { return __float_as_uint(w) & 0xffu; }
+
+// Packed FP32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2): two IEEE round-to-nearest operations per issue slot.  Each
+// half is rounded exactly like the scalar instruction, so packing changes the instruction count, not a single bit.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+struct PixPk {  // a packed-plane pixel viewed as two FP32 pairs: (r,g) and (b, census bits)
+    f32x2 xy, zw;
+};
+__device__ __forceinline__ PixPk pack_pix(const float4& p) { return PixPk{pk2(p.x, p.y), pk2(p.z, p.w)}; }
+
+// max(|a.x-b.x|, |a.y-b.y|, |a.z-b.z|) with the three subtractions issued as two packed ones (the .w half is ignored)
+__device__ __forceinline__ float max3abs_diff(const PixPk& a, const PixPk& b) {
+    float dx, dy, dz, dw;
+    upk2(sub2(a.xy, b.xy), dx, dy);
+    upk2(sub2(a.zw, b.zw), dz, dw);
+    return fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
 }
 
 // One sample of the bilateral-weighted AD+census patch cost (bao_pmflow_kernel.cu:274-296):
 //   cost   = 1 - exp(-c^2/lambda_ad^2) + LUT_census[popc(census1 ^ census2)],  c = max|rgb1-rgb2|
 //   weight = exp(-(d1^2 + d2^2)/sigma_r^2) * G[|j|]*G[|i|],                     dk = max|centre_k - p_k|
 // accumulated as cost_sum = fma(cost, weight, cost_sum); weight_sum += weight, in sample order.
-// d1 (image-1 side) is passed in so callers can hoist it across candidates.
-__device__ __forceinline__ void sample_term(const float4& p1, const float4& p2, const float4& c2, float d1, float gg, const float* s_census,
-                                            float& cost_sum, float& weight_sum) {
-    const float c = max3abs_diff(p1, p2);
-    const float cost = __fadd_rn(one_minus_exp_ref(div_neg_0p01(__fmul_rn(c, c))), census_lut(s_census, p1, p2));
-    const float d2 = max3abs_diff(c2, p2);
-    const float arg = __fmaf_rn(d1, d1, __fmul_rn(d2, d2));
-    const float w = __fmul_rn(exp_ref(div_neg_0p01(arg)), gg);
+// d1 (image-1 side) is passed in so callers can hoist it across candidates.  The AD chain (c^2 -> /-0.01 -> *log2e) and
+// the weight chain (arg -> /-0.01 -> *log2e) run side by side in the two halves of packed instructions.
+__device__ __forceinline__ void sample_term(const float4& p1, const PixPk& p1k, const float4& p2, const PixPk& c2k, float d1, float gg,
+                                            const float* s_census, float& cost_sum, float& weight_sum) {
+    const PixPk p2k = pack_pix(p2);
+    const float c = max3abs_diff(p1k, p2k);
+    const float d2 = max3abs_diff(c2k, p2k);
+    float cc, d22;
+    const f32x2 cd = pk2(c, d2);
+    upk2(mul2(cd, cd), cc, d22);
+    const float arg = __fmaf_rn(d1, d1, d22);
+    // div_neg_0p01 on both halves: q0 = x*r; rem = fma(q0, 0.01', x); q = fma(r, rem, q0); then * log2e
+    const f32x2 x = pk2(cc, arg);
+    const f32x2 R = pk2(-99.99999237060546875f, -99.99999237060546875f), D = pk2(0.010000000707805156708f, 0.010000000707805156708f);
+    const f32x2 q0 = fma2(x, R, pk2(0.f, 0.f));
+    const f32x2 rem = fma2(q0, D, x);
+    const f32x2 q = fma2(R, rem, q0);
+    float t1, t2;
+    upk2(mul2(q, pk2(1.4426950216293334961f, 1.4426950216293334961f)), t1, t2);
+    // AD term: 1 - ex2(t1); no fix-up needed (see one_minus_exp_ref)
+    const float cost = __fadd_rn(__fadd_rn(1.0f, -ex2_mufu(t1)), census_lut(s_census, p1, p2));
+    // weight term: __expf fix-up for t2 < -126 (see exp_ref)
+    const bool tiny = t2 < -126.0f;
+    if (tiny) t2 = __fmul_rn(t2, 0.5f);
+    float e2 = ex2_mufu(t2);
+    if (tiny) e2 = __fmul_rn(e2, e2);
+    const float w = __fmul_rn(e2, gg);
     cost_sum = __fmaf_rn(cost, w, cost_sum);
     weight_sum = __fadd_rn(weight_sum, w);
 }
@@ -119,8 +165,8 @@ __device__ __forceinline__ float patch_cost(const float4* __restrict__ A, const 
     const unsigned sj = TRANSPOSED ? pitch : 1, si = TRANSPOSED ? 1 : pitch;
     const unsigned oa = (unsigned)(x1 + PAD) * sj + (unsigned)(y1 + PAD) * si;
     const unsigned ob = (unsigned)(x2 + PAD) * sj + (unsigned)(y2 + PAD) * si;
-    const float4 c1 = ldpix(A + oa);
-    const float4 c2 = ldpix(B + ob);
+    const PixPk c1k = pack_pix(ldpix(A + oa));
+    const PixPk c2k = pack_pix(ldpix(B + ob));
     float cost_sum = 0.f, weight_sum = 0.f;
 #pragma unroll 1
     for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
@@ -131,8 +177,9 @@ __device__ __forceinline__ float patch_cost(const float4* __restrict__ A, const 
             for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE) {
                 const float4 p1 = ldpix(A + (ra + (unsigned)(j * (int)sj)));
                 const float4 p2 = ldpix(B + (rb + (unsigned)(j * (int)sj)));
-                const float d1 = max3abs_diff(c1, p1);
-                sample_term(p1, p2, c2, d1, lut.gg[ai][j < 0 ? -j : j], s_census, cost_sum, weight_sum);
+                const PixPk p1k = pack_pix(p1);
+                const float d1 = max3abs_diff(c1k, p1k);
+                sample_term(p1, p1k, p2, c2k, d1, lut.gg[ai][j < 0 ? -j : j], s_census, cost_sum, weight_sum);
             }
         } else {
             const float4* ar = A + (oa + (unsigned)(i * (int)si));
@@ -141,8 +188,9 @@ __device__ __forceinline__ float patch_cost(const float4* __restrict__ A, const 
             for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE) {
                 const float4 p1 = ldpix(ar + j);
                 const float4 p2 = ldpix(br + j);
-                const float d1 = max3abs_diff(c1, p1);
-                sample_term(p1, p2, c2, d1, lut.gg[ai][j < 0 ? -j : j], s_census, cost_sum, weight_sum);
+                const PixPk p1k = pack_pix(p1);
+                const float d1 = max3abs_diff(c1k, p1k);
+                sample_term(p1, p1k, p2, c2k, d1, lut.gg[ai][j < 0 ? -j : j], s_census, cost_sum, weight_sum);
             }
         }
     }

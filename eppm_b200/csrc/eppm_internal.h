@@ -85,6 +85,7 @@ struct eppm_context {
     eppm::CostLut cost_lut;
     eppm::SmoothLut smooth_lut;
     eppm::WmfLut wmf_lut;
+    int smooth_fast_div = 0;                     // set at create time when the constant-division fast path was verified exact
 };
 
 namespace eppm {
@@ -111,6 +112,7 @@ void op_fill_holes(cudaStream_t s, const short2* src, short2* dst, const float4*
 void op_nnf_to_flow(cudaStream_t s, const short2* nnf, float2* flow, int w, int h, int n);
 void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const LevelGeom& g, const float2* coarse, int ws, int hs, int upsample,
                float2* out, int n);
+long long selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits);
 void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pix1, const LevelGeom& g, int n);
 void op_preblur_rgba(eppm_context* c, const uchar4* src1, const uchar4* src2, size_t pitch_bytes);
 void op_pyramid_and_pack(eppm_context* c, int n);

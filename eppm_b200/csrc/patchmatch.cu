@@ -76,7 +76,7 @@ __device__ __forceinline__ void pm_select(const PmArgs& a, int z, const float4*&
 
 // Random field + initial cost (d_gen_rand_field + d_compute_cost_field).
 __global__ void __launch_bounds__(128) k_pm_init(PmArgs a, const short2* __restrict__ rng_init, const __grid_constant__ CostLut lut) {
-    __shared__ float s_census[9];
+    __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= a.w) return;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128) k_pm_init(PmArgs a, const short2* __restr
 template <int DIR>
 __global__ void __launch_bounds__(896) k_pm_propagate(PmArgs a, int seg_len, const __grid_constant__ CostLut lut) {
     constexpr bool ROW = (DIR == 0 || DIR == 2), FWD = (DIR < 2);
-    __shared__ float s_census[9];
+    __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
     const int line = blockIdx.x * blockDim.x + threadIdx.x;
     const int seg = threadIdx.y;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(896) k_pm_propagate(PmArgs a, int seg_len, con
 // ENTRY best target, evaluated in order with strict '<'.
 __global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __restrict__ rng, int num_guess, int search_range, int radius_min,
                                                    const __grid_constant__ CostLut lut) {
-    __shared__ float s_census[9];
+    __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= a.w) return;

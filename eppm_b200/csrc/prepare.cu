@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) k_census_pack(const uchar4* __restrict__ 
     o.x = __fdiv_rn((float)c.x, 255.f);
     o.y = __fdiv_rn((float)c.y, 255.f);
     o.z = __fdiv_rn((float)c.z, 255.f);
-    o.w = __uint_as_float(cen * 0x01010101u);  // census byte replicated: popc(w1^w2) = 4*hamming (see census_lut)
+    o.w = __uint_as_float(pack_census(cen));  // see census_lut
     pix[(size_t)blockIdx.z * pw * ph + (size_t)py * pw + px] = o;
 }
 
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) k_pack_foreign(const uchar4* __restrict__
     o.x = __fdiv_rn((float)c.x, 255.f);
     o.y = __fdiv_rn((float)c.y, 255.f);
     o.z = __fdiv_rn((float)c.z, 255.f);
-    o.w = __uint_as_float(cen * 0x01010101u);
+    o.w = __uint_as_float(pack_census(cen));
     pix[(size_t)py * pw + px] = o;
 }
 
@@ -249,7 +249,7 @@ void op_pack_foreign(cudaStream_t s, const uchar4* rgba, size_t rgba_pitch_bytes
 __global__ void k_extract_census_pitched(const float4* __restrict__ pix, int pw, unsigned char* __restrict__ out, size_t pitch, int w, int h) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
-    out[(size_t)y * pitch + x] = (unsigned char)(__float_as_uint(pix[(size_t)(y + PAD) * pw + x + PAD].w) & 0xffu);
+    out[(size_t)y * pitch + x] = (unsigned char)unpack_census(pix[(size_t)(y + PAD) * pw + x + PAD].w);
 }
 
 void op_extract_census(cudaStream_t s, const float4* pix, const LevelGeom& g, unsigned char* out, size_t out_pitch_bytes) {

@@ -65,7 +65,7 @@ __device__ __forceinline__ float min_ref(float a, float b) { return a < b ? a : 
 __global__ void __launch_bounds__(RF_PIX * 3) k_c2f_refine(RefineArgs a, const __grid_constant__ CostLut lut) {
     __shared__ float s_best[3][RF_PIX];
     __shared__ int s_bn[3][RF_PIX];
-    __shared__ float s_census[9];
+    __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
     const int m = threadIdx.x >> 5, pl = threadIdx.x & 31;
     const int x = blockIdx.x * RF_PIX + pl, y = blockIdx.y;
@@ -96,13 +96,13 @@ __global__ void __launch_bounds__(RF_PIX * 3) k_c2f_refine(RefineArgs a, const _
 #pragma unroll
             for (int q = 0; q < 4; q++) cs[n][q] = ws[n][q] = 0.f;
         const float4* a0 = I1 + (unsigned)((y + PAD) * a.pw + x + PAD);
-        const float4 c1 = ldpix(a0);
-        float4 c2[3];
+        const PixPk c1k = pack_pix(ldpix(a0));
+        PixPk c2k[3];
 #pragma unroll
         for (int n = 0; n < 3; n++) {
             const int cy = max(-PAD, min(a.h - 1 + PAD, (int)cyc + n - 1));  // invalid rows are never used; clamp keeps the load in-plane
             const int cxs = max(-PAD, min(a.w - 1 + PAD, (int)cx));
-            c2[n] = ldpix(I2 + (unsigned)((cy + PAD) * a.pw + cxs + PAD));
+            c2k[n] = pack_pix(ldpix(I2 + (unsigned)((cy + PAD) * a.pw + cxs + PAD)));
         }
         const float uu = (float)((int)cx - x);  // :350 float uu = x2 - x1
 #pragma unroll 1
@@ -113,12 +113,13 @@ __global__ void __launch_bounds__(RF_PIX * 3) k_c2f_refine(RefineArgs a, const _
             for (int j = -PATCH_R; j <= PATCH_R; j += 2) {
                 const float fj = (float)j;
                 const float4 p1 = ldpix(a0 + i * a.pw + j);
-                const float d1 = max3abs_diff(c1, p1);
+                const PixPk p1k = pack_pix(p1);
+                const float d1 = max3abs_diff(c1k, p1k);
                 const float gg = lut.gg[ai][j < 0 ? -j : j];
                 // x coordinates of the 4 models: cx2 = fma(i, C_uy, fma(j, C_ux, float(x1+j) + uu))   (:402, :440, :478 as contracted)
                 const float bx = __fadd_rn(uu, (float)(x + j));
                 int sx[4];
-                sx[0] = __float2int_rd(bx) + PAD;
+                sx[0] = (int)cx + j + PAD;  // identity model: float(x1+j) + float(x2-x1) is the exact integer x2+j
 #pragma unroll
                 for (int q = 0; q < 3; q++) sx[q + 1] = __float2int_rd(__fmaf_rn(fi, c_pf[q][1], __fmaf_rn(fj, c_pf[q][0], bx))) + PAD;
 #pragma unroll
@@ -128,13 +129,13 @@ __global__ void __launch_bounds__(RF_PIX * 3) k_c2f_refine(RefineArgs a, const _
                     const float vv = (float)(cy - y);
                     const float by = __fadd_rn((float)(y + i), vv);
                     int sy[4];
-                    sy[0] = __float2int_rd(by) + PAD;
+                    sy[0] = cy + i + PAD;
 #pragma unroll
                     for (int q = 0; q < 3; q++) sy[q + 1] = __float2int_rd(__fmaf_rn(fi, c_pf[q][3], __fmaf_rn(fj, c_pf[q][2], by))) + PAD;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const float4 p2 = ldpix(I2 + (unsigned)(sy[q] * a.pw + sx[q]));
-                        sample_term(p1, p2, c2[n], d1, gg, s_census, cs[n][q], ws[n][q]);
+                        sample_term(p1, p1k, p2, c2k[n], d1, gg, s_census, cs[n][q], ws[n][q]);
                     }
                 }
             }
@@ -181,24 +182,30 @@ __global__ void __launch_bounds__(RF_PIX * 3) k_c2f_refine(RefineArgs a, const _
 struct SmoothArgs {
     const float2* src;
     float2* dst;
-    const float4* pix;  // logical (0,0), image 1
+    const float4* pix;  // padded origin, image 1
     size_t plane;
     int pw, w, h;
     int R;
-    float neg_sig_r2;
+    float neg_sig_r2;   // -(sig_r*sig_r), the divisor nvcc folds `-(d*d)/(SIG_R*SIG_R)` into
+    float recip;        // RN(1/neg_sig_r2)
+    int fast_div;       // 1: x/neg_sig_r2 as q0=x*r, rem=fma(-q0,d,x), q=fma(rem,r,q0) (exactness verified by eppm_selftest_const_div)
 };
 
 constexpr int SM_T = 16;
 __global__ void __launch_bounds__(SM_T* SM_T) k_flow_smooth(SmoothArgs a, const __grid_constant__ SmoothLut lut) {
-    extern __shared__ float4 smem[];  // [TW*TW] colours, then float2 [TW*TW] flows
+    extern __shared__ float4 smem[];  // [TW*TW] colours, then float2 [TW*TW] flows, then float [(R+1)^2] spatial weights
     const int R = a.R, TW = SM_T + 2 * R;
     float4* s_pix = smem;
     float2* s_flow = reinterpret_cast<float2*>(smem + TW * TW);
+    float* s_gg = reinterpret_cast<float*>(s_flow + TW * TW);
     const int b = blockIdx.z;
     const float2* f = a.src + (size_t)b * a.w * a.h;
-    const float4* img = a.pix + (size_t)b * a.plane;
+    const float4* img = a.pix + (size_t)b * a.plane + (size_t)PAD * a.pw + PAD;
     const int x0 = blockIdx.x * SM_T - R, y0 = blockIdx.y * SM_T - R;
-    for (int i = threadIdx.y * SM_T + threadIdx.x; i < TW * TW; i += SM_T * SM_T) {
+    const int tid = threadIdx.y * SM_T + threadIdx.x;
+    for (int i = tid; i < (R + 1) * (R + 1); i += SM_T * SM_T)
+        s_gg[i] = __fmul_rn(lut.g[i % (R + 1)], lut.g[i / (R + 1)]);  // cBlfGaussian[|dx|] * cBlfGaussian[|dy|] (:759)
+    for (int i = tid; i < TW * TW; i += SM_T * SM_T) {
         const int ty = i / TW, tx = i % TW;
         const int cx = x0 + tx, cy = y0 + ty;
         float2 fl = make_float2(EPPM_UNKNOWN_FLOW, EPPM_UNKNOWN_FLOW);  // outside the image: skipped like unknown flow (:776,:778)
@@ -214,17 +221,26 @@ __global__ void __launch_bounds__(SM_T* SM_T) k_flow_smooth(SmoothArgs a, const 
     const int x = blockIdx.x * SM_T + threadIdx.x, y = blockIdx.y * SM_T + threadIdx.y;
     if (x >= a.w || y >= a.h) return;
     const float4 c = s_pix[(threadIdx.y + R) * TW + threadIdx.x + R];
+    const float r = a.recip, nd = -a.neg_sig_r2;
     float nx = 0.f, ny = 0.f, wsum = 0.f;
     for (int dy = -R; dy <= R; dy++) {
-        const float gy = lut.g[abs(dy)];
+        const float* ggr = s_gg + abs(dy) * (R + 1);
         const int rowb = (threadIdx.y + R + dy) * TW + threadIdx.x + R;
+#pragma unroll 3
         for (int dx = -R; dx <= R; dx++) {
             const float2 fl = s_flow[rowb + dx];
-            if (fl.x > EPPM_UNKNOWN_FLOW_THRESH || fl.y > EPPM_UNKNOWN_FLOW_THRESH) continue;
+            if (fmaxf(fl.x, fl.y) > EPPM_UNKNOWN_FLOW_THRESH) continue;                        // :778 (same truth table as x > T || y > T)
             const float4 p = s_pix[rowb + dx];
             const float dr = max3abs_diff(p, c);                                              // :757
-            const float coef_r = __expf(__fdiv_rn(__fmul_rn(dr, dr), a.neg_sig_r2));          // :758
-            const float wgt = __fmul_rn(coef_r, __fmul_rn(lut.g[abs(dx)], gy));               // :759-760
+            const float xx = __fmul_rn(dr, dr);
+            float q;
+            if (a.fast_div) {
+                const float q0 = __fmul_rn(xx, r);
+                q = __fmaf_rn(__fmaf_rn(q0, nd, xx), r, q0);
+            } else {
+                q = __fdiv_rn(xx, a.neg_sig_r2);
+            }
+            const float wgt = __fmul_rn(exp_ref(q), ggr[abs(dx)]);                             // :758-760
             nx = __fmaf_rn(wgt, fl.x, nx);                                                    // :782-783
             ny = __fmaf_rn(wgt, fl.y, ny);
             wsum = __fadd_rn(wsum, wgt);
@@ -233,6 +249,32 @@ __global__ void __launch_bounds__(SM_T* SM_T) k_flow_smooth(SmoothArgs a, const 
     float2 out = s_flow[(threadIdx.y + R) * TW + threadIdx.x + R];
     if (wsum != 0.f) out = make_float2(__fdiv_rn(nx, wsum), __fdiv_rn(ny, wsum));  // :790-796 (untouched otherwise)
     a.dst[(size_t)b * a.w * a.h + (size_t)y * a.w + x] = out;
+}
+
+// Exhaustive check that the 3-instruction constant division equals div.rn for every float in [lo, hi) (bit patterns).
+__global__ void k_selftest_const_div(float d, float r, unsigned lo_bits, unsigned hi_bits, unsigned long long* mismatches) {
+    unsigned long long local = 0;
+    for (unsigned long long b = lo_bits + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; b < hi_bits;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)b);
+        const float q0 = __fmul_rn(x, r);
+        const float q = __fmaf_rn(__fmaf_rn(q0, -d, x), r, q0);
+        if (__float_as_uint(q) != __float_as_uint(__fdiv_rn(x, d))) local++;
+    }
+    if (local) atomicAdd(mismatches, local);
+}
+
+long long selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits) {
+    unsigned long long* dm = nullptr;
+    if (cudaMalloc((void**)&dm, 8) != cudaSuccess) return -1;
+    cudaMemset(dm, 0, 8);
+    volatile float one = 1.0f;
+    const float r = one / d;
+    k_selftest_const_div<<<148 * 8, 256>>>(d, r, lo_bits, hi_bits, dm);
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, dm, 8, cudaMemcpyDeviceToHost);
+    cudaFree(dm);
+    return e == cudaSuccess ? (long long)h : -1;
 }
 
 void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const LevelGeom& g, const float2* coarse, int ws, int hs, int upsample,
@@ -252,12 +294,15 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
 void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pix1, const LevelGeom& g, int n) {
     SmoothArgs a;
     a.src = src; a.dst = dst;
-    a.pix = pix1 + (size_t)PAD * g.pw + PAD;
+    a.pix = pix1;
     a.plane = g.plane; a.pw = g.pw; a.w = g.w; a.h = g.h;
     a.R = 2 * c->prm.blf_sig_s;
     a.neg_sig_r2 = -(c->prm.blf_sig_r * c->prm.blf_sig_r);
+    volatile float one = 1.0f;
+    a.recip = one / a.neg_sig_r2;
+    a.fast_div = c->smooth_fast_div;
     const int TW = SM_T + 2 * a.R;
-    const size_t smem = (size_t)TW * TW * (sizeof(float4) + sizeof(float2));
+    const size_t smem = (size_t)TW * TW * (sizeof(float4) + sizeof(float2)) + (size_t)(a.R + 1) * (a.R + 1) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_flow_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -120,6 +120,12 @@ long eppm_read_plane(eppm_context* ctx, int which, int level, int pair, void* ho
 long eppm_write_plane(eppm_context* ctx, int which, int level, int pair, const void* host_in);
 int eppm_stage_patchmatch_partial(eppm_context* ctx, int n_steps);
 
+/* Exhaustive device self-test: number of floats x with bit patterns in [lo_bits, hi_bits) for which the 3-instruction
+ * constant division (q0 = x*r; q = fma(fma(q0,-d,x), r, q0), r = RN(1/d)) differs from div.rn(x, d); 0 = exact everywhere.
+ * eppm_smooth_uses_fast_div reports whether a context's smoothing kernel was allowed to use it. */
+long long eppm_selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits);
+int eppm_smooth_uses_fast_div(eppm_context* ctx);
+
 /* Number of kernel launches issued by this library since the counter was last reset (bench.py's gpu_launches). */
 unsigned long long eppm_launch_count(int reset);
 

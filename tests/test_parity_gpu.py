@@ -344,3 +344,16 @@ def test_properties_full_hd():
     f2 = ctx.compute_batch_host(np.stack([a, a]), np.stack([a, shifted]))
     assert same_bits(f, f2)
     ctx.close()
+
+
+def test_constant_division_fast_path_is_exact(mine):
+    """The smoothing kernel's 3-instruction division by -(0.02f*0.02f) and the patch cost's by -(0.1f*0.1f) must equal div.rn for
+    EVERY float in the operand range (exhaustive sweep over the bit patterns of [2^-20, 2))."""
+    lo = np.array([2.0 ** -20], np.float32).view(np.uint32)[0]
+    hi = np.array([2.0], np.float32).view(np.uint32)[0]
+    for sig in (0.02, 0.1):
+        d = -(np.float32(sig) * np.float32(sig))
+        assert mine.eppm_selftest_const_div(float(d), int(lo), int(hi)) == 0
+    ctx = E.EppmContext(96, 128, 1)
+    assert ctx.lib.eppm_smooth_uses_fast_div(ctx._ctx) == 1
+    ctx.close()
