@@ -1,0 +1,35 @@
+"""Host-side sharding of independent frame pairs across ranks (one process per GPU, no data-path collective).
+
+The dense-correspondence path has no exchange step for batched pairs: every pair is an independent unit and
+the RNG stream depends on the level geometry only, so results do not depend on how a batch is split.  The only
+cross-rank traffic is the timing reduction of the benchmark (max over ranks)."""
+
+
+def shard_range(n_total, rank, world):
+    """Contiguous shard [lo, hi) of `n_total` units for `rank`; sizes differ by at most one, earlier ranks get the extra unit."""
+    if world < 1 or not (0 <= rank < world) or n_total < 0:
+        raise ValueError("bad shard arguments")
+    base, extra = divmod(n_total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def max_over_ranks(value, world, device=None):
+    """MAX all-reduce of a python float over the default process group (gloo on CPU, nccl on GPU); identity when world == 1."""
+    if world == 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, world, device=None):
+    if world == 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
