@@ -357,3 +357,25 @@ def test_constant_division_fast_path_is_exact(mine):
     ctx = E.EppmContext(96, 128, 1)
     assert ctx.lib.eppm_smooth_uses_fast_div(ctx._ctx) == 1
     ctx.close()
+
+
+@needs_ref
+def test_unmodified_main_cpp_drop_in(tmp_path):
+    """The reference's UNMODIFIED main.cpp, compiled against include/compat and linked with libeppm_b200.so (build/runeppm_b200),
+    against the reference's own executable on the shipped pair (BASELINE config 1)."""
+    import shutil, subprocess
+    exe = os.path.join(ROOT, "build", "runeppm_b200")
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "runeppm")
+    if not (os.path.exists(exe) and os.path.exists(ref_exe) and os.path.exists(os.path.join(refharness.REF_DATA, "frame10.ppm"))):
+        pytest.skip("drop-in executables not built")
+    flows = []
+    for k, binary in enumerate((ref_exe, exe)):
+        d = tmp_path / f"run{k}"
+        d.mkdir()
+        for f in ("frame10.ppm", "frame11.ppm"):
+            shutil.copy(os.path.join(refharness.REF_DATA, f), d / f)
+        subprocess.run([binary], cwd=d, check=True, stdout=subprocess.DEVNULL, timeout=300)
+        flows.append(synth.read_flo(str(d / "flow.flo")))
+    assert flows[0].shape == flows[1].shape == (480, 640, 2)
+    dd = np.sqrt(((flows[0] - flows[1]) ** 2).sum(-1))
+    assert dd.mean() <= 0.05, dd.mean()
