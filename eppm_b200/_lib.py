@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeppm_b200.so")
+LIB_PATH = os.environ.get("EPPM_LIB_PATH") or os.path.join(_HERE, "libeppm_b200.so")  # override = A/B builds while tuning
 
 
 class EppmParams(C.Structure):

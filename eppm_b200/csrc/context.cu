@@ -101,7 +101,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
     const eppm_params& p = c->prm;
     if (p.pyr_levels < 1 || p.pyr_levels > MAX_LEVELS || p.patch_r != 9 || p.patch_stride != 2 || p.wmf_radius != 4 || p.num_iter < 0 ||
         p.num_rand_guess < 0 || p.num_rand_guess > 16 || p.prop_seg_length < 1 || p.blf_sig_s < 1 || p.blf_sig_s > 10 || p.stat_radius < 0 ||
-        p.stat_radius > 16 || p.rng_mode != EPPM_RNG_XORWOW || p.lambda_ad != 0.1f || p.pm_sig_r != 0.1f) {
+        p.stat_radius > 16 || (p.rng_mode != EPPM_RNG_XORWOW && p.rng_mode != EPPM_RNG_PHILOX) || p.lambda_ad != 0.1f || p.pm_sig_r != 0.1f) {
         set_error("eppm_create: parameter combination not supported by this build");
         delete c;
         return EPPM_ERR_ARG;

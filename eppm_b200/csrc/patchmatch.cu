@@ -45,8 +45,32 @@ __global__ void k_rng_tables(short2* __restrict__ init, short2* __restrict__ sea
                 }
 }
 
+// EPPM_RNG_PHILOX: counter-based Philox4x32-10 (curand's implementation of Salmon et al., SC'11), one independent stream per
+// PIXEL: sub-sequence = y*w + x of the coarsest level, key = seed; draws 0,1 = initial target, then two draws per
+// (iteration, guess).  Unlike XORWOW there is no serial dependence between pixels of a block; the same tables feed the same kernels.
+__global__ void k_rng_tables_philox(short2* __restrict__ init, short2* __restrict__ search, int w, int h, int num_iter, int num_guess,
+                                    unsigned long long seed) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= w * h) return;
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (unsigned long long)id, 0, &st);
+    const unsigned r1 = curand(&st), r2 = curand(&st);
+    init[id] = make_short2((short)(r1 % (unsigned)(w + 1)), (short)(r2 % (unsigned)(h + 1)));
+    for (int it = 0; it < num_iter; it++)
+        for (int k = 0; k < num_guess; k++) {
+            const unsigned a = curand(&st), b = curand(&st);
+            search[(size_t)(it * num_guess + k) * w * h + id] = make_short2((short)a, (short)b);
+        }
+}
+
 void build_rng_tables(eppm_context* c) {
     const LevelGeom& g = c->lv[c->n_levels - 1];
+    if (c->prm.rng_mode == EPPM_RNG_PHILOX) {
+        k_rng_tables_philox<<<(g.w * g.h + 127) / 128, 128, 0, c->stream>>>(c->rng_init, c->rng_search, g.w, g.h, c->prm.num_iter, c->prm.num_rand_guess,
+                                                                          c->prm.seed);
+        EPPM_LAUNCH_COUNT(1);
+        return;
+    }
     const int gx = (g.w + RB - 1) / RB, gy = (g.h + RB - 1) / RB;
     k_rng_tables<<<(gx * gy + 63) / 64, 64, 0, c->stream>>>(c->rng_init, c->rng_search, g.w, g.h, gx, gy, c->prm.num_iter, c->prm.num_rand_guess,
                                                           c->prm.seed);

@@ -62,7 +62,10 @@ struct RefineArgs {
 // reads); the three column minima of a pixel meet in shared memory.
 constexpr int RF_PIX = 32;
 __device__ __forceinline__ float min_ref(float a, float b) { return a < b ? a : b; }  // the reference's __min macro
-__global__ void __launch_bounds__(RF_PIX * 3) k_c2f_refine(RefineArgs a, const __grid_constant__ CostLut lut) {
+#ifndef RF_MINBLOCKS
+#define RF_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine(RefineArgs a, const __grid_constant__ CostLut lut) {
     __shared__ float s_best[3][RF_PIX];
     __shared__ int s_bn[3][RF_PIX];
     __shared__ float s_census[CENSUS_LUT_N];
@@ -191,21 +194,41 @@ struct SmoothArgs {
     int fast_div;       // 1: x/neg_sig_r2 as q0=x*r, rem=fma(-q0,d,x), q=fma(rem,r,q0) (exactness verified by eppm_selftest_const_div)
 };
 
-constexpr int SM_T = 16;
-__global__ void __launch_bounds__(SM_T* SM_T) k_flow_smooth(SmoothArgs a, const __grid_constant__ SmoothLut lut) {
-    extern __shared__ float4 smem[];  // [TW*TW] colours, then float2 [TW*TW] flows, then float [(R+1)^2] spatial weights
-    const int R = a.R, TW = SM_T + 2 * R;
+// CTA = 32 x 8 threads, every thread filters TWO vertically adjacent pixels (y, y+1): a tile row is tap row dy of the upper
+// pixel and dy-1 of the lower one, so each shared-memory read (16 B colour + 8 B flow) feeds two taps -- the kernel was
+// shared-memory-bandwidth bound with one pixel per thread.  Each pixel still accumulates its taps in (dy, dx) raster order.
+constexpr int SM_TX = 32, SM_TY = 8, SM_PY = 2;
+__device__ __forceinline__ void smooth_tap(const SmoothArgs& a, const float4& c, const float4& p, const float2& fl, float gg, float r, float nd, float& nx,
+                                           float& ny, float& wsum) {
+    const float dr = max3abs_diff(p, c);                                              // :757
+    const float xx = __fmul_rn(dr, dr);
+    float q;
+    if (a.fast_div) {
+        const float q0 = __fmul_rn(xx, r);
+        q = __fmaf_rn(__fmaf_rn(q0, nd, xx), r, q0);
+    } else {
+        q = __fdiv_rn(xx, a.neg_sig_r2);
+    }
+    const float wgt = __fmul_rn(exp_ref(q), gg);                                      // :758-760
+    nx = __fmaf_rn(wgt, fl.x, nx);                                                    // :782-783
+    ny = __fmaf_rn(wgt, fl.y, ny);
+    wsum = __fadd_rn(wsum, wgt);
+}
+
+__global__ void __launch_bounds__(SM_TX* SM_TY) k_flow_smooth(SmoothArgs a, const __grid_constant__ SmoothLut lut) {
+    extern __shared__ float4 smem[];  // [TH*TW] colours, then float2 [TH*TW] flows, then float [(R+1)^2] spatial weights
+    const int R = a.R, TW = SM_TX + 2 * R, TH = SM_TY * SM_PY + 2 * R;
     float4* s_pix = smem;
-    float2* s_flow = reinterpret_cast<float2*>(smem + TW * TW);
-    float* s_gg = reinterpret_cast<float*>(s_flow + TW * TW);
+    float2* s_flow = reinterpret_cast<float2*>(smem + TW * TH);
+    float* s_gg = reinterpret_cast<float*>(s_flow + TW * TH);
     const int b = blockIdx.z;
     const float2* f = a.src + (size_t)b * a.w * a.h;
     const float4* img = a.pix + (size_t)b * a.plane + (size_t)PAD * a.pw + PAD;
-    const int x0 = blockIdx.x * SM_T - R, y0 = blockIdx.y * SM_T - R;
-    const int tid = threadIdx.y * SM_T + threadIdx.x;
-    for (int i = tid; i < (R + 1) * (R + 1); i += SM_T * SM_T)
+    const int x0 = blockIdx.x * SM_TX - R, y0 = blockIdx.y * SM_TY * SM_PY - R;
+    const int tid = threadIdx.y * SM_TX + threadIdx.x;
+    for (int i = tid; i < (R + 1) * (R + 1); i += SM_TX * SM_TY)
         s_gg[i] = __fmul_rn(lut.g[i % (R + 1)], lut.g[i / (R + 1)]);  // cBlfGaussian[|dx|] * cBlfGaussian[|dy|] (:759)
-    for (int i = tid; i < TW * TW; i += SM_T * SM_T) {
+    for (int i = tid; i < TW * TH; i += SM_TX * SM_TY) {
         const int ty = i / TW, tx = i % TW;
         const int cx = x0 + tx, cy = y0 + ty;
         float2 fl = make_float2(EPPM_UNKNOWN_FLOW, EPPM_UNKNOWN_FLOW);  // outside the image: skipped like unknown flow (:776,:778)
@@ -218,37 +241,39 @@ __global__ void __launch_bounds__(SM_T* SM_T) k_flow_smooth(SmoothArgs a, const 
         s_pix[i] = p;
     }
     __syncthreads();
-    const int x = blockIdx.x * SM_T + threadIdx.x, y = blockIdx.y * SM_T + threadIdx.y;
+    const int x = blockIdx.x * SM_TX + threadIdx.x;
+    const int ly = threadIdx.y * SM_PY;               // local row of the upper pixel
+    const int y = blockIdx.y * SM_TY * SM_PY + ly;
     if (x >= a.w || y >= a.h) return;
-    const float4 c = s_pix[(threadIdx.y + R) * TW + threadIdx.x + R];
+    const float4 cA = s_pix[(ly + R) * TW + threadIdx.x + R];
+    const float4 cB = s_pix[(ly + 1 + R) * TW + threadIdx.x + R];
     const float r = a.recip, nd = -a.neg_sig_r2;
-    float nx = 0.f, ny = 0.f, wsum = 0.f;
-    for (int dy = -R; dy <= R; dy++) {
-        const float* ggr = s_gg + abs(dy) * (R + 1);
-        const int rowb = (threadIdx.y + R + dy) * TW + threadIdx.x + R;
+    float nxA = 0.f, nyA = 0.f, wA = 0.f, nxB = 0.f, nyB = 0.f, wB = 0.f;
+    // tile rows ly .. ly + 2R + 1: row t is tap dy = t - R of pixel A and dy = t - R - 1 of pixel B
+    for (int t = 0; t <= 2 * R + 1; t++) {
+        const int dyA = t - R, dyB = t - R - 1;
+        const bool useA = dyA <= R, useB = dyB >= -R;
+        const float* ggA = s_gg + abs(dyA) * (R + 1);
+        const float* ggB = s_gg + abs(dyB) * (R + 1);
+        const int rowb = (ly + t) * TW + threadIdx.x + R;
 #pragma unroll 3
         for (int dx = -R; dx <= R; dx++) {
             const float2 fl = s_flow[rowb + dx];
             if (fmaxf(fl.x, fl.y) > EPPM_UNKNOWN_FLOW_THRESH) continue;                        // :778 (same truth table as x > T || y > T)
             const float4 p = s_pix[rowb + dx];
-            const float dr = max3abs_diff(p, c);                                              // :757
-            const float xx = __fmul_rn(dr, dr);
-            float q;
-            if (a.fast_div) {
-                const float q0 = __fmul_rn(xx, r);
-                q = __fmaf_rn(__fmaf_rn(q0, nd, xx), r, q0);
-            } else {
-                q = __fdiv_rn(xx, a.neg_sig_r2);
-            }
-            const float wgt = __fmul_rn(exp_ref(q), ggr[abs(dx)]);                             // :758-760
-            nx = __fmaf_rn(wgt, fl.x, nx);                                                    // :782-783
-            ny = __fmaf_rn(wgt, fl.y, ny);
-            wsum = __fadd_rn(wsum, wgt);
+            const int adx = abs(dx);
+            if (useA) smooth_tap(a, cA, p, fl, ggA[adx], r, nd, nxA, nyA, wA);
+            if (useB) smooth_tap(a, cB, p, fl, ggB[adx], r, nd, nxB, nyB, wB);
         }
     }
-    float2 out = s_flow[(threadIdx.y + R) * TW + threadIdx.x + R];
-    if (wsum != 0.f) out = make_float2(__fdiv_rn(nx, wsum), __fdiv_rn(ny, wsum));  // :790-796 (untouched otherwise)
-    a.dst[(size_t)b * a.w * a.h + (size_t)y * a.w + x] = out;
+    float2 outA = s_flow[(ly + R) * TW + threadIdx.x + R];
+    if (wA != 0.f) outA = make_float2(__fdiv_rn(nxA, wA), __fdiv_rn(nyA, wA));  // :790-796 (untouched otherwise)
+    a.dst[(size_t)b * a.w * a.h + (size_t)y * a.w + x] = outA;
+    if (y + 1 < a.h) {
+        float2 outB = s_flow[(ly + 1 + R) * TW + threadIdx.x + R];
+        if (wB != 0.f) outB = make_float2(__fdiv_rn(nxB, wB), __fdiv_rn(nyB, wB));
+        a.dst[(size_t)b * a.w * a.h + (size_t)(y + 1) * a.w + x] = outB;
+    }
 }
 
 // Exhaustive check that the 3-instruction constant division equals div.rn for every float in [lo, hi) (bit patterns).
@@ -301,14 +326,14 @@ void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pi
     volatile float one = 1.0f;
     a.recip = one / a.neg_sig_r2;
     a.fast_div = c->smooth_fast_div;
-    const int TW = SM_T + 2 * a.R;
-    const size_t smem = (size_t)TW * TW * (sizeof(float4) + sizeof(float2)) + (size_t)(a.R + 1) * (a.R + 1) * sizeof(float);
+    const int TW = SM_TX + 2 * a.R, TH = SM_TY * SM_PY + 2 * a.R;
+    const size_t smem = (size_t)TW * TH * (sizeof(float4) + sizeof(float2)) + (size_t)(a.R + 1) * (a.R + 1) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_flow_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    dim3 blk(SM_T, SM_T), grd((g.w + SM_T - 1) / SM_T, (g.h + SM_T - 1) / SM_T, n);
+    dim3 blk(SM_TX, SM_TY), grd((g.w + SM_TX - 1) / SM_TX, (g.h + SM_TY * SM_PY - 1) / (SM_TY * SM_PY), n);
     k_flow_smooth<<<grd, blk, smem, c->stream>>>(a, c->smooth_lut);
     EPPM_LAUNCH_COUNT(1);
 }
