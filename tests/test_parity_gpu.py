@@ -379,3 +379,21 @@ def test_unmodified_main_cpp_drop_in(tmp_path):
     assert flows[0].shape == flows[1].shape == (480, 640, 2)
     dd = np.sqrt(((flows[0] - flows[1]) ** 2).sum(-1))
     assert dd.mean() <= 0.05, dd.mean()
+
+
+@needs_ref
+def test_philox_mode_epe_delta(ref):
+    """Stated counter-based RNG (EPPM_RNG_PHILOX, Philox4x32-10 keyed by seed with one sub-sequence per coarse pixel): the NNF is a
+    different random realisation, so the bar is the north star's: accuracy against ground truth within 0.05 px of the reference's."""
+    h, w = 436, 1024
+    a, b, gt, valid = synth.make_pair(h, w, 1)
+    rc = ref.create(h, w)
+    ref.set_data(rc, a, b)
+    fr = ref.compute_flow(rc, h, w)
+    p = E.default_params()
+    p.rng_mode = 1
+    ctx = E.EppmContext(h, w, 1, params=p)
+    fm = ctx.compute_batch_host(a[None], b[None])[0]
+    e_ref, e_me = synth.epe(fr, gt, valid), synth.epe(fm, gt, valid)
+    assert e_me <= e_ref + 0.05, (e_me, e_ref)
+    ref.destroy(rc); ctx.close()
