@@ -39,6 +39,11 @@ EPPM_SYMBOLS = {
     "eppm_read_plane": (C.c_long, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "eppm_write_plane": (C.c_long, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "eppm_stage_patchmatch_partial": (C.c_int, [C.c_void_p, C.c_int]),
+    "eppm_set_band": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "eppm_band_rows": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "eppm_tiled_pm_steps": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "eppm_tiled_c2f_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "eppm_device_plane": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
     "eppm_selftest_const_div": (C.c_longlong, [C.c_float, C.c_uint, C.c_uint]),
     "eppm_smooth_uses_fast_div": (C.c_int, [C.c_void_p]),
     "eppm_launch_count": (C.c_ulonglong, [C.c_int]),

@@ -163,6 +163,8 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         c->flow_tmp = A.take<float2>(B * c->lv[0].w * c->lv[0].h);
         if (pass == 0) A.size = A.used;
     }
+    c->band_y0 = 0;
+    c->band_y1 = gc.h;
     host_luts(c);
     {
         // The smoothing kernel divides by the constant -(sig_r^2).  Its 3-instruction form is used only if it reproduces div.rn
@@ -349,6 +351,51 @@ long eppm_read_plane(eppm_context* c, int which, int level, int pair, void* host
         return EPPM_ERR_ARG;
     }
     return cuda_ok(e, "read_plane copy") ? bytes : EPPM_ERR_CUDA;
+}
+
+// ---- spatial tiling of one large frame across GPUs: every rank holds the full pyramids and fields, owns a band of
+// coarsest-level rows aligned to the propagation segment length, and exchanges one boundary row per column pass (eppm_b200/tiled.py).
+int eppm_set_band(eppm_context* c, int band, int n_bands) {
+    if (!c || n_bands < 1 || band < 0 || band >= n_bands) { set_error("eppm_set_band: bad argument"); return EPPM_ERR_ARG; }
+    const LevelGeom& gc = c->lv[c->n_levels - 1];
+    const int sl = c->prm.prop_seg_length;
+    const int n_seg = (gc.h + sl - 1) / sl;
+    if (n_bands > 1 && n_seg / n_bands < 2) { set_error("eppm_set_band: fewer than two segments per band"); return EPPM_ERR_ARG; }
+    const int base = n_seg / n_bands, extra = n_seg % n_bands;
+    const int s0 = band * base + (band < extra ? band : extra), s1 = s0 + base + (band < extra ? 1 : 0);
+    c->band_y0 = s0 * sl;
+    c->band_y1 = s1 * sl < gc.h ? s1 * sl : gc.h;
+    return EPPM_OK;
+}
+int eppm_band_rows(eppm_context* c, int level, int* y0, int* y1) {
+    if (!c || level < 0 || level >= c->n_levels || !y0 || !y1) return EPPM_ERR_ARG;
+    band_rows(c, level, y0, y1);
+    return EPPM_OK;
+}
+int eppm_tiled_pm_steps(eppm_context* c, int first_step, int end_step) {
+    if (!c || c->n_cur < 1) { set_error("patchmatch before prepare"); return EPPM_ERR_STATE; }
+    cudaSetDevice(c->device);
+    run_patchmatch_dirs(c, 2, end_step, first_step);
+    return cuda_ok(cudaGetLastError(), "tiled patchmatch") ? EPPM_OK : EPPM_ERR_CUDA;
+}
+int eppm_tiled_c2f_step(eppm_context* c, int level, int kind) {
+    if (!c || c->n_cur < 1 || level < 0 || level >= c->n_levels || kind < 0 || kind > 2 || (kind == 0 && level >= c->n_levels - 1)) {
+        set_error("eppm_tiled_c2f_step: bad argument");
+        return EPPM_ERR_ARG;
+    }
+    cudaSetDevice(c->device);
+    run_c2f_step(c, level, kind, nullptr);
+    return cuda_ok(cudaGetLastError(), "tiled c2f") ? EPPM_OK : EPPM_ERR_CUDA;
+}
+void* eppm_device_plane(eppm_context* c, int which, int level) {
+    if (!c || level < 0 || level >= c->n_levels) return nullptr;
+    switch (which) {
+    case EPPM_PLANE_NNF_FWD: case EPPM_PLANE_NNF_BWD: return c->nnf[which - EPPM_PLANE_NNF_FWD];
+    case EPPM_PLANE_COST_FWD: case EPPM_PLANE_COST_BWD: return c->cost[which - EPPM_PLANE_COST_FWD];
+    case EPPM_PLANE_FLOW: return c->flow[level];
+    case EPPM_PLANE_FLOW_TMP: return c->flow_tmp;
+    }
+    return nullptr;
 }
 
 long long eppm_selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits) { return selftest_const_div(d, lo_bits, hi_bits); }

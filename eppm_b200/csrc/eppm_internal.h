@@ -85,6 +85,7 @@ struct eppm_context {
     eppm::CostLut cost_lut;
     eppm::SmoothLut smooth_lut;
     eppm::WmfLut wmf_lut;
+    int band_y0 = 0, band_y1 = 0;                // rows of the coarsest level this context owns (whole level unless tiled across GPUs)
     int smooth_fast_div = 0;                     // set at create time when the constant-division fast path was verified exact
 };
 
@@ -97,7 +98,9 @@ extern unsigned long long g_launches;
 // stage drivers (each enqueues on ctx->stream)
 void run_prepare(eppm_context* c, const uint8_t* d_img1, const uint8_t* d_img2, int n);
 void run_patchmatch(eppm_context* c);
-void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps = 1 << 30);
+void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps = 1 << 30, int first_step = 0);
+void run_c2f_step(eppm_context* c, int level, int kind, float2* out);
+void band_rows(const eppm_context* c, int level, int* y0, int* y1);
 void run_consistency(eppm_context* c);
 void run_c2f(eppm_context* c, float* d_flow_out);
 void build_rng_tables(eppm_context* c);
@@ -111,9 +114,9 @@ void wmf_sweeps(eppm_context* c, short2*& cur, short2*& other, const float4* pix
 void op_fill_holes(cudaStream_t s, const short2* src, short2* dst, const float4* pix, size_t plane, int pw, int w, int h, int n);
 void op_nnf_to_flow(cudaStream_t s, const short2* nnf, float2* flow, int w, int h, int n);
 void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const LevelGeom& g, const float2* coarse, int ws, int hs, int upsample,
-               float2* out, int n);
+               float2* out, int n, int y0 = 0, int y1 = -1);
 long long selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits);
-void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pix1, const LevelGeom& g, int n);
+void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pix1, const LevelGeom& g, int n, int y0 = 0, int y1 = -1);
 void op_preblur_rgba(eppm_context* c, const uchar4* src1, const uchar4* src2, size_t pitch_bytes);
 void op_pyramid_and_pack(eppm_context* c, int n);
 void op_pack_foreign(cudaStream_t s, const uchar4* rgba, size_t rgba_pitch_bytes, const unsigned char* census, size_t census_pitch_bytes, float4* pix,

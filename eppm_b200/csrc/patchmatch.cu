@@ -86,6 +86,7 @@ struct PmArgs {
     float* cost[2];
     int w, h;
     int n_dirs;             // 2: grid.z = pair*2 + direction; 1: forward only (legacy single-direction entry point)
+    int y0, y1;             // row band [y0, y1) this launch owns (whole level unless the frame is tiled across GPUs); segment aligned
 };
 
 template <bool T>
@@ -102,7 +103,7 @@ __device__ __forceinline__ void pm_select(const PmArgs& a, int z, const float4*&
 __global__ void __launch_bounds__(128) k_pm_init(PmArgs a, const short2* __restrict__ rng_init, const __grid_constant__ CostLut lut) {
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y;
     if (x >= a.w) return;
     const float4 *A, *B; short2* nnf; float* cost;
     pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
@@ -120,9 +121,10 @@ __global__ void __launch_bounds__(896) k_pm_propagate(PmArgs a, int seg_len, con
     constexpr bool ROW = (DIR == 0 || DIR == 2), FWD = (DIR < 2);
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
-    const int line = blockIdx.x * blockDim.x + threadIdx.x;
-    const int seg = threadIdx.y;
-    const int n_line = ROW ? a.h : a.w;   // number of scan lines
+    // row passes: the band owns whole scan lines y0..y1-1; column passes: the band owns the segments that lie inside it
+    const int line = (ROW ? a.y0 : 0) + blockIdx.x * blockDim.x + threadIdx.x;
+    const int seg = (ROW ? 0 : a.y0 / seg_len) + threadIdx.y;
+    const int n_line = ROW ? a.y1 : a.w;  // end of the scan lines
     const int len = ROW ? a.w : a.h;      // pixels along a line
     const float4 *A, *B; short2* nnf; float* cost;
     pm_select<ROW>(a, blockIdx.z, A, B, nnf, cost);
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __res
                                                    const __grid_constant__ CostLut lut) {
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y;
     if (x >= a.w) return;
     const float4 *A, *B; short2* nnf; float* cost;
     pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
@@ -206,8 +208,10 @@ __global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __res
 template <int DIR>
 static void launch_propagate(eppm_context* c, const PmArgs& a, int n) {
     const bool row = (DIR == 0 || DIR == 2);
-    const int len = row ? a.w : a.h, n_line = row ? a.h : a.w;
-    const int n_seg = (len + c->prm.prop_seg_length - 1) / c->prm.prop_seg_length;
+    const int sl = c->prm.prop_seg_length;
+    const int n_line = row ? a.y1 - a.y0 : a.w;
+    // segments per line: all of them for row passes; only those inside the band for column passes (bands are segment aligned)
+    const int n_seg = row ? (a.w + sl - 1) / sl : (a.y1 + sl - 1) / sl - a.y0 / sl;
     int lines = 32;  // adjacent scan lines per CTA = coalescing width; all segments of a line stay in one CTA (lock-step barrier)
     while (lines > 1 && lines * n_seg > 896) lines >>= 1;
     dim3 blk(lines, n_seg), grd((n_line + lines - 1) / lines, 1, a.n_dirs * n);
@@ -217,7 +221,7 @@ static void launch_propagate(eppm_context* c, const PmArgs& a, int n) {
 
 void run_patchmatch(eppm_context* c) { run_patchmatch_dirs(c, 2); }
 
-void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps) {
+void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps, int first_step) {
     const int L = c->n_levels - 1, n = c->n_cur;
     const LevelGeom& g = c->lv[L];
     PmArgs a;
@@ -231,21 +235,21 @@ void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps) {
     a.cost[0] = c->cost[0]; a.cost[1] = c->cost[1];
     a.w = g.w; a.h = g.h;
     a.n_dirs = n_dirs;
-    dim3 blk(128), grd((g.w + 127) / 128, g.h, n_dirs * n);
+    a.y0 = c->band_y0; a.y1 = c->band_y1;
+    dim3 blk(128), grd((g.w + 127) / 128, a.y1 - a.y0, n_dirs * n);
+    // steps [first_step, n_steps): 0 = random field + cost, then per iteration 4 propagation passes and 1 random search
     int step = 0;
-    if (step++ >= n_steps) return;
-    k_pm_init<<<grd, blk, 0, c->stream>>>(a, c->rng_init, c->cost_lut);
-    EPPM_LAUNCH_COUNT(1);
-    for (int it = 0; it < c->prm.num_iter; it++) {
-        if (step++ >= n_steps) return;
-        launch_propagate<0>(c, a, n);
-        if (step++ >= n_steps) return;
-        launch_propagate<1>(c, a, n);
-        if (step++ >= n_steps) return;
-        launch_propagate<2>(c, a, n);
-        if (step++ >= n_steps) return;
-        launch_propagate<3>(c, a, n);
-        if (step++ >= n_steps) return;
+    auto run = [&]() { const bool r = step >= first_step && step < n_steps; step++; return r; };
+    if (run()) {
+        k_pm_init<<<grd, blk, 0, c->stream>>>(a, c->rng_init, c->cost_lut);
+        EPPM_LAUNCH_COUNT(1);
+    }
+    for (int it = 0; it < c->prm.num_iter && step < n_steps; it++) {
+        if (run()) launch_propagate<0>(c, a, n);
+        if (run()) launch_propagate<1>(c, a, n);
+        if (run()) launch_propagate<2>(c, a, n);
+        if (run()) launch_propagate<3>(c, a, n);
+        if (!run()) continue;
         k_pm_search<<<grd, blk, 0, c->stream>>>(a, c->rng_search + (size_t)it * c->prm.num_rand_guess * g.w * g.h, c->prm.num_rand_guess,
                                                c->prm.search_range, c->prm.search_radius_min, c->cost_lut);
         EPPM_LAUNCH_COUNT(1);

@@ -56,6 +56,7 @@ struct RefineArgs {
     int ws, hs;
     float2* flow;         // [B][h][w] out
     int upsample;         // 1: coarse is the next-coarser level (x2 upsample fused); 0: coarse is already at this level
+    int y0;               // first row of the band this launch owns (grid.y = rows in the band)
 };
 
 // CTA = 3 warps x 32 pixels: warp m evaluates candidate column m of 32 consecutive pixels of one row (coalesced plane
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine(RefineA
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
     const int m = threadIdx.x >> 5, pl = threadIdx.x & 31;
-    const int x = blockIdx.x * RF_PIX + pl, y = blockIdx.y;
+    const int x = blockIdx.x * RF_PIX + pl, y = a.y0 + blockIdx.y;
     const bool in = x < a.w;
     const int b = blockIdx.z;
     const float4* I1 = a.pix1 + (size_t)b * a.plane;
@@ -191,6 +192,7 @@ struct SmoothArgs {
     int R;
     float neg_sig_r2;   // -(sig_r*sig_r), the divisor nvcc folds `-(d*d)/(SIG_R*SIG_R)` into
     float recip;        // RN(1/neg_sig_r2)
+    int y0, y1;         // row band [y0, y1) this launch owns
     int fast_div;       // 1: x/neg_sig_r2 as q0=x*r, rem=fma(-q0,d,x), q=fma(rem,r,q0) (exactness verified by eppm_selftest_const_div)
 };
 
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(SM_TX* SM_TY) k_flow_smooth(SmoothArgs a, cons
     const int b = blockIdx.z;
     const float2* f = a.src + (size_t)b * a.w * a.h;
     const float4* img = a.pix + (size_t)b * a.plane + (size_t)PAD * a.pw + PAD;
-    const int x0 = blockIdx.x * SM_TX - R, y0 = blockIdx.y * SM_TY * SM_PY - R;
+    const int x0 = blockIdx.x * SM_TX - R, y0 = a.y0 + blockIdx.y * SM_TY * SM_PY - R;
     const int tid = threadIdx.y * SM_TX + threadIdx.x;
     for (int i = tid; i < (R + 1) * (R + 1); i += SM_TX * SM_TY)
         s_gg[i] = __fmul_rn(lut.g[i % (R + 1)], lut.g[i / (R + 1)]);  // cBlfGaussian[|dx|] * cBlfGaussian[|dy|] (:759)
@@ -243,8 +245,8 @@ __global__ void __launch_bounds__(SM_TX* SM_TY) k_flow_smooth(SmoothArgs a, cons
     __syncthreads();
     const int x = blockIdx.x * SM_TX + threadIdx.x;
     const int ly = threadIdx.y * SM_PY;               // local row of the upper pixel
-    const int y = blockIdx.y * SM_TY * SM_PY + ly;
-    if (x >= a.w || y >= a.h) return;
+    const int y = a.y0 + blockIdx.y * SM_TY * SM_PY + ly;
+    if (x >= a.w || y >= a.y1) return;
     const float4 cA = s_pix[(ly + R) * TW + threadIdx.x + R];
     const float4 cB = s_pix[(ly + 1 + R) * TW + threadIdx.x + R];
     const float r = a.recip, nd = -a.neg_sig_r2;
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(SM_TX* SM_TY) k_flow_smooth(SmoothArgs a, cons
     float2 outA = s_flow[(ly + R) * TW + threadIdx.x + R];
     if (wA != 0.f) outA = make_float2(__fdiv_rn(nxA, wA), __fdiv_rn(nyA, wA));  // :790-796 (untouched otherwise)
     a.dst[(size_t)b * a.w * a.h + (size_t)y * a.w + x] = outA;
-    if (y + 1 < a.h) {
+    if (y + 1 < a.y1) {
         float2 outB = s_flow[(ly + 1 + R) * TW + threadIdx.x + R];
         if (wB != 0.f) outB = make_float2(__fdiv_rn(nxB, wB), __fdiv_rn(nyB, wB));
         a.dst[(size_t)b * a.w * a.h + (size_t)(y + 1) * a.w + x] = outB;
@@ -303,7 +305,8 @@ long long selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits) {
 }
 
 void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const LevelGeom& g, const float2* coarse, int ws, int hs, int upsample,
-               float2* out, int n) {
+               float2* out, int n, int y0, int y1) {
+    if (y1 < 0) y1 = g.h;
     RefineArgs a;
     a.pix1 = pix1;
     a.pix2 = pix2;
@@ -311,13 +314,16 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
     a.coarse = coarse; a.ws = ws; a.hs = hs;
     a.flow = out;
     a.upsample = upsample;
-    dim3 blk(RF_PIX * 3), grd((g.w + RF_PIX - 1) / RF_PIX, g.h, n);
+    a.y0 = y0;
+    dim3 blk(RF_PIX * 3), grd((g.w + RF_PIX - 1) / RF_PIX, y1 - y0, n);
     k_c2f_refine<<<grd, blk, 0, c->stream>>>(a, c->cost_lut);
     EPPM_LAUNCH_COUNT(1);
 }
 
-void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pix1, const LevelGeom& g, int n) {
+void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pix1, const LevelGeom& g, int n, int y0, int y1) {
+    if (y1 < 0) y1 = g.h;
     SmoothArgs a;
+    a.y0 = y0; a.y1 = y1;
     a.src = src; a.dst = dst;
     a.pix = pix1;
     a.plane = g.plane; a.pw = g.pw; a.w = g.w; a.h = g.h;
@@ -333,35 +339,48 @@ void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pi
         cudaFuncSetAttribute(k_flow_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    dim3 blk(SM_TX, SM_TY), grd((g.w + SM_TX - 1) / SM_TX, (g.h + SM_TY * SM_PY - 1) / (SM_TY * SM_PY), n);
+    dim3 blk(SM_TX, SM_TY), grd((g.w + SM_TX - 1) / SM_TX, (y1 - y0 + SM_TY * SM_PY - 1) / (SM_TY * SM_PY), n);
     k_flow_smooth<<<grd, blk, smem, c->stream>>>(a, c->smooth_lut);
     EPPM_LAUNCH_COUNT(1);
 }
 
-static void launch_smooth(eppm_context* c, const float2* src, float2* dst, int level, int n) {
-    op_smooth(c, src, dst, c->pix[0][level], c->lv[level], n);
+// rows of level `level` that correspond to the context's band of coarsest-level rows (the last band takes the remainder)
+void band_rows(const eppm_context* c, int level, int* y0, int* y1) {
+    const int L = c->n_levels - 1, sh = L - level;
+    *y0 = c->band_y0 << sh;
+    *y1 = c->band_y1 >= c->lv[L].h ? c->lv[level].h : min(c->lv[level].h, c->band_y1 << sh);
+}
+
+// One step of the coarse-to-fine stage on the context's band: kind 0 = x2 upsample + plane-fitting refine of `level`
+// (flow[level+1] -> flow_tmp), 1 = smoothing flow_tmp -> flow[level], 2 = final smoothing flow[0] -> out (or flow_tmp).
+void run_c2f_step(eppm_context* c, int level, int kind, float2* out) {
+    const int n = c->n_cur;
+    int y0, y1;
+    band_rows(c, level, &y0, &y1);
+    const LevelGeom& g = c->lv[level];
+    if (kind == 0) {
+        const LevelGeom& gs = c->lv[level + 1];
+        if (c->profile && level == 0) cudaEventRecord(c->ev_k[0], c->stream);
+        op_refine(c, c->pix[0][level], c->pix[1][level], g, c->flow[level + 1], gs.w, gs.h, 1, c->flow_tmp, n, y0, y1);
+        if (c->profile && level == 0) cudaEventRecord(c->ev_k[1], c->stream);
+    } else if (kind == 1) {
+        op_smooth(c, c->flow_tmp, c->flow[level], c->pix[0][level], g, n, y0, y1);
+    } else {
+        if (c->profile) cudaEventRecord(c->ev_k[2], c->stream);
+        op_smooth(c, c->flow[0], out ? out : c->flow_tmp, c->pix[0][0], g, n, y0, y1);
+        if (c->profile) cudaEventRecord(c->ev_k[3], c->stream);
+    }
 }
 
 void run_c2f(eppm_context* c, float* d_flow_out) {
-    const int n = c->n_cur;
     for (int level = c->n_levels - 2; level >= 0; level--) {
-        const LevelGeom& g = c->lv[level];
-        const LevelGeom& gs = c->lv[level + 1];
-        if (c->profile && level == 0) cudaEventRecord(c->ev_k[0], c->stream);
-        op_refine(c, c->pix[0][level], c->pix[1][level], g, c->flow[level + 1], gs.w, gs.h, 1, c->flow_tmp, n);
-        if (c->profile && level == 0) cudaEventRecord(c->ev_k[1], c->stream);
-        launch_smooth(c, c->flow_tmp, c->flow[level], level, n);
+        run_c2f_step(c, level, 0, nullptr);
+        run_c2f_step(c, level, 1, nullptr);
     }
     // final smoothing at level 0 (…cuda.cpp:289); with a single level the loop above did not run
     float2* out = reinterpret_cast<float2*>(d_flow_out);
-    if (c->profile) cudaEventRecord(c->ev_k[2], c->stream);
-    if (c->n_levels >= 2) {
-        launch_smooth(c, c->flow[0], out ? out : c->flow_tmp, 0, n);
-        if (!out) cudaMemcpyAsync(c->flow[0], c->flow_tmp, (size_t)n * c->lv[0].w * c->lv[0].h * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream);
-    } else {
-        launch_smooth(c, c->flow[0], out ? out : c->flow_tmp, 0, n);
-    }
-    if (c->profile) cudaEventRecord(c->ev_k[3], c->stream);
+    run_c2f_step(c, 0, 2, out);
+    if (!out) cudaMemcpyAsync(c->flow[0], c->flow_tmp, (size_t)c->n_cur * c->lv[0].w * c->lv[0].h * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream);
 }
 
 }  // namespace eppm

@@ -110,7 +110,8 @@ int eppm_stage_c2f(eppm_context* ctx, float* d_flow);
 enum {
     EPPM_PLANE_RGBA1 = 0, EPPM_PLANE_RGBA2 = 1, EPPM_PLANE_CENSUS1 = 2, EPPM_PLANE_CENSUS2 = 3,
     EPPM_PLANE_NNF_FWD = 4, EPPM_PLANE_NNF_BWD = 5, EPPM_PLANE_COST_FWD = 6, EPPM_PLANE_COST_BWD = 7,
-    EPPM_PLANE_FLOW = 8
+    EPPM_PLANE_FLOW = 8,
+    EPPM_PLANE_FLOW_TMP = 9 /* scratch flow plane (level-0 sized): output of a tiled refine step / of the final smoothing */
 };
 long eppm_read_plane(eppm_context* ctx, int which, int level, int pair, void* host_out);
 
@@ -119,6 +120,24 @@ long eppm_read_plane(eppm_context* ctx, int which, int level, int pair, void* ho
  * (1 = random field + initial cost, then per iteration 4 propagation passes and 1 random search). */
 long eppm_write_plane(eppm_context* ctx, int which, int level, int pair, const void* host_in);
 int eppm_stage_patchmatch_partial(eppm_context* ctx, int n_steps);
+
+/* Spatial tiling of ONE large frame pair across GPUs (one context per GPU, all holding the full frame; batch of 1).
+ *   eppm_set_band(ctx, band, n_bands): this context owns band `band` of `n_bands` row bands of the coarsest level, aligned to the
+ *       propagation segment length so column segments never straddle a band.  (band 0 of 1 = whole frame, the default.)
+ *   eppm_band_rows: the rows [y0, y1) of `level` the band maps to.
+ *   eppm_tiled_pm_steps(ctx, first, end): PatchMatch launch groups [first, end) on the band (numbering of
+ *       eppm_stage_patchmatch_partial: 0 = random field + cost, 1+5*it+k = pass k of iteration it, k = 4 random search).
+ *       Between a row pass and the following column pass the caller copies ONE boundary row of both NNF planes from the
+ *       neighbouring band (row y0-1 before a forward column pass, row y1 before a reverse one) -- the halo exchange.
+ *   eppm_tiled_c2f_step(ctx, level, kind): kind 0 = upsample+refine (-> FLOW_TMP), 1 = smoothing FLOW_TMP -> FLOW[level],
+ *       2 = final smoothing FLOW[0] -> FLOW_TMP, each on the band's rows; the caller all-gathers the written rows in between.
+ *   eppm_device_plane: device address of pair 0 of a plane, for the caller's NCCL / peer copies.
+ * eppm_b200/tiled.py drives this with torch.distributed; results are bit-identical to the untiled run. */
+int eppm_set_band(eppm_context* ctx, int band, int n_bands);
+int eppm_band_rows(eppm_context* ctx, int level, int* y0, int* y1);
+int eppm_tiled_pm_steps(eppm_context* ctx, int first_step, int end_step);
+int eppm_tiled_c2f_step(eppm_context* ctx, int level, int kind);
+void* eppm_device_plane(eppm_context* ctx, int which, int level);
 
 /* Exhaustive device self-test: number of floats x with bit patterns in [lo_bits, hi_bits) for which the 3-instruction
  * constant division (q0 = x*r; q = fma(fma(q0,-d,x), r, q0), r = RN(1/d)) differs from div.rn(x, d); 0 = exact everywhere.

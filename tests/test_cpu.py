@@ -220,3 +220,61 @@ def test_two_rank_sharding_and_timing_reduction_gloo():
         p.join(timeout=60)
     assert [(r[1], r[2]) for r in res] == [(0, 5), (5, 10)]
     assert all(r[3] == 150.0 and r[4] == 10.0 for r in res)
+
+
+# ------------------------------------------------------------------------------------------------ spatial tiling host logic (gloo)
+def test_band_partition_is_segment_aligned():
+    from eppm_b200 import tiled
+    for h, world in ((540, 8), (270, 4), (120, 2), (109, 2)):
+        bands = tiled.band_partition(h, 10, world)
+        assert bands[0][0] == 0 and bands[-1][1] == h
+        assert all(b[0] % 10 == 0 for b in bands) and all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+        assert all(b[1] - b[0] >= 20 or b[1] == h for b in bands)
+        fine = [tiled.level_rows(b, h, 4 * h + 3, 2) for b in bands]
+        assert fine[0][0] == 0 and fine[-1][1] == 4 * h + 3 and all(fine[i][1] == fine[i + 1][0] for i in range(world - 1))
+    with pytest.raises(ValueError):
+        tiled.band_partition(30, 10, 2)
+
+
+def _tiled_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from eppm_b200 import tiled
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    h, w = 60, 7
+    bands = tiled.band_partition(h, 10, world)
+    y0, y1 = bands[rank]
+    plane = torch.full((h, w), -1, dtype=torch.int32)
+    plane[y0:y1] = torch.arange(y0, y1, dtype=torch.int32)[:, None] * 100 + rank  # my rows carry (row, owner)
+    tiled.exchange_boundary_rows([plane], bands, rank, world, +1)
+    fwd_halo = int(plane[y0 - 1, 0]) if rank > 0 else None
+    tiled.exchange_boundary_rows([plane], bands, rank, world, -1)
+    rev_halo = int(plane[y1, 0]) if rank + 1 < world else None
+    tiled.allgather_bands(plane, bands, world)
+    owners = [int(plane[b[0], 0]) % 100 for b in bands]
+    complete = bool((plane[:, 0] // 100 == torch.arange(h, dtype=torch.int32)).all())
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, (y0, y1), fwd_halo, rev_halo, owners, complete))
+
+
+def test_halo_exchange_and_band_gather_gloo():
+    """World-size-2 run of the communication schedule of the spatially tiled path on CPU tensors: the forward column pass sees the
+    last row of the band above, the reverse pass the first row of the band below, and the gather completes every rank's plane."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_tiled_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    (r0, b0, f0, v0, o0, c0), (r1, b1, f1, v1, o1, c1) = res
+    assert b0 == (0, 30) and b1 == (30, 60)
+    assert f0 is None and f1 == 29 * 100 + 0      # rank 1 received row 29 from rank 0
+    assert v0 == 30 * 100 + 1 and v1 is None      # rank 0 received row 30 from rank 1
+    assert o0 == [0, 1] and o1 == [0, 1] and c0 and c1
