@@ -147,6 +147,9 @@ def run_b200(args):
     d = a.shape[0]
     chunk = min(args.chunk, args.batch)
     ctx = E.EppmContext(H, W, chunk, device=local)
+    # optional second context on its own stream: alternate chunks so that one chunk's PatchMatch (L1-bound) can overlap the
+    # other's refine (issue-bound) on the same SMs
+    ctxs = [ctx] + [E.EppmContext(H, W, chunk, device=local) for _ in range(args.streams - 1)]
     # pinned host batch (cycled distinct pairs) and device-resident copy
     idx = [i % d for i in range(args.batch)]
     h_a = torch.empty((args.batch, H, W, 3), dtype=torch.uint8).pin_memory()
@@ -155,13 +158,16 @@ def run_b200(args):
         h_a[i] = torch.from_numpy(a[j]); h_b[i] = torch.from_numpy(b[j])
     h_flow = torch.empty((args.batch, H, W, 2), dtype=torch.float32).pin_memory()
     d_a = h_a.cuda(); d_b = h_b.cuda()
-    d_flow = torch.empty((chunk, H, W, 2), dtype=torch.float32, device="cuda")
+    d_flows = [torch.empty((chunk, H, W, 2), dtype=torch.float32, device="cuda") for _ in ctxs]
     stream = torch.cuda.ExternalStream(ctx.lib.eppm_stream(ctx._ctx))
+    streams = [torch.cuda.ExternalStream(c.lib.eppm_stream(c._ctx)) for c in ctxs]
 
     def step_resident():
-        for s in range(0, args.batch, chunk):
+        for k, s in enumerate(range(0, args.batch, chunk)):
             n = min(chunk, args.batch - s)
-            ctx.compute_batch_device(d_a[s:s + n], d_b[s:s + n], n, d_flow)
+            ctxs[k % len(ctxs)].compute_batch_device(d_a[s:s + n], d_b[s:s + n], n, d_flows[k % len(ctxs)])
+        for k in range(1, len(ctxs)):  # join the extra streams into the timed one
+            ev = torch.cuda.Event(); ev.record(streams[k]); stream.wait_event(ev)
 
     def step_host():
         for s in range(0, args.batch, chunk):
@@ -250,7 +256,7 @@ def cpu_baseline(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import golden
     from eppm_b200 import synth
-    h, w = 128, 224
+    h, w = 192, 320
     a, b, _, _ = synth.make_pair(h, w, 0, scale_to=0.12)
     g = golden.Golden(h, w)
     t0 = time.time()
@@ -324,6 +330,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=16, help="pairs per kernel launch (context max_batch)")
     ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic pairs generated and cycled through the batch")
     ap.add_argument("--ref-sample", type=int, default=8, help="pairs per step for --impl reference")
+    ap.add_argument("--streams", type=int, default=1, help="contexts/streams alternating over the chunks of a step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
