@@ -25,9 +25,13 @@ def pitched(arr, align=512):
     return torch.from_numpy(buf).cuda(), pitch
 
 
+def variant_lib(name):
+    return os.path.join(ROOT, "oracle", "_ref", f"libeppm_ref_{name}.so")
+
+
 class Ref:
-    def __init__(self):
-        lib = C.CDLL(REF_LIB)
+    def __init__(self, lib_path=None):
+        lib = C.CDLL(lib_path or REF_LIB)
         P, I, S = C.c_void_p, C.c_int, C.c_size_t
         lib.ref_create.restype = P; lib.ref_create.argtypes = [I, I]
         lib.ref_destroy.argtypes = [P]
@@ -77,6 +81,9 @@ class Ref:
         h, w = C.c_int(), C.c_int()
         self.lib.ref_level_dims(ctx, level, C.byref(h), C.byref(w))
         return h.value, w.value
+
+    def num_levels(self, ctx):
+        return self.lib.ref_num_levels(ctx)
 
     def read_plane(self, ctx, which, level):
         h, w = self.level_dims(ctx, level)

@@ -397,3 +397,44 @@ def test_philox_mode_epe_delta(ref):
     e_ref, e_me = synth.epe(fr, gt, valid), synth.epe(fm, gt, valid)
     assert e_me <= e_ref + 0.05, (e_me, e_ref)
     ref.destroy(rc); ctx.close()
+
+
+@pytest.mark.parametrize("name,depth,iters", [("d2i5", 2, 5), ("d4i2", 4, 2)])
+def test_non_default_depth_and_iterations_vs_reference_variants(name, depth, iters):
+    """BASELINE config 5 sweeps pyramid depth x propagation iterations.  The reference fixes both as macros, so oracle/Makefile
+    rebuilds it per sweep point (`make variants`); here they are run-time parameters.  Pyramid/census and the whole PatchMatch
+    must stay bit-exact, the final flow as accurate against ground truth."""
+    path = refharness.variant_lib(name)
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not built")
+    ref = refharness.Ref(path)
+    h, w = 480, 640
+    a, b, gt, valid = synth.make_pair(h, w, 4)
+    rc = ref.create(h, w)
+    assert ref.num_levels(rc) == depth
+    ref.set_data(rc, a, b)
+    p = E.default_params()
+    p.pyr_levels, p.num_iter = depth, iters
+    ctx = E.EppmContext(h, w, 1, params=p)
+    ctx.stage_prepare(dev(a[None]), dev(b[None]), 1)
+    planes = {}
+    for l in range(depth):
+        assert ctx.level_dims(l) == ref.level_dims(rc, l)
+        for which in (0, 1, 2, 3):
+            planes[(which, l)] = ref.read_plane(rc, which, l)
+            assert same_bits(ctx.read_plane(which, l), planes[(which, l)]), (which, l)
+    L = depth - 1
+    hc, wc = ctx.level_dims(L)
+    i1, i2 = refharness.pitched(planes[(0, L)]), refharness.pitched(planes[(1, L)])
+    c1, c2 = refharness.pitched(planes[(2, L)]), refharness.pitched(planes[(3, L)])
+    nf, cf = ref.tap_patchmatch(i1, i2, c1, c2, wc, hc, 1000)
+    nb, cb = ref.tap_patchmatch(i2, i1, c2, c1, wc, hc, 1000)
+    ctx.stage_patchmatch()
+    assert same_bits(ctx.read_plane(E.PLANE_NNF_FWD), nf) and same_bits(ctx.read_plane(E.PLANE_NNF_BWD), nb)
+    assert same_bits(ctx.read_plane(E.PLANE_COST_FWD), cf) and same_bits(ctx.read_plane(E.PLANE_COST_BWD), cb)
+    fr = ref.compute_flow(rc, h, w)
+    fm = ctx.compute_batch_host(a[None], b[None])[0]
+    # with a 60x80 coarsest level and 2 iterations most coarse pixels are re-filled by the (racy, in the reference) weighted median;
+    # the bar is "no worse against ground truth than the reference" (measured: 2.28 px here vs 2.51 px reference at depth 4)
+    assert synth.epe(fm, gt, valid) <= synth.epe(fr, gt, valid) + 0.05
+    ref.destroy(rc); ctx.close()
