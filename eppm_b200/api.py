@@ -11,7 +11,7 @@ import numpy as np
 from . import _lib
 
 PLANE_RGBA1, PLANE_RGBA2, PLANE_CENSUS1, PLANE_CENSUS2 = 0, 1, 2, 3
-PLANE_NNF_FWD, PLANE_NNF_BWD, PLANE_COST_FWD, PLANE_COST_BWD, PLANE_FLOW = 4, 5, 6, 7, 8
+PLANE_NNF_FWD, PLANE_NNF_BWD, PLANE_COST_FWD, PLANE_COST_BWD, PLANE_FLOW, PLANE_FLOW_TMP = 4, 5, 6, 7, 8, 9
 
 
 class EppmError(RuntimeError):
@@ -118,13 +118,17 @@ class EppmContext:
             PLANE_CENSUS1: ((h, w), np.uint8), PLANE_CENSUS2: ((h, w), np.uint8),
             PLANE_NNF_FWD: ((h, w, 2), np.int16), PLANE_NNF_BWD: ((h, w, 2), np.int16),
             PLANE_COST_FWD: ((h, w), np.float32), PLANE_COST_BWD: ((h, w), np.float32),
-            PLANE_FLOW: ((h, w, 2), np.float32),
+            PLANE_FLOW: ((h, w, 2), np.float32), PLANE_FLOW_TMP: ((h, w, 2), np.float32),
         }[which]
         out = np.empty(shape, dt)
         n = self.lib.eppm_read_plane(self._ctx, which, level, pair, out.ctypes.data)
         if n != out.nbytes:
             raise EppmError(f"eppm_read_plane returned {n}: {self.lib.eppm_last_error().decode()}")
         return out
+
+    def c2f_step(self, level, kind):
+        """One coarse-to-fine step on the context's band: 0 = upsample + refine (-> FLOW_TMP), 1 = smoothing, 2 = final smoothing."""
+        self._check(self.lib.eppm_tiled_c2f_step(self._ctx, level, kind), "eppm_tiled_c2f_step")
 
     def last_stage_ms(self):
         buf = (C.c_float * 5)()

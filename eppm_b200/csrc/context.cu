@@ -99,7 +99,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
     c->h = h; c->w = w; c->max_batch = max_batch;
     if (params) c->prm = *params; else eppm_default_params(&c->prm);
     const eppm_params& p = c->prm;
-    if (p.pyr_levels < 1 || p.pyr_levels > MAX_LEVELS || p.patch_r != 9 || p.patch_stride != 2 || p.wmf_radius != 4 || p.num_iter < 0 ||
+    if (p.pyr_levels < 1 || p.pyr_levels > MAX_LEVELS || p.patch_r != 9 || p.patch_stride < 1 || p.patch_stride > 3 || p.wmf_radius != 4 || p.num_iter < 0 ||
         p.num_rand_guess < 0 || p.num_rand_guess > 16 || p.prop_seg_length < 1 || p.blf_sig_s < 1 || p.blf_sig_s > 10 || p.stat_radius < 0 ||
         p.stat_radius > 16 || (p.rng_mode != EPPM_RNG_XORWOW && p.rng_mode != EPPM_RNG_PHILOX) || p.lambda_ad != 0.1f || p.pm_sig_r != 0.1f) {
         set_error("eppm_create: parameter combination not supported by this build");
@@ -346,6 +346,10 @@ long eppm_read_plane(eppm_context* c, int which, int level, int pair, void* host
     case EPPM_PLANE_FLOW:
         bytes = n * 8;
         e = cudaMemcpy(host_out, c->flow[level] + pair * n, bytes, cudaMemcpyDeviceToHost);
+        break;
+    case EPPM_PLANE_FLOW_TMP:  // scratch plane, laid out with the dims of `level` by the step that wrote it
+        bytes = n * 8;
+        e = cudaMemcpy(host_out, c->flow_tmp + pair * n, bytes, cudaMemcpyDeviceToHost);
         break;
     default:
         return EPPM_ERR_ARG;

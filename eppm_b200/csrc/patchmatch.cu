@@ -100,6 +100,7 @@ __device__ __forceinline__ void pm_select(const PmArgs& a, int z, const float4*&
 }
 
 // Random field + initial cost (d_gen_rand_field + d_compute_cost_field).
+template <int STRIDE>
 __global__ void __launch_bounds__(128) k_pm_init(PmArgs a, const short2* __restrict__ rng_init, const __grid_constant__ CostLut lut) {
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
@@ -109,14 +110,14 @@ __global__ void __launch_bounds__(128) k_pm_init(PmArgs a, const short2* __restr
     pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
     const short2 t = rng_init[y * a.w + x];
     nnf[y * a.w + x] = t;
-    cost[y * a.w + x] = patch_cost<2, false>(A, B, a.pw, x, y, t.x, t.y, lut, s_census);
+    cost[y * a.w + x] = patch_cost<STRIDE, false>(A, B, a.pw, x, y, t.x, t.y, lut, s_census);
 }
 
 // Segment propagation, the four passes of baoSegPropagate.  DIR: 0 row forward, 1 column forward, 2 row reverse,
 // 3 column reverse.  blockDim = (lines per CTA, all segments of a line); every thread owns one (line, segment).
 // Lanes of a warp are ADJACENT scan lines working on the same position along the line: column passes read the
 // row-major planes, row passes the column-major copies, so both sides of every sample are coalesced.
-template <int DIR>
+template <int DIR, int STRIDE>
 __global__ void __launch_bounds__(896) k_pm_propagate(PmArgs a, int seg_len, const __grid_constant__ CostLut lut) {
     constexpr bool ROW = (DIR == 0 || DIR == 2), FWD = (DIR < 2);
     __shared__ float s_census[CENSUS_LUT_N];
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(896) k_pm_propagate(PmArgs a, int seg_len, con
             if (DIR == 2) prev.x = max(prev.x - 1, 0);
             if (DIR == 3) prev.y = max(prev.y - 1, 0);
             const int x1 = ROW ? i : line, y1 = ROW ? line : i;
-            const float cv = patch_cost<2, ROW>(A, B, pitch, x1, y1, prev.x, prev.y, lut, s_census);
+            const float cv = patch_cost<STRIDE, ROW>(A, B, pitch, x1, y1, prev.x, prev.y, lut, s_census);
             if (cv < cur_best) {
                 nnf[id] = prev;
                 cost[id] = cv;
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(896) k_pm_propagate(PmArgs a, int seg_len, con
 
 // Random search (d_update_random_guess): num_guess candidates drawn in windows of radius 30,15,7,3,1,1 around the
 // ENTRY best target, evaluated in order with strict '<'.
+template <int STRIDE>
 __global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __restrict__ rng, int num_guess, int search_range, int radius_min,
                                                    const __grid_constant__ CostLut lut) {
     __shared__ float s_census[CENSUS_LUT_N];
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __res
         const short gx = (short)(xmin + r1 % (unsigned)(xmax - xmin));
         const short gy = (short)(ymin + r2 % (unsigned)(ymax - ymin));
         if (mag / 2 >= radius_min) mag /= 2;
-        const float cv = patch_cost<2, false>(A, B, a.pw, x, y, gx, gy, lut, s_census);
+        const float cv = patch_cost<STRIDE, false>(A, B, a.pw, x, y, gx, gy, lut, s_census);
         if (cv < best_cost) {
             best = make_short2(gx, gy);
             best_cost = cv;
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __res
     cost[id] = best_cost;
 }
 
-template <int DIR>
+template <int DIR, int STRIDE>
 static void launch_propagate(eppm_context* c, const PmArgs& a, int n) {
     const bool row = (DIR == 0 || DIR == 2);
     const int sl = c->prm.prop_seg_length;
@@ -215,13 +217,26 @@ static void launch_propagate(eppm_context* c, const PmArgs& a, int n) {
     int lines = 32;  // adjacent scan lines per CTA = coalescing width; all segments of a line stay in one CTA (lock-step barrier)
     while (lines > 1 && lines * n_seg > 896) lines >>= 1;
     dim3 blk(lines, n_seg), grd((n_line + lines - 1) / lines, 1, a.n_dirs * n);
-    k_pm_propagate<DIR><<<grd, blk, 0, c->stream>>>(a, c->prm.prop_seg_length, c->cost_lut);
+    k_pm_propagate<DIR, STRIDE><<<grd, blk, 0, c->stream>>>(a, c->prm.prop_seg_length, c->cost_lut);
     EPPM_LAUNCH_COUNT(1);
 }
 
 void run_patchmatch(eppm_context* c) { run_patchmatch_dirs(c, 2); }
 
+template <int STRIDE>
+static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first_step);
+
 void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps, int first_step) {
+    // the sample stride of the patch ("pixel skipping", bao_pmflow_kernel.cu:269,272) is a compile-time constant of the kernels
+    switch (c->prm.patch_stride) {
+    case 1: run_patchmatch_t<1>(c, n_dirs, n_steps, first_step); break;
+    case 3: run_patchmatch_t<3>(c, n_dirs, n_steps, first_step); break;
+    default: run_patchmatch_t<2>(c, n_dirs, n_steps, first_step); break;
+    }
+}
+
+template <int STRIDE>
+static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first_step) {
     const int L = c->n_levels - 1, n = c->n_cur;
     const LevelGeom& g = c->lv[L];
     PmArgs a;
@@ -241,16 +256,16 @@ void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps, int first_ste
     int step = 0;
     auto run = [&]() { const bool r = step >= first_step && step < n_steps; step++; return r; };
     if (run()) {
-        k_pm_init<<<grd, blk, 0, c->stream>>>(a, c->rng_init, c->cost_lut);
+        k_pm_init<STRIDE><<<grd, blk, 0, c->stream>>>(a, c->rng_init, c->cost_lut);
         EPPM_LAUNCH_COUNT(1);
     }
     for (int it = 0; it < c->prm.num_iter && step < n_steps; it++) {
-        if (run()) launch_propagate<0>(c, a, n);
-        if (run()) launch_propagate<1>(c, a, n);
-        if (run()) launch_propagate<2>(c, a, n);
-        if (run()) launch_propagate<3>(c, a, n);
+        if (run()) launch_propagate<0, STRIDE>(c, a, n);
+        if (run()) launch_propagate<1, STRIDE>(c, a, n);
+        if (run()) launch_propagate<2, STRIDE>(c, a, n);
+        if (run()) launch_propagate<3, STRIDE>(c, a, n);
         if (!run()) continue;
-        k_pm_search<<<grd, blk, 0, c->stream>>>(a, c->rng_search + (size_t)it * c->prm.num_rand_guess * g.w * g.h, c->prm.num_rand_guess,
+        k_pm_search<STRIDE><<<grd, blk, 0, c->stream>>>(a, c->rng_search + (size_t)it * c->prm.num_rand_guess * g.w * g.h, c->prm.num_rand_guess,
                                                c->prm.search_range, c->prm.search_radius_min, c->cost_lut);
         EPPM_LAUNCH_COUNT(1);
     }

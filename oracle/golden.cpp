@@ -53,6 +53,7 @@ inline float max3abs(const F3& a, const F3& b) {
 struct golden_ctx {
     int n_levels, num_iter;
     int num_guess = 6, search_range = 30, radius_min = 1, seg_len = 10;  // defs.h:36-38, bao_pmflow_kernel.cu:979
+    int stride = 2;  // sample stride of the patch loops (bao_pmflow_kernel.cu:269,272)
     std::vector<Level> lv;
     std::vector<S2> nnf[2], rng_init, rng_search;
     std::vector<float> cost[2];
@@ -279,8 +280,8 @@ inline void sample(const golden_ctx* c, const F3& p1, uint8_t cen1, const F3& p2
 float patch_cost(const golden_ctx* c, const Level& L, int A, int B, int x1, int y1, int x2, int y2) {
     const F3 c1 = L.C(A, x1, y1), c2 = L.C(B, x2, y2);
     float cs = 0.f, ws = 0.f;
-    for (int i = -PATCH_R; i <= PATCH_R; i += 2)
-        for (int j = -PATCH_R; j <= PATCH_R; j += 2)
+    for (int i = -PATCH_R; i <= PATCH_R; i += c->stride)
+        for (int j = -PATCH_R; j <= PATCH_R; j += c->stride)
             sample(c, L.C(A, x1 + j, y1 + i), L.Cen(A, x1 + j, y1 + i), L.C(B, x2 + j, y2 + i), L.Cen(B, x2 + j, y2 + i), c1, c2, abs(i), abs(j), cs, ws);
     return cs / ws;
 }
@@ -294,8 +295,8 @@ float patch_cost_pf(const golden_ctx* c, const Level& L, int x1, int y1, int x2,
     float best = 0.f;
     for (int q = 0; q < 4; q++) {
         float cs = 0.f, ws = 0.f;
-        for (int i = -PATCH_R; i <= PATCH_R; i += 2)
-            for (int j = -PATCH_R; j <= PATCH_R; j += 2) {
+        for (int i = -PATCH_R; i <= PATCH_R; i += c->stride)
+            for (int j = -PATCH_R; j <= PATCH_R; j += c->stride) {
                 float cx2 = (float)(x1 + j) + uu, cy2 = (float)(y1 + i) + vv;
                 if (q > 0) {
                     cx2 = fmaf((float)i, kPF[q - 1][1], fmaf((float)j, kPF[q - 1][0], cx2));
@@ -618,6 +619,7 @@ golden_ctx* golden_create(int h, int w, int levels, int num_iter) {
     return c;
 }
 void golden_destroy(golden_ctx* c) { delete c; }
+void golden_set_stride(golden_ctx* c, int stride) { c->stride = stride; }
 int golden_num_levels(const golden_ctx* c) { return c->n_levels; }
 void golden_level_dims(const golden_ctx* c, int level, int* h, int* w) { *h = c->lv[level].h; *w = c->lv[level].w; }
 

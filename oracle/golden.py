@@ -21,6 +21,7 @@ def lib():
         P, I = C.c_void_p, C.c_int
         l.golden_create.restype = P; l.golden_create.argtypes = [I, I, I, I]
         l.golden_destroy.argtypes = [P]
+        l.golden_set_stride.argtypes = [P, I]
         l.golden_num_levels.argtypes = [P]
         l.golden_level_dims.argtypes = [P, I, C.POINTER(I), C.POINTER(I)]
         l.golden_prepare.argtypes = [P, P, P]
@@ -50,10 +51,11 @@ def level_dims_for(h, w, level):
 
 
 class Golden:
-    def __init__(self, h, w, levels=3, num_iter=10):
+    def __init__(self, h, w, levels=3, num_iter=10, stride=2):
         self.l = lib()
         self.h, self.w = h, w
         self.ctx = self.l.golden_create(h, w, levels, num_iter)
+        self.l.golden_set_stride(self.ctx, stride)
         self.num_levels = levels
 
     def __del__(self):

@@ -438,3 +438,54 @@ def test_non_default_depth_and_iterations_vs_reference_variants(name, depth, ite
     # the bar is "no worse against ground truth than the reference" (measured: 2.28 px here vs 2.51 px reference at depth 4)
     assert synth.epe(fm, gt, valid) <= synth.epe(fr, gt, valid) + 0.05
     ref.destroy(rc); ctx.close()
+
+
+@pytest.mark.parametrize("name,stride", [("s3", 3), ("s1", 1)])
+def test_patch_stride_variants_bit_exact(name, stride):
+    """Third axis of BASELINE config 5: the sample stride of the 19x19 patch ("pixel skipping", bao_pmflow_kernel.cu:269,272; 2 upstream).
+    Against the reference rebuilt with stride 3 / 1 (`make -C oracle variants`): the whole PatchMatch and the upsample + plane-fitting
+    refine of both finer levels are bit-exact."""
+    path = refharness.variant_lib(name)
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not built")
+    ref = refharness.Ref(path)
+    h, w = (240, 320) if stride == 1 else (480, 640)
+    a, b, gt, valid = synth.make_pair(h, w, 6, scale_to=0.25)
+    rc = ref.create(h, w)
+    ref.set_data(rc, a, b)
+    p = E.default_params()
+    p.patch_stride = stride
+    ctx = E.EppmContext(h, w, 1, params=p)
+    ctx.stage_prepare(dev(a[None]), dev(b[None]), 1)
+    dims = [ref.level_dims(rc, l) for l in range(3)]
+    img = [[refharness.pitched(ref.read_plane(rc, k, l)) for l in range(3)] for k in (0, 1)]
+    cen = [[refharness.pitched(ref.read_plane(rc, 2 + k, l)) for l in range(3)] for k in (0, 1)]
+    hc, wc = dims[2]
+    nf, cf = ref.tap_patchmatch(img[0][2], img[1][2], cen[0][2], cen[1][2], wc, hc, 1000)
+    nb, cb = ref.tap_patchmatch(img[1][2], img[0][2], cen[1][2], cen[0][2], wc, hc, 1000)
+    ctx.stage_patchmatch()
+    assert same_bits(ctx.read_plane(E.PLANE_NNF_FWD), nf) and same_bits(ctx.read_plane(E.PLANE_NNF_BWD), nb)
+    assert same_bits(ctx.read_plane(E.PLANE_COST_FWD), cf) and same_bits(ctx.read_plane(E.PLANE_COST_BWD), cb)
+    # refine: reference's own coarse flow in, upsample + plane-fitting refine out, per level
+    fr = ref.compute_flow(rc, h, w)
+    nl = 3
+    PtrArr, IntArr, SzArr = C.c_void_p * nl, C.c_int * nl, C.c_size_t * nl
+    ref.lib.baoCudaBLF_C2F.argtypes = [C.c_void_p] * 11 + [C.c_int]
+    ref.lib.baoCudaBLF_C2F.restype = None
+    for l in (1, 0):
+        coarse = ref.read_plane(rc, 8, l + 1)
+        hl, wl = dims[l]
+        flows = [None] * nl
+        flows[l] = torch.zeros((hl, wl, 2), dtype=torch.float32, device="cuda")
+        flows[l + 1] = dev(coarse)
+        ref.lib.baoCudaBLF_C2F(PtrArr(*[P(x) if x is not None else None for x in flows]), PtrArr(*[P(img[0][k][0]) for k in range(nl)]),
+                               PtrArr(*[P(img[1][k][0]) for k in range(nl)]), PtrArr(*[P(cen[0][k][0]) for k in range(nl)]),
+                               PtrArr(*[P(cen[1][k][0]) for k in range(nl)]), None, None, IntArr(*[d[0] for d in dims]), IntArr(*[d[1] for d in dims]),
+                               SzArr(*[img[0][k][1] for k in range(nl)]), SzArr(*[cen[0][k][1] for k in range(nl)]), l)
+        torch.cuda.synchronize()
+        ctx.write_plane(E.PLANE_FLOW, coarse, level=l + 1)
+        ctx.c2f_step(l, 0)
+        assert same_bits(ctx.read_plane(E.PLANE_FLOW_TMP, l), flows[l].cpu().numpy()), f"refine differs at level {l}"
+    fm = ctx.compute_batch_host(a[None], b[None])[0]
+    assert synth.epe(fm, gt, valid) <= synth.epe(fr, gt, valid) + 0.05
+    ref.destroy(rc); ctx.close()
