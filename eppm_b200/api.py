@@ -73,7 +73,8 @@ class EppmContext:
 
     # --- whole pipeline ------------------------------------------------------------------------------
     def compute_batch_host(self, img1, img2, out=None):
-        """img1, img2: uint8 [n,h,w,3] host arrays (numpy or pinned torch); returns float32 [n,h,w,2] (u,v)."""
+        """img1, img2: uint8 [n,h,w,3] host arrays (numpy or pinned torch); returns float32 [n,h,w,2] (u,v).
+        n may exceed max_batch (chunked, copies overlapped with compute inside the library)."""
         n = int(img1.shape[0])
         if out is None:
             out = np.empty((n, self.h, self.w, 2), np.float32)

@@ -127,6 +127,11 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev_k[i]);
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming);
+    }
 
     // ---- arena: two passes (measure, then carve) ----
     const size_t B = max_batch;
@@ -140,6 +145,8 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         }
         for (int img = 0; img < 2; img++) c->d_rgb[img] = A.take<uint8_t>(B * h * w * 3);
         c->d_flow_out = A.take<float>(B * h * w * 2);
+        for (int img = 0; img < 2; img++) c->d_rgb_alt[img] = A.take<uint8_t>(B * h * w * 3);
+        c->d_flow_out_alt = A.take<float>(B * h * w * 2);
         for (int i = 0; i < c->n_levels; i++)
             for (int img = 0; img < 2; img++) {
                 c->rgba[img][i] = A.take<uchar4>(B * c->lv[i].w * c->lv[i].h);
@@ -202,6 +209,11 @@ void eppm_destroy(eppm_context* c) {
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 4; i++)
         if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+    for (int i = 0; i < 2; i++) {
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+        if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -296,18 +308,39 @@ int eppm_last_kernel_ms(eppm_context* c, int which, float* ms) {
     return cuda_ok(cudaEventElapsedTime(ms, c->ev_k[2 * which], c->ev_k[2 * which + 1]), "event elapsed") ? EPPM_OK : EPPM_ERR_CUDA;
 }
 
+// Host-buffer entry point.  n may exceed max_batch: the batch is processed in chunks of max_batch pairs, double buffered --
+// while chunk k computes on the context's stream, chunk k+1 is uploaded and chunk k-1's flow is downloaded on the copy stream
+// (true overlap needs pinned host memory; pageable memory still works, the copies then serialise on the host).
 int eppm_compute_batch_host(eppm_context* c, const uint8_t* img1, const uint8_t* img2, int n, float* flow) {
-    int rc = check_batch(c, img1, img2, n);
-    if (rc) return rc;
+    if (!c || !img1 || !img2 || n < 1) { set_error("bad argument (null pointer or empty batch)"); return EPPM_ERR_ARG; }
     if (!flow) { set_error("null output"); return EPPM_ERR_ARG; }
-    const size_t in_bytes = (size_t)n * c->h * c->w * 3, out_bytes = (size_t)n * c->h * c->w * 2 * sizeof(float);
-    cudaStream_t s = c->stream;
-    // Pageable or pinned host memory both work; pinned buffers make the copies truly asynchronous.
-    if (!cuda_ok(cudaMemcpyAsync(c->d_rgb[0], img1, in_bytes, cudaMemcpyHostToDevice, s), "H2D img1")) return EPPM_ERR_CUDA;
-    if (!cuda_ok(cudaMemcpyAsync(c->d_rgb[1], img2, in_bytes, cudaMemcpyHostToDevice, s), "H2D img2")) return EPPM_ERR_CUDA;
-    rc = eppm_compute_batch_device(c, c->d_rgb[0], c->d_rgb[1], n, c->d_flow_out);
-    if (rc) return rc;
-    if (!cuda_ok(cudaMemcpyAsync(flow, c->d_flow_out, out_bytes, cudaMemcpyDeviceToHost, s), "D2H flow")) return EPPM_ERR_CUDA;
+    cudaSetDevice(c->device);
+    const size_t px = (size_t)c->h * c->w;
+    cudaStream_t s = c->stream, cs = c->copy_stream;
+    uint8_t* in[2][2] = {{c->d_rgb[0], c->d_rgb[1]}, {c->d_rgb_alt[0], c->d_rgb_alt[1]}};
+    float* out[2] = {c->d_flow_out, c->d_flow_out_alt};
+    const int B = c->max_batch, n_chunks = (n + B - 1) / B;
+    auto upload = [&](int k) {
+        const int off = k * B, m = n - off < B ? n - off : B, slot = k & 1;
+        if (k >= 2) cudaStreamWaitEvent(cs, c->ev_done[slot], 0);  // the chunk that used this slot has consumed its inputs
+        cudaMemcpyAsync(in[slot][0], img1 + (size_t)off * px * 3, (size_t)m * px * 3, cudaMemcpyHostToDevice, cs);
+        cudaMemcpyAsync(in[slot][1], img2 + (size_t)off * px * 3, (size_t)m * px * 3, cudaMemcpyHostToDevice, cs);
+        cudaEventRecord(c->ev_h2d[slot], cs);
+    };
+    upload(0);
+    for (int k = 0; k < n_chunks; k++) {
+        const int off = k * B, m = n - off < B ? n - off : B, slot = k & 1;
+        cudaStreamWaitEvent(s, c->ev_h2d[slot], 0);
+        if (k >= 2) cudaStreamWaitEvent(s, c->ev_d2h[slot], 0);  // the previous result in this slot has left the device
+        int rc = eppm_compute_batch_device(c, in[slot][0], in[slot][1], m, out[slot]);
+        if (rc) return rc;
+        cudaEventRecord(c->ev_done[slot], s);
+        if (k + 1 < n_chunks) upload(k + 1);
+        cudaStreamWaitEvent(cs, c->ev_done[slot], 0);
+        cudaMemcpyAsync(flow + (size_t)off * px * 2, out[slot], (size_t)m * px * 2 * sizeof(float), cudaMemcpyDeviceToHost, cs);
+        cudaEventRecord(c->ev_d2h[slot], cs);
+    }
+    if (!cuda_ok(cudaStreamSynchronize(cs), "compute_batch_host (copy stream)")) return EPPM_ERR_CUDA;
     return cuda_ok(cudaStreamSynchronize(s), "compute_batch_host") ? EPPM_OK : EPPM_ERR_CUDA;
 }
 

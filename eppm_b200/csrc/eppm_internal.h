@@ -63,6 +63,9 @@ struct eppm_context {
     // inputs staged on the device for the host-buffer API
     uint8_t* d_rgb[2] = {nullptr, nullptr};      // [B][h][w][3]
     float* d_flow_out = nullptr;                 // [B][h][w][2]
+    uint8_t* d_rgb_alt[2] = {nullptr, nullptr};  // second staging set: chunk k+1 uploads while chunk k computes
+    float* d_flow_out_alt = nullptr;
+    cudaEvent_t ev_h2d[2] = {}, ev_done[2] = {}, ev_d2h[2] = {};
     uint8_t* h_pinned_in[2] = {nullptr, nullptr};
     float* h_pinned_out = nullptr;
     // pyramid

@@ -79,6 +79,8 @@ int eppm_level_dims(const eppm_context* ctx, int level, int* h, int* w);
 /* One batch, HOST buffers (the call a user of the reference's class makes, batched):
  *   img1,img2 : [n][h][w][3] u8 interleaved RGB (bao_alloc layout, main.cpp:42-57)
  *   flow      : [n][h][w][2] f32 interleaved (u,v) — what compute_flow returns as u[][] / v[][]
+ * n may exceed max_batch: the batch is then processed in chunks of max_batch pairs with the upload of chunk k+1 and the
+ * download of chunk k-1 overlapped with the compute of chunk k (pinned host memory recommended).
  * H2D, all stages, D2H; returns after the result is in `flow`.
  * Replaces set_data + compute_flow (…cuda.cpp:159-168,217-306). */
 int eppm_compute_batch_host(eppm_context* ctx, const uint8_t* img1, const uint8_t* img2, int n, float* flow);

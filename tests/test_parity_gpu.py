@@ -303,6 +303,15 @@ def test_batch_equals_single_pairs_and_is_deterministic():
     ctx1.close(); ctx3.close()
 
 
+def test_host_api_chunks_batches_larger_than_max_batch():
+    h, w = 192, 256
+    i1, i2, _, _ = synth.make_batch(h, w, 5, first_idx=40)
+    ctx2 = E.EppmContext(h, w, 2)   # 5 pairs through a context of 2: chunks 2+2+1, double buffered
+    ctx5 = E.EppmContext(h, w, 5)
+    assert same_bits(ctx2.compute_batch_host(i1, i2), ctx5.compute_batch_host(i1, i2))
+    ctx2.close(); ctx5.close()
+
+
 def test_device_api_equals_host_api_and_class_mirror():
     h, w = 192, 256
     i1, i2, _, _ = synth.make_batch(h, w, 2, first_idx=30)
@@ -325,7 +334,8 @@ def test_error_behaviour():
         E.EppmContext(2, 2, 1)  # coarsest pyramid level would be empty
     ctx = E.EppmContext(96, 128, 1)
     with pytest.raises(E.EppmError):
-        ctx.compute_batch_host(np.zeros((2, 96, 128, 3), np.uint8), np.zeros((2, 96, 128, 3), np.uint8))  # batch > max_batch
+        ctx.compute_batch_device(dev(np.zeros((2, 96, 128, 3), np.uint8)), dev(np.zeros((2, 96, 128, 3), np.uint8)), 2,
+                                 torch.zeros((2, 96, 128, 2), device="cuda"))  # device API: batch > max_batch
     with pytest.raises(E.EppmError):
         E.EppmContext(96, 128, 1).stage_patchmatch()  # before prepare
     ctx.close()
