@@ -30,6 +30,7 @@ EPPM_SYMBOLS = {
     "eppm_level_dims": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "eppm_compute_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "eppm_compute_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "eppm_compute_stream_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "eppm_synchronize": (C.c_int, [C.c_void_p]),
     "eppm_stream": (C.c_void_p, [C.c_void_p]),
     "eppm_stage_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

@@ -85,6 +85,10 @@ class EppmContext:
         """Device-resident tensors / raw device addresses; stream-ordered, returns without synchronising."""
         self._check(self.lib.eppm_compute_batch_device(self._ctx, _ptr(d_img1), _ptr(d_img2), n, _ptr(d_flow)), "eppm_compute_batch_device")
 
+    def compute_stream_device(self, d_frames, n_pairs, d_flow):
+        """Consecutive pairs of a frame list [n_pairs+1,h,w,3] (device); each frame is prepared once."""
+        self._check(self.lib.eppm_compute_stream_device(self._ctx, _ptr(d_frames), n_pairs, _ptr(d_flow)), "eppm_compute_stream_device")
+
     def synchronize(self):
         self._check(self.lib.eppm_synchronize(self._ctx), "eppm_synchronize")
 

@@ -292,6 +292,32 @@ int eppm_compute_batch_device(eppm_context* c, const uint8_t* d_img1, const uint
     return cuda_ok(cudaGetLastError(), "compute_batch") ? EPPM_OK : EPPM_ERR_CUDA;
 }
 
+// Video stream: n_pairs consecutive pairs (frame f, frame f+1) of a list of n_pairs+1 frames; every frame's
+// pyramid / census / packed planes are built once and shared by the two pairs it belongs to.
+int eppm_compute_stream_device(eppm_context* c, const uint8_t* d_frames, int n_pairs, float* d_flow) {
+    if (!c || !d_frames || !d_flow || n_pairs < 1 || n_pairs + 1 > c->max_batch) {
+        set_error("bad argument (null pointer, or n_pairs + 1 frames exceed max_batch)");
+        return EPPM_ERR_ARG;
+    }
+    cudaSetDevice(c->device);
+    run_prepare_frames(c, d_frames, n_pairs + 1);
+    // image 2 of pair f is frame f+1: alias the image-2 plane bases one plane behind the image-1 bases for this call
+    float4* keep_pix[MAX_LEVELS];
+    float4* keep_pixT = c->pixT[1];
+    for (int l = 0; l < c->n_levels; l++) {
+        keep_pix[l] = c->pix[1][l];
+        c->pix[1][l] = c->pix[0][l] + c->lv[l].plane;
+    }
+    c->pixT[1] = c->pixT[0] + c->lv[c->n_levels - 1].plane;
+    c->n_cur = n_pairs;
+    run_patchmatch(c);
+    run_consistency(c);
+    run_c2f(c, d_flow);
+    for (int l = 0; l < c->n_levels; l++) c->pix[1][l] = keep_pix[l];
+    c->pixT[1] = keep_pixT;
+    return cuda_ok(cudaGetLastError(), "compute_stream") ? EPPM_OK : EPPM_ERR_CUDA;
+}
+
 int eppm_last_stage_ms(eppm_context* c, float out[5]) {
     if (!c || !c->profile) return EPPM_ERR_STATE;
     cudaSetDevice(c->device);

@@ -121,7 +121,8 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
 long long selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits);
 void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pix1, const LevelGeom& g, int n, int y0 = 0, int y1 = -1);
 void op_preblur_rgba(eppm_context* c, const uchar4* src1, const uchar4* src2, size_t pitch_bytes);
-void op_pyramid_and_pack(eppm_context* c, int n);
+void op_pyramid_and_pack(eppm_context* c, int n, int two = 2);
+void run_prepare_frames(eppm_context* c, const uint8_t* d_frames, int n_frames);
 void op_pack_foreign(cudaStream_t s, const uchar4* rgba, size_t rgba_pitch_bytes, const unsigned char* census, size_t census_pitch_bytes, float4* pix,
                      const LevelGeom& g);
 void op_transpose_plane(cudaStream_t s, const float4* src, float4* dst, const LevelGeom& g, int n_img);

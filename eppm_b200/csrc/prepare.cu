@@ -57,10 +57,11 @@ constexpr int PB_T = 16;
 template <bool SRC_RGBA>
 __global__ void __launch_bounds__(PB_T* PB_T) k_preblur_rgb(const uint8_t* __restrict__ rgb0, const uint8_t* __restrict__ rgb1,
                                                            uchar4* __restrict__ out0, uchar4* __restrict__ out1, int w, int h,
-                                                           const float* __restrict__ wtab, size_t pitch) {
+                                                           const float* __restrict__ wtab, size_t pitch, int two) {
     __shared__ uchar4 tile[PB_T + 4][PB_T + 4];
     __shared__ float sw[26];
-    const int img = blockIdx.z & 1, b = blockIdx.z >> 1;
+    // two = 2: grid.z = pair*2 + image (two source arrays); two = 1: grid.z = frame of ONE flat frame list (video stream)
+    const int img = two == 2 ? (blockIdx.z & 1) : 0, b = two == 2 ? (blockIdx.z >> 1) : blockIdx.z;
     const uint8_t* src = (img ? rgb1 : rgb0) + (SRC_RGBA ? (size_t)b * h * pitch : (size_t)b * h * w * 3);
     uchar4* dst = (img ? out1 : out0) + (size_t)b * h * w;
     const int tid = threadIdx.y * PB_T + threadIdx.x;
@@ -102,12 +103,12 @@ __global__ void __launch_bounds__(PB_T* PB_T) k_preblur_rgb(const uint8_t* __res
 // One thread per OUTPUT pixel, taps read straight from the source level (L1/L2-cache resident).
 __global__ void __launch_bounds__(128) k_pyr_decimate(const uchar4* __restrict__ l0a, const uchar4* __restrict__ l0b, uchar4* __restrict__ outa,
                                                       uchar4* __restrict__ outb, int w0, int h0, int w, int h, int step, int r,
-                                                      const float* __restrict__ wtab) {
+                                                      const float* __restrict__ wtab, int two) {
     extern __shared__ float sw[];
     const int n = 2 * r + 1;
     for (int i = threadIdx.x; i <= n * n; i += blockDim.x) sw[i] = wtab[i];
     __syncthreads();
-    const int img = blockIdx.z & 1, b = blockIdx.z >> 1;
+    const int img = two == 2 ? (blockIdx.z & 1) : 0, b = two == 2 ? (blockIdx.z >> 1) : blockIdx.z;
     const uchar4* src = (img ? l0b : l0a) + (size_t)b * h0 * w0;
     uchar4* dst = (img ? outb : outa) + (size_t)b * h * w;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -279,7 +280,7 @@ void op_preblur_rgba(eppm_context* c, const uchar4* src1, const uchar4* src2, si
     const LevelGeom& g0 = c->lv[0];
     dim3 blk(PB_T, PB_T), grd((g0.w + PB_T - 1) / PB_T, (g0.h + PB_T - 1) / PB_T, 2);
     k_preblur_rgb<true><<<grd, blk, 0, c->stream>>>(reinterpret_cast<const uint8_t*>(src1), reinterpret_cast<const uint8_t*>(src2), c->rgba[0][0],
-                                                  c->rgba[1][0], g0.w, g0.h, c->gauss[0].d_w, pitch_bytes);
+                                                  c->rgba[1][0], g0.w, g0.h, c->gauss[0].d_w, pitch_bytes, 2);
     EPPM_LAUNCH_COUNT(1);
 }
 
@@ -288,13 +289,23 @@ void run_prepare(eppm_context* c, const uint8_t* d_img1, const uint8_t* d_img2, 
     const LevelGeom& g0 = c->lv[0];
     {
         dim3 blk(PB_T, PB_T), grd((g0.w + PB_T - 1) / PB_T, (g0.h + PB_T - 1) / PB_T, 2 * n);
-        k_preblur_rgb<false><<<grd, blk, 0, s>>>(d_img1, d_img2, c->rgba[0][0], c->rgba[1][0], g0.w, g0.h, c->gauss[0].d_w, 0);
+        k_preblur_rgb<false><<<grd, blk, 0, s>>>(d_img1, d_img2, c->rgba[0][0], c->rgba[1][0], g0.w, g0.h, c->gauss[0].d_w, 0, 2);
         EPPM_LAUNCH_COUNT(1);
     }
     op_pyramid_and_pack(c, n);
 }
 
-void op_pyramid_and_pack(eppm_context* c, int n) {
+// Video stream: n_frames consecutive frames, each prepared ONCE into the image-1 arrays (frame f = plane f); pair f then reads
+// frame f as image 1 and frame f+1 as image 2 through base pointers one plane apart (run_stream in context.cu).
+void run_prepare_frames(eppm_context* c, const uint8_t* d_frames, int n_frames) {
+    const LevelGeom& g0 = c->lv[0];
+    dim3 blk(PB_T, PB_T), grd((g0.w + PB_T - 1) / PB_T, (g0.h + PB_T - 1) / PB_T, n_frames);
+    k_preblur_rgb<false><<<grd, blk, 0, c->stream>>>(d_frames, d_frames, c->rgba[0][0], c->rgba[0][0], g0.w, g0.h, c->gauss[0].d_w, 0, 1);
+    EPPM_LAUNCH_COUNT(1);
+    op_pyramid_and_pack(c, n_frames, 1);
+}
+
+void op_pyramid_and_pack(eppm_context* c, int n, int two) {
     cudaStream_t s = c->stream;
     const LevelGeom& g0 = c->lv[0];
     for (int i = 1; i < c->n_levels; i++) {
@@ -304,13 +315,13 @@ void op_pyramid_and_pack(eppm_context* c, int n) {
         // :656 ratio = pow(ratio,i) for i <= n (= 0.5 at i = 1); :661 (float)pow(ratio,i)*W[0]/W[i-n] beyond
         const float ratio = i == 1 ? 0.5f : (float)pow((double)0.5f, i) * g0.w / gs.w;
         if (ratio == 0.5f) {
-            dim3 blk(128), grd((g.w + 127) / 128, g.h, 2 * n);
+            dim3 blk(128), grd((g.w + 127) / 128, g.h, two * n);
             size_t smem = ((2 * r + 1) * (2 * r + 1) + 1) * sizeof(float);
             k_pyr_decimate<<<grd, blk, smem, s>>>(c->rgba[0][i - 1], c->rgba[1][i - 1], c->rgba[0][i], c->rgba[1][i], gs.w, gs.h, g.w, g.h, 2, r,
-                                                  c->gauss[i].d_w);
+                                                  c->gauss[i].d_w, two);
             EPPM_LAUNCH_COUNT(1);
         } else {
-            for (int img = 0; img < 2; img++) {
+            for (int img = 0; img < two; img++) {
                 dim3 blk(128), grd((gs.w + 127) / 128, gs.h, n);
                 k_blur_full<<<grd, blk, 0, s>>>(c->rgba[img][i - 1], c->blur_tmp[img], gs.w, gs.h, r, c->gauss[i].d_w);
                 dim3 grd2((g.w + 127) / 128, g.h, n);
@@ -321,11 +332,11 @@ void op_pyramid_and_pack(eppm_context* c, int n) {
     }
     for (int i = 0; i < c->n_levels; i++) {
         const LevelGeom& g = c->lv[i];
-        for (int img = 0; img < 2; img++)
+        for (int img = 0; img < two; img++)
             k_pack_planes(s, c->rgba[img][i], (size_t)g.w * 4, (size_t)g.w * g.h * 4, c->pix[img][i], g, n);
     }
     const int L = c->n_levels - 1;
-    for (int img = 0; img < 2; img++) op_transpose_plane(s, c->pix[img][L], c->pixT[img], c->lv[L], n);
+    for (int img = 0; img < two; img++) op_transpose_plane(s, c->pix[img][L], c->pixT[img], c->lv[L], n);
 }
 
 }  // namespace eppm

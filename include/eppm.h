@@ -88,6 +88,10 @@ int eppm_compute_batch_host(eppm_context* ctx, const uint8_t* img1, const uint8_
 /* Same with DEVICE-resident inputs/outputs (same layouts), stream-ordered on the context's stream;
  * returns without synchronising. */
 int eppm_compute_batch_device(eppm_context* ctx, const uint8_t* d_img1, const uint8_t* d_img2, int n, float* d_flow);
+/* Video stream: d_frames = [n_pairs + 1][h][w][3] consecutive frames (device), d_flow = [n_pairs][h][w][2]; pair f is
+ * (frame f -> frame f+1).  Each frame's pyramid, census and packed planes are built once and used by both pairs it belongs to
+ * (the reference rebuilds them per pair, bao_flow_patchmatch_multiscale_cuda.cpp:159-168).  n_pairs + 1 <= max_batch. */
+int eppm_compute_stream_device(eppm_context* ctx, const uint8_t* d_frames, int n_pairs, float* d_flow);
 int eppm_synchronize(eppm_context* ctx);
 void* eppm_stream(eppm_context* ctx); /* cudaStream_t */
 

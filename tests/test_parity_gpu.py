@@ -499,3 +499,17 @@ def test_patch_stride_variants_bit_exact(name, stride):
     fm = ctx.compute_batch_host(a[None], b[None])[0]
     assert synth.epe(fm, gt, valid) <= synth.epe(fr, gt, valid) + 0.05
     ref.destroy(rc); ctx.close()
+
+
+def test_video_stream_reuses_frames_and_matches_pairwise():
+    """eppm_compute_stream_device: 4 consecutive frames -> 3 flows, each frame prepared once; identical to the pair-by-pair result."""
+    h, w = 192, 256
+    base, _, _, _ = synth.make_pair(h, w, 50, scale_to=0.2)
+    frames = np.stack([np.roll(base, (k, 2 * k), (0, 1)) for k in range(4)])
+    ctx = E.EppmContext(h, w, 4)
+    d_flow = torch.zeros((3, h, w, 2), dtype=torch.float32, device="cuda")
+    ctx.compute_stream_device(dev(frames), 3, d_flow)
+    ctx.synchronize()
+    pairwise = ctx.compute_batch_host(frames[:3], frames[1:])
+    assert same_bits(d_flow.cpu().numpy(), pairwise)
+    ctx.close()

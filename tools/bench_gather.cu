@@ -35,6 +35,23 @@ __global__ void k_tex(cudaTextureObject_t tex, const short2* __restrict__ centre
     out[i] = acc;
 }
 
+__global__ void k_mix(const float4* __restrict__ plane, int pw, cudaTextureObject_t tex, const short2* __restrict__ centres, float* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    short2 c = centres[i];
+    float acc = 0.f;
+    const float fx = (float)c.x, fy = (float)c.y;
+    for (int dy = -9; dy <= 9; dy += 2)
+#pragma unroll
+        for (int dx = -9; dx <= 9; dx += 4) {   // alternate: one sample through the LSU, the next through the texture unit
+            float4 p = __ldg(plane + (c.y + 16 + dy) * pw + c.x + 16 + dx);
+            acc += p.x + p.y * 0.5f + p.z * 0.25f + __uint_as_float(__float_as_uint(p.w) & 0x3f800000u);
+            float4 q = tex2D<float4>(tex, fx + (float)(dx + 2), fy + (float)dy);
+            acc += q.x + q.y * 0.5f + q.z * 0.25f + q.w;
+        }
+    out[i] = acc;
+}
+
 int main(int argc, char** argv) {
     const int w = 480, h = 270, pw = w + 32, ph = h + 32, n = 480 * 270 * 16;
     const int coherent = argc > 1 ? atoi(argv[1]) : 0;
@@ -60,16 +77,17 @@ int main(int argc, char** argv) {
     td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 0;
     cudaTextureObject_t tex; CK(cudaCreateTextureObject(&tex, &rd, &td, NULL));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int which = 0; which < 2; which++) {
+    for (int which = 0; which < 3; which++) {
         float best = 1e9f;
         for (int rep = 0; rep < 5; rep++) {
             cudaEventRecord(e0);
             if (which == 0) k_ldg<<<(n + 127) / 128, 128>>>(d_plane, pw, d_cen, d_out, n);
-            else k_tex<<<(n + 127) / 128, 128>>>(tex, d_cen, d_out, n);
+            else if (which == 1) k_tex<<<(n + 127) / 128, 128>>>(tex, d_cen, d_out, n);
+            else k_mix<<<(n + 127) / 128, 128>>>(d_plane, pw, tex, d_cen, d_out, n);
             cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
             float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
         }
-        printf("%s %s: %.3f ms for %d lanes x 100 gathers = %.1f Ggather/s\n", coherent ? "coherent" : "random", which ? "TEX uchar4" : "LDG.128 float4", best, n,
+        printf("%s %s: %.3f ms for %d lanes x 100 gathers = %.1f Ggather/s\n", coherent ? "coherent" : "random", which == 0 ? "LDG.128 float4" : which == 1 ? "TEX uchar4" : "half LDG half TEX", best, n,
                n * 100.0 / best / 1e6);
     }
     return 0;
