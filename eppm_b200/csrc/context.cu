@@ -192,6 +192,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
     }
     build_gauss_tables(c);
     build_rng_tables(c);
+    if (!getenv("EPPM_NO_TMA")) build_smooth_tensor_maps(c);
     if (!cuda_ok(cudaStreamSynchronize(c->stream), "context setup kernels")) { eppm_destroy(c); return EPPM_ERR_CUDA; }
     *out = c;
     return EPPM_OK;
@@ -463,6 +464,7 @@ void* eppm_device_plane(eppm_context* c, int which, int level) {
 
 long long eppm_selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits) { return selftest_const_div(d, lo_bits, hi_bits); }
 int eppm_smooth_uses_fast_div(eppm_context* c) { return c ? c->smooth_fast_div : EPPM_ERR_ARG; }
+int eppm_smooth_uses_tma(eppm_context* c) { return c ? c->tmap_ok[0] : EPPM_ERR_ARG; }
 
 long eppm_write_plane(eppm_context* c, int which, int level, int pair, const void* host_in) {
     if (!c || !host_in || level < 0 || level >= c->n_levels || pair < 0 || pair >= c->max_batch) return EPPM_ERR_ARG;

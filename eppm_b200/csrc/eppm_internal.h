@@ -1,5 +1,6 @@
 // Host-side context of libeppm_b200 (not part of the public ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -88,6 +89,8 @@ struct eppm_context {
     eppm::CostLut cost_lut;
     eppm::SmoothLut smooth_lut;
     eppm::WmfLut wmf_lut;
+    CUtensorMap tmap_pix0[eppm::MAX_LEVELS];     // TMA descriptors of the image-1 packed planes (smoothing tile loads)
+    int tmap_ok[eppm::MAX_LEVELS] = {};
     int band_y0 = 0, band_y1 = 0;                // rows of the coarsest level this context owns (whole level unless tiled across GPUs)
     int smooth_fast_div = 0;                     // set at create time when the constant-division fast path was verified exact
 };
@@ -103,6 +106,7 @@ void run_prepare(eppm_context* c, const uint8_t* d_img1, const uint8_t* d_img2, 
 void run_patchmatch(eppm_context* c);
 void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps = 1 << 30, int first_step = 0);
 void run_c2f_step(eppm_context* c, int level, int kind, float2* out);
+bool build_smooth_tensor_maps(eppm_context* c);
 void band_rows(const eppm_context* c, int level, int* y0, int* y1);
 void run_consistency(eppm_context* c);
 void run_c2f(eppm_context* c, float* d_flow_out);

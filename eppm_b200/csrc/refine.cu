@@ -15,6 +15,7 @@
 //    the reference's m-outer / n-inner first-minimum order.  (One thread per pixel with all 36 pairs was measured 33 % slower:
 //    168 registers, a third of the warps.)
 //  * smoothing reads a snapshot and writes a second buffer (the reference filters in place).
+#include <cuda.h>
 #include <float.h>
 #include <stdlib.h>
 
@@ -220,8 +221,31 @@ __device__ __forceinline__ void smooth_tap(const SmoothArgs& a, const float4& c,
     wsum = __fadd_rn(wsum, wgt);
 }
 
-__global__ void __launch_bounds__(SM_TX* SM_TY) k_flow_smooth(SmoothArgs a, const __grid_constant__ SmoothLut lut) {
-    extern __shared__ float4 smem[];  // [TH*TW] colours, then float2 [TH*TW] flows, then float [(R+1)^2] spatial weights
+// mbarrier / TMA helpers (PTX, sm_90+): one thread arms the barrier with the byte count, issues the bulk tensor copy, everyone waits.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(SM_TX* SM_TY) k_flow_smooth(SmoothArgs a, const __grid_constant__ SmoothLut lut, const __grid_constant__ CUtensorMap tmap,
+                                                              int use_tma) {
+    extern __shared__ __align__(128) float4 smem[];
+    __shared__ __align__(8) unsigned long long s_bar;  // [TH*TW] colours, then float2 [TH*TW] flows, then float [(R+1)^2] spatial weights
     const int R = a.R, TW = SM_TX + 2 * R, TH = SM_TY * SM_PY + 2 * R;
     float4* s_pix = smem;
     float2* s_flow = reinterpret_cast<float2*>(smem + TW * TH);
@@ -233,6 +257,18 @@ __global__ void __launch_bounds__(SM_TX* SM_TY) k_flow_smooth(SmoothArgs a, cons
     const int tid = threadIdx.y * SM_TX + threadIdx.x;
     for (int i = tid; i < (R + 1) * (R + 1); i += SM_TX * SM_TY)
         s_gg[i] = __fmul_rn(lut.g[i % (R + 1)], lut.g[i / (R + 1)]);  // cBlfGaussian[|dx|] * cBlfGaussian[|dy|] (:759)
+    // Colour tile (+R halo) of image 1: ONE TMA bulk tensor copy from the padded packed plane (box TW x TH pixels of 16 B; coordinates in
+    // floats along x; out-of-range parts are zero-filled and never used because their flow is marked unknown below).
+    if (use_tma) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar, (unsigned)(TW * TH * sizeof(float4)));
+            tma_load_3d(s_pix, &tmap, (x0 + PAD) * 4, y0 + PAD, b, &s_bar);
+        }
+    }
     for (int i = tid; i < TW * TH; i += SM_TX * SM_TY) {
         const int ty = i / TW, tx = i % TW;
         const int cx = x0 + tx, cy = y0 + ty;
@@ -240,11 +276,12 @@ __global__ void __launch_bounds__(SM_TX* SM_TY) k_flow_smooth(SmoothArgs a, cons
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cx >= 0 && cy >= 0 && cx < a.w && cy < a.h) {
             fl = f[(size_t)cy * a.w + cx];
-            p = ldpix(img + (size_t)cy * a.pw + cx);
+            if (!use_tma) p = ldpix(img + (size_t)cy * a.pw + cx);
         }
         s_flow[i] = fl;
-        s_pix[i] = p;
+        if (!use_tma) s_pix[i] = p;
     }
+    if (use_tma) mbar_wait(&s_bar, 0);
     __syncthreads();
     const int x = blockIdx.x * SM_TX + threadIdx.x;
     const int ly = threadIdx.y * SM_PY;               // local row of the upper pixel
@@ -347,8 +384,42 @@ void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pi
         attr_set = true;
     }
     dim3 blk(SM_TX, SM_TY), grd((g.w + SM_TX - 1) / SM_TX, (y1 - y0 + SM_TY * SM_PY - 1) / (SM_TY * SM_PY), n);
-    k_flow_smooth<<<grd, blk, smem, c->stream>>>(a, c->smooth_lut);
+    // TMA path: the plane must be one of the context's own image-1 planes (a tensor map exists per level) and the box must fit
+    // the 256-element limit of a tensor-map box dimension
+    int level = -1;
+    for (int l = 0; l < c->n_levels; l++)
+        if (pix1 == c->pix[0][l]) level = l;
+    const int use_tma = level >= 0 && c->tmap_ok[level] && TW * 4 <= 256 && TH <= 256;
+    static const CUtensorMap dummy = {};
+    k_flow_smooth<<<grd, blk, smem, c->stream>>>(a, c->smooth_lut, use_tma ? c->tmap_pix0[level] : dummy, use_tma);
     EPPM_LAUNCH_COUNT(1);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link dependency on libcuda).
+// Map of the image-1 packed planes of one level: dims (x in floats = pw*4, y = ph, z = plane index), box = smoothing tile.
+bool build_smooth_tensor_maps(eppm_context* c) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const int R = 2 * c->prm.blf_sig_s, TW = SM_TX + 2 * R, TH = SM_TY * SM_PY + 2 * R;
+    for (int l = 0; l < c->n_levels; l++) {
+        c->tmap_ok[l] = 0;
+        if (TW * 4 > 256 || TH > 256) continue;
+        const LevelGeom& g = c->lv[l];
+        const cuuint64_t dims[3] = {(cuuint64_t)g.pw * 4, (cuuint64_t)g.ph, (cuuint64_t)c->max_batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.pw * 16, (cuuint64_t)g.plane * 16};  // bytes, dims 1 and 2
+        const cuuint32_t box[3] = {(cuuint32_t)TW * 4, (cuuint32_t)TH, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = ((encode_fn)fn)(&c->tmap_pix0[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->pix[0][l], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        c->tmap_ok[l] = r == CUDA_SUCCESS;
+    }
+    return true;
 }
 
 // rows of level `level` that correspond to the context's band of coarsest-level rows (the last band takes the remainder)

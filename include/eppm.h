@@ -150,6 +150,8 @@ void* eppm_device_plane(eppm_context* ctx, int which, int level);
  * eppm_smooth_uses_fast_div reports whether a context's smoothing kernel was allowed to use it. */
 long long eppm_selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits);
 int eppm_smooth_uses_fast_div(eppm_context* ctx);
+/* 1 when the smoothing kernel stages its colour tile with TMA (cp.async.bulk.tensor); EPPM_NO_TMA=1 in the environment disables it. */
+int eppm_smooth_uses_tma(eppm_context* ctx);
 
 /* Number of kernel launches issued by this library since the counter was last reset (bench.py's gpu_launches). */
 unsigned long long eppm_launch_count(int reset);
