@@ -122,6 +122,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         delete c;
         return EPPM_ERR_ARG;
     }
+    c->variant = getenv("EPPM_VARIANT") ? atoi(getenv("EPPM_VARIANT")) : 0;
     c->profile = getenv("EPPM_PROFILE") && atoi(getenv("EPPM_PROFILE")) != 0;
     if (!cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return EPPM_ERR_CUDA; }
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
@@ -190,6 +191,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         }
         c->smooth_fast_div = checked_ok;
     }
+    for (int l = 0; l + 1 < c->n_levels; l++) c->aff_ok[l] = p.patch_stride == 2 && build_affine_tab(c->aff_tab[l], c->lv[l].pw, c->lv[l].w, c->lv[l].h);
     build_gauss_tables(c);
     build_rng_tables(c);
     if (!getenv("EPPM_NO_TMA")) build_smooth_tensor_maps(c);

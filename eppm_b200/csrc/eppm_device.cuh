@@ -83,8 +83,12 @@ __device__ __forceinline__ float max3abs_diff(const float4& a, const float4& b) 
 // indexed by the XOR itself avoids POPC but was measured slower: its bank conflicts cost more L1 wavefronts than POPC costs XU slots.)
 constexpr int CENSUS_LUT_N = 9;
 __device__ __forceinline__ float census_lut(const float* s_census, const float4& p1, const float4& p2) {
+    // ld.shared on the 32-bit window address: ptxas folds the table's static offset into the LDS immediate, so the lookup is
+    // LOP3 + POPC + LDS (through a generic pointer it re-derives the window base with four uniform instructions per use)
     const unsigned off = __popc(__float_as_uint(p1.w) ^ __float_as_uint(p2.w));
-    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_census) + off);
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(s_census) + off));
+    return v;
 }
 __device__ __forceinline__ void load_census_lut(float* s_census, const CostLut& lut) {
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
@@ -120,35 +124,72 @@ __device__ __forceinline__ float max3abs_diff(const PixPk& a, const PixPk& b) {
 //   cost   = 1 - exp(-c^2/lambda_ad^2) + LUT_census[popc(census1 ^ census2)],  c = max|rgb1-rgb2|
 //   weight = exp(-(d1^2 + d2^2)/sigma_r^2) * G[|j|]*G[|i|],                     dk = max|centre_k - p_k|
 // accumulated as cost_sum = fma(cost, weight, cost_sum); weight_sum += weight, in sample order.
-// d1 (image-1 side) is passed in so callers can hoist it across candidates.  The AD chain (c^2 -> /-0.01 -> *log2e) and
-// the weight chain (arg -> /-0.01 -> *log2e) run side by side in the two halves of packed instructions.
-__device__ __forceinline__ void sample_term(const float4& p1, const PixPk& p1k, const float4& p2, const PixPk& c2k, float d1, float gg,
-                                            const float* s_census, float& cost_sum, float& weight_sum) {
+// d1 (image-1 side) is passed in -- packed as (0, d1) -- so callers can hoist it across candidates.  The AD chain
+// (c^2 -> /-0.01 -> *log2e) and the weight chain (arg -> /-0.01 -> *log2e) run side by side in the two halves of packed instructions.
+// sample_eval returns the AD+census cost and the exponent t2 of the range weight; the caller forms e2 = __expf-equivalent of t2
+// (ex2 with the `t2 < -126` fix-up, which a group of samples can share one test for), w = e2*gg, and accumulates.
+__device__ __forceinline__ void sample_eval(const float4& p1, const PixPk& p1k, const float4& p2, const PixPk& c2k, f32x2 zd1, const float* s_census,
+                                            float& cost, float& t2) {
     const PixPk p2k = pack_pix(p2);
     const float c = max3abs_diff(p1k, p2k);
     const float d2 = max3abs_diff(c2k, p2k);
-    float cc, d22;
     const f32x2 cd = pk2(c, d2);
-    upk2(mul2(cd, cd), cc, d22);
-    const float arg = __fmaf_rn(d1, d1, d22);
-    // div_neg_0p01 on both halves: q0 = x*r; rem = fma(q0, 0.01', x); q = fma(r, rem, q0); then * log2e
-    const f32x2 x = pk2(cc, arg);
+    // (c^2, d1^2 + d2^2): the second half is the reference's fma(d1, d1, d2*d2); the first adds 0*0 to c^2 >= 0, which changes nothing.
+    // Staying packed avoids the register-pair copies a scalar FFMA into one half costs.
+    const f32x2 x = fma2(zd1, zd1, mul2(cd, cd));
     const f32x2 R = pk2(-99.99999237060546875f, -99.99999237060546875f), D = pk2(0.010000000707805156708f, 0.010000000707805156708f);
     const f32x2 q0 = fma2(x, R, pk2(0.f, 0.f));
     const f32x2 rem = fma2(q0, D, x);
     const f32x2 q = fma2(R, rem, q0);
-    float t1, t2;
+    float t1;
     upk2(mul2(q, pk2(1.4426950216293334961f, 1.4426950216293334961f)), t1, t2);
-    // AD term: 1 - ex2(t1); no fix-up needed (see one_minus_exp_ref)
-    const float cost = __fadd_rn(__fadd_rn(1.0f, -ex2_mufu(t1)), census_lut(s_census, p1, p2));
-    // weight term: __expf fix-up for t2 < -126 (see exp_ref)
-    const bool tiny = t2 < -126.0f;
+    cost = __fadd_rn(__fadd_rn(1.0f, -ex2_mufu(t1)), census_lut(s_census, p1, p2));
+}
+// __expf of an exponent already multiplied by log2e, for the rare t < -126 case (see exp_ref)
+__device__ __forceinline__ float ex2_tiny(float t) {
+    const float r = ex2_mufu(__fmul_rn(t, 0.5f));
+    return __fmul_rn(r, r);
+}
+
+// sample_eval + the per-sample fix-up + accumulation: the plain form of one sample
+__device__ __forceinline__ void sample_term(const float4& p1, const PixPk& p1k, const float4& p2, const PixPk& c2k, f32x2 zd1, float gg,
+                                            const float* s_census, float& cost_sum, float& weight_sum) {
+    float cost, t2;
+    sample_eval(p1, p1k, p2, c2k, zd1, s_census, cost, t2);
+    const bool tiny = t2 < -126.0f;   // __expf fix-up (see exp_ref)
     if (tiny) t2 = __fmul_rn(t2, 0.5f);
     float e2 = ex2_mufu(t2);
     if (tiny) e2 = __fmul_rn(e2, e2);
     const float w = __fmul_rn(e2, gg);
     cost_sum = __fmaf_rn(cost, w, cost_sum);
     weight_sum = __fadd_rn(weight_sum, w);
+}
+
+// G consecutive samples of ONE accumulator pair: evaluated side by side with the bare ex2, one test for the rare fix-up, then added
+// in sample order -- the same bits as G calls of sample_term.
+template <int G>
+__device__ __forceinline__ void sample_group(const float4 (&p1)[G], const float4 (&p2)[G], const PixPk& c1k, const PixPk& c2k, const float (&gg)[G],
+                                             const float* s_census, float& cost_sum, float& weight_sum) {
+    float ct[G], t2[G], w[G];
+    float tmin = 0.f;
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+        const PixPk p1k = pack_pix(p1[k]);
+        const float d1 = max3abs_diff(c1k, p1k);
+        sample_eval(p1[k], p1k, p2[k], c2k, pk2(0.f, d1), s_census, ct[k], t2[k]);
+        w[k] = __fmul_rn(ex2_mufu(t2[k]), gg[k]);
+        tmin = fminf(tmin, t2[k]);
+    }
+    if (tmin < -126.0f) {
+#pragma unroll
+        for (int k = 0; k < G; k++)
+            if (t2[k] < -126.0f) w[k] = __fmul_rn(ex2_tiny(t2[k]), gg[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+        cost_sum = __fmaf_rn(ct[k], w[k], cost_sum);
+        weight_sum = __fadd_rn(weight_sum, w[k]);
+    }
 }
 
 // _d_compute_patch_dist (bao_pmflow_kernel.cu:255-301): 100 samples at stride 2 over a 19x19 patch.
@@ -168,29 +209,34 @@ __device__ __forceinline__ float patch_cost(const float4* __restrict__ A, const 
     const PixPk c1k = pack_pix(ldpix(A + oa));
     const PixPk c2k = pack_pix(ldpix(B + ob));
     float cost_sum = 0.f, weight_sum = 0.f;
+    constexpr int NJ = (2 * PATCH_R) / STRIDE + 1;           // samples per patch row
+    constexpr int G = NJ % 5 == 0 ? 5 : (NJ == 7 ? 7 : 1);   // 10 -> two groups of 5, 7 -> one group, 19 -> plain
 #pragma unroll 1
     for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
         const int ai = i < 0 ? -i : i;
-        if (TRANSPOSED) {
-            const unsigned ra = oa + (unsigned)i, rb = ob + (unsigned)i;
+        const unsigned ra = oa + (unsigned)(i * (int)si), rb = ob + (unsigned)(i * (int)si);
+        if (G > 1) {
+#pragma unroll
+            for (int j0 = 0; j0 < NJ; j0 += G) {
+                float4 p1[G], p2[G];
+                float gg[G];
+#pragma unroll
+                for (int k = 0; k < G; k++) {
+                    const int j = -PATCH_R + (j0 + k) * STRIDE;
+                    p1[k] = ldpix(A + (ra + (unsigned)(j * (int)sj)));
+                    p2[k] = ldpix(B + (rb + (unsigned)(j * (int)sj)));
+                    gg[k] = lut.gg[ai][j < 0 ? -j : j];
+                }
+                sample_group<G>(p1, p2, c1k, c2k, gg, s_census, cost_sum, weight_sum);
+            }
+        } else {
 #pragma unroll
             for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE) {
                 const float4 p1 = ldpix(A + (ra + (unsigned)(j * (int)sj)));
                 const float4 p2 = ldpix(B + (rb + (unsigned)(j * (int)sj)));
                 const PixPk p1k = pack_pix(p1);
                 const float d1 = max3abs_diff(c1k, p1k);
-                sample_term(p1, p1k, p2, c2k, d1, lut.gg[ai][j < 0 ? -j : j], s_census, cost_sum, weight_sum);
-            }
-        } else {
-            const float4* ar = A + (oa + (unsigned)(i * (int)si));
-            const float4* br = B + (ob + (unsigned)(i * (int)si));
-#pragma unroll
-            for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE) {
-                const float4 p1 = ldpix(ar + j);
-                const float4 p2 = ldpix(br + j);
-                const PixPk p1k = pack_pix(p1);
-                const float d1 = max3abs_diff(c1k, p1k);
-                sample_term(p1, p1k, p2, c2k, d1, lut.gg[ai][j < 0 ? -j : j], s_census, cost_sum, weight_sum);
+                sample_term(p1, p1k, p2, c2k, pk2(0.f, d1), lut.gg[ai][j < 0 ? -j : j], s_census, cost_sum, weight_sum);
             }
         }
     }

@@ -13,6 +13,14 @@ namespace eppm {
 
 constexpr int MAX_LEVELS = 6;
 
+// A/B switches read once from the environment variable EPPM_VARIANT at eppm_create (measurement knobs; every setting computes the same bits)
+enum {
+    EPPM_VAR_REFINE_GENERIC = 1,   // plane-fitting refine: coordinates computed per sample instead of the verified site table
+    EPPM_VAR_REFINE_NOGROUP = 2,   // table kernel with the per-sample __expf fix-up instead of the grouped test
+    EPPM_VAR_SEARCH_SERIAL = 4,    // random search: one guess at a time instead of all guesses side by side
+    EPPM_VAR_PROP_NOSKIP = 8,      // propagation: evaluate candidates that equal the current target (the reference does)
+};
+
 struct LevelGeom {
     int w, h;     // bao_pyr_init_dim: int(double(dim) * pow(0.5, level))  (basic/bao_basic.h:196-211)
     int pw, ph;   // padded plane dims: w + 2*PAD, h + 2*PAD
@@ -34,6 +42,10 @@ struct Arena {
         used += bytes;
         return p;
     }
+};
+
+struct AffineTab {
+    int off[3][100];   // dy * pw + dx of affine model 1..3 at sample (i, j) of the stride-2 patch, relative to the candidate centre; i outer, j inner
 };
 
 struct SmoothLut {
@@ -92,6 +104,9 @@ struct eppm_context {
     CUtensorMap tmap_pix0[eppm::MAX_LEVELS];     // TMA descriptors of the image-1 packed planes (smoothing tile loads)
     int tmap_ok[eppm::MAX_LEVELS] = {};
     int band_y0 = 0, band_y1 = 0;                // rows of the coarsest level this context owns (whole level unless tiled across GPUs)
+    eppm::AffineTab aff_tab[eppm::MAX_LEVELS];   // per level (pitch): verified sample-site tables of the plane-fitting refine
+    int aff_ok[eppm::MAX_LEVELS] = {};
+    int variant = 0;                             // EPPM_VARIANT bit mask (A/B switches for measurements, see EPPM_VAR_*)
     int smooth_fast_div = 0;                     // set at create time when the constant-division fast path was verified exact
 };
 
@@ -112,6 +127,7 @@ void run_consistency(eppm_context* c);
 void run_c2f(eppm_context* c, float* d_flow_out);
 void build_rng_tables(eppm_context* c);
 void build_gauss_tables(eppm_context* c);
+bool build_affine_tab(AffineTab& t, int pw, int w, int h);
 
 // building blocks reused by the legacy stage ABI (foreign buffers)
 void op_lr_check(cudaStream_t s, short2* nnf, float* cost, const short2* nnf2, int w, int h, int n);

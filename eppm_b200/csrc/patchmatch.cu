@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128) k_pm_init(PmArgs a, const short2* __restr
 // Lanes of a warp are ADJACENT scan lines working on the same position along the line: column passes read the
 // row-major planes, row passes the column-major copies, so both sides of every sample are coalesced.
 template <int DIR, int STRIDE>
-__global__ void __launch_bounds__(896) k_pm_propagate(PmArgs a, int seg_len, const __grid_constant__ CostLut lut) {
+__global__ void __launch_bounds__(896) k_pm_propagate(PmArgs a, int seg_len, int skip_equal, const __grid_constant__ CostLut lut) {
     constexpr bool ROW = (DIR == 0 || DIR == 2), FWD = (DIR < 2);
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
@@ -160,12 +160,19 @@ __global__ void __launch_bounds__(896) k_pm_propagate(PmArgs a, int seg_len, con
             if (DIR == 2) prev.x = max(prev.x - 1, 0);
             if (DIR == 3) prev.y = max(prev.y - 1, 0);
             const int x1 = ROW ? i : line, y1 = ROW ? line : i;
-            const float cv = patch_cost<STRIDE, ROW>(A, B, pitch, x1, y1, prev.x, prev.y, lut, s_census);
-            if (cv < cur_best) {
-                nnf[id] = prev;
-                cost[id] = cv;
+            const short2 cur = nnf[id];
+            // A candidate equal to the pixel's current target would be scored with the very evaluation that produced cost[id]
+            // (same function, same arguments), so `cv < cur_best` is false: the reference's outcome without the 100 samples.
+            if (skip_equal && prev.x == cur.x && prev.y == cur.y) {
+                // prev stays (== nnf[id])
             } else {
-                prev = nnf[id];
+                const float cv = patch_cost<STRIDE, ROW>(A, B, pitch, x1, y1, prev.x, prev.y, lut, s_census);
+                if (cv < cur_best) {
+                    nnf[id] = prev;
+                    cost[id] = cv;
+                } else {
+                    prev = cur;
+                }
             }
         }
         __syncthreads();  // lock-step: step t of every segment completes before step t+1 starts
@@ -207,6 +214,87 @@ __global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __res
     cost[id] = best_cost;
 }
 
+// The same search with all NG guesses of a pixel scored side by side: every guess is drawn around the ENTRY target, so the
+// evaluations are independent; the image-1 side of each sample (load, range distance, spatial weight) is computed once for the NG
+// candidates and the scattered image-2 gathers of the guesses overlap.  Each guess still adds its samples in the reference's order,
+// and the guesses are compared in order with strict '<', so the outcome is the serial kernel's bit for bit.
+template <int STRIDE, int NG>
+__global__ void __launch_bounds__(128) k_pm_search_joint(PmArgs a, const short2* __restrict__ rng, int search_range, int radius_min,
+                                                         const __grid_constant__ CostLut lut) {
+    __shared__ float s_census[CENSUS_LUT_N];
+    load_census_lut(s_census, lut);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y;
+    if (x >= a.w) return;
+    const float4 *A, *B; short2* nnf; float* cost;
+    pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
+    const int id = y * a.w + x;
+    const short2 entry = nnf[id];
+    short gx[NG], gy[NG];
+    unsigned ob[NG];
+    PixPk c2k[NG];
+    int mag = search_range;
+#pragma unroll
+    for (int k = 0; k < NG; k++) {
+        const short2 rr = rng[(size_t)k * a.w * a.h + id];
+        const unsigned r1 = (unsigned)(int)rr.x, r2 = (unsigned)(int)rr.y;   // :1557-1563
+        const short xmin = (short)max(entry.x - mag, 0), xmax = (short)min(entry.x + mag + 1, a.w + 1);
+        const short ymin = (short)max(entry.y - mag, 0), ymax = (short)min(entry.y + mag + 1, a.h + 1);
+        gx[k] = (short)(xmin + r1 % (unsigned)(xmax - xmin));
+        gy[k] = (short)(ymin + r2 % (unsigned)(ymax - ymin));
+        if (mag / 2 >= radius_min) mag /= 2;
+        ob[k] = (unsigned)(gx[k] + PAD) + (unsigned)(gy[k] + PAD) * (unsigned)a.pw;
+        c2k[k] = pack_pix(ldpix(B + ob[k]));
+    }
+    const unsigned oa = (unsigned)(x + PAD) + (unsigned)(y + PAD) * (unsigned)a.pw;
+    const PixPk c1k = pack_pix(ldpix(A + oa));
+    float cs[NG], ws[NG];
+#pragma unroll
+    for (int k = 0; k < NG; k++) cs[k] = ws[k] = 0.f;
+#pragma unroll 1
+    for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
+        const int ai = i < 0 ? -i : i;
+        const unsigned irow = (unsigned)(i * a.pw);
+#pragma unroll 2
+        for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE) {
+            const unsigned off = irow + (unsigned)j;
+            const float4 p1 = ldpix(A + (oa + off));
+            const PixPk p1k = pack_pix(p1);
+            const f32x2 zd1 = pk2(0.f, max3abs_diff(c1k, p1k));
+            const float gg = lut.gg[ai][j < 0 ? -j : j];
+            float ct[NG], t2[NG], w[NG];
+            float tmin = 0.f;
+#pragma unroll
+            for (int k = 0; k < NG; k++) {
+                sample_eval(p1, p1k, ldpix(B + (ob[k] + off)), c2k[k], zd1, s_census, ct[k], t2[k]);
+                w[k] = __fmul_rn(ex2_mufu(t2[k]), gg);
+                tmin = fminf(tmin, t2[k]);
+            }
+            if (tmin < -126.0f) {   // rare: the __expf fix-up (see exp_ref), one test per NG samples
+#pragma unroll
+                for (int k = 0; k < NG; k++)
+                    if (t2[k] < -126.0f) w[k] = __fmul_rn(ex2_tiny(t2[k]), gg);
+            }
+#pragma unroll
+            for (int k = 0; k < NG; k++) {
+                cs[k] = __fmaf_rn(ct[k], w[k], cs[k]);
+                ws[k] = __fadd_rn(ws[k], w[k]);
+            }
+        }
+    }
+    short2 best = entry;
+    float best_cost = cost[id];
+#pragma unroll
+    for (int k = 0; k < NG; k++) {
+        const float cv = __fdiv_rn(cs[k], ws[k]);
+        if (cv < best_cost) {
+            best = make_short2(gx[k], gy[k]);
+            best_cost = cv;
+        }
+    }
+    nnf[id] = best;
+    cost[id] = best_cost;
+}
+
 template <int DIR, int STRIDE>
 static void launch_propagate(eppm_context* c, const PmArgs& a, int n) {
     const bool row = (DIR == 0 || DIR == 2);
@@ -217,7 +305,7 @@ static void launch_propagate(eppm_context* c, const PmArgs& a, int n) {
     int lines = 32;  // adjacent scan lines per CTA = coalescing width; all segments of a line stay in one CTA (lock-step barrier)
     while (lines > 1 && lines * n_seg > 896) lines >>= 1;
     dim3 blk(lines, n_seg), grd((n_line + lines - 1) / lines, 1, a.n_dirs * n);
-    k_pm_propagate<DIR, STRIDE><<<grd, blk, 0, c->stream>>>(a, c->prm.prop_seg_length, c->cost_lut);
+    k_pm_propagate<DIR, STRIDE><<<grd, blk, 0, c->stream>>>(a, c->prm.prop_seg_length, !(c->variant & EPPM_VAR_PROP_NOSKIP), c->cost_lut);
     EPPM_LAUNCH_COUNT(1);
 }
 
@@ -265,8 +353,11 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
         if (run()) launch_propagate<2, STRIDE>(c, a, n);
         if (run()) launch_propagate<3, STRIDE>(c, a, n);
         if (!run()) continue;
-        k_pm_search<STRIDE><<<grd, blk, 0, c->stream>>>(a, c->rng_search + (size_t)it * c->prm.num_rand_guess * g.w * g.h, c->prm.num_rand_guess,
-                                               c->prm.search_range, c->prm.search_radius_min, c->cost_lut);
+        const short2* rng = c->rng_search + (size_t)it * c->prm.num_rand_guess * g.w * g.h;
+        if (c->prm.num_rand_guess == 6 && !(c->variant & EPPM_VAR_SEARCH_SERIAL))
+            k_pm_search_joint<STRIDE, 6><<<grd, blk, 0, c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut);
+        else
+            k_pm_search<STRIDE><<<grd, blk, 0, c->stream>>>(a, rng, c->prm.num_rand_guess, c->prm.search_range, c->prm.search_radius_min, c->cost_lut);
         EPPM_LAUNCH_COUNT(1);
     }
 }

@@ -17,6 +17,7 @@
 //  * smoothing reads a snapshot and writes a second buffer (the reference filters in place).
 #include <cuda.h>
 #include <float.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include "eppm_internal.h"
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine(RefineA
                 const PixPk p1k = pack_pix(p1);
                 const float d1 = max3abs_diff(c1k, p1k);
                 const float gg = lut.gg[ai][j < 0 ? -j : j];
+                const f32x2 zd1 = pk2(0.f, d1);
                 // x coordinates of the 4 models: cx2 = fma(i, C_uy, fma(j, C_ux, float(x1+j) + uu))   (:402, :440, :478 as contracted)
                 const float bx = __fadd_rn(uu, (float)(x + j));
                 int sx[4];
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine(RefineA
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const float4 p2 = ldpix(I2 + (unsigned)(sy[q] * a.pw + sx[q]));
-                        sample_term(p1, p1k, p2, c2k[n], d1, gg, s_census, cs[n][q], ws[n][q]);
+                        sample_term(p1, p1k, p2, c2k[n], zd1, gg, s_census, cs[n][q], ws[n][q]);
                     }
                 }
             }
@@ -183,6 +185,161 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine(RefineA
         }
         a.flow[(size_t)b * a.w * a.h + (size_t)y * a.w + x] = out;
     }
+}
+
+// ---- table-driven refine (default at patch stride 2) ----
+// The sample sites of the three affine models are floor(fma(i, C_y, fma(j, C_x, float(X)))) with X = cx + j an exact integer
+// (bao_pmflow_kernel.cu:402,440,478 as contracted by nvcc).  For odd (i, j) the real value j*C_x + i*C_y never comes closer than
+// 1e-3 to an integer, far more than the two FFMA roundings can move it at any |X| < 2^15, so site - X is a function of (i, j, model)
+// alone.  build_affine_tab() tabulates it and CHECKS that claim for every X the level can produce with the host's correctly rounded
+// fmaf; only then is this kernel used.  It replaces 2 FFMA + F2I + IADD + IMAD per coordinate by one table read per site,
+// and groups the `t2 < -126` fix-up of __expf (taken by ~1 % of the samples) of the four models of a candidate into one test.
+// base + off pixels as ONE IMAD.WIDE (left to itself the compiler sign-extends and shifts with three ALU instructions)
+__device__ __forceinline__ const float4* pix_at(const float4* base, int off) {
+    const float4* r;
+    asm("mad.wide.s32 %0, %1, 16, %2;" : "=l"(r) : "r"(off), "l"(base));
+    return r;
+}
+
+template <bool GROUP_TINY>
+__global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine_tab(RefineArgs a, const __grid_constant__ CostLut lut,
+                                                                             const __grid_constant__ AffineTab tab) {
+    __shared__ float s_best[3][RF_PIX];
+    __shared__ int s_bn[3][RF_PIX];
+    __shared__ float s_census[CENSUS_LUT_N];
+    load_census_lut(s_census, lut);
+    const int m = threadIdx.x >> 5, pl = threadIdx.x & 31;
+    const int x = blockIdx.x * RF_PIX + pl, y = a.y0 + blockIdx.y;
+    const bool in = x < a.w;
+    const int b = blockIdx.z;
+    const float4* I1 = a.pix1 + (size_t)b * a.plane;
+    const float4* I2 = a.pix2 + (size_t)b * a.plane;
+    float2 fl = make_float2(0.f, 0.f);
+    if (in) fl = a.upsample ? upsample2(a.coarse + (size_t)b * a.ws * a.hs, a.ws, a.hs, x, y) : a.coarse[(size_t)b * a.w * a.h + (size_t)y * a.w + x];
+    const bool unknown = fl.x > EPPM_UNKNOWN_FLOW_THRESH || fl.y > EPPM_UNKNOWN_FLOW_THRESH;  // :2011
+    const short cxc = (short)((short)(int)fl.x + x), cyc = (short)((short)(int)fl.y + y);     // :2014-2019
+    const short cx = (short)(cxc + (m - 1));
+    float cost[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+    bool valid[3];
+#pragma unroll
+    for (int n = 0; n < 3; n++) {
+        const short cy = (short)(cyc + (n - 1));
+        valid[n] = in && !unknown && !(cx < 0 || cy < 0 || cx >= a.w || cy >= a.h);  // :2029
+    }
+    if (valid[0] || valid[1] || valid[2]) {
+        float cs[3][4], ws[3][4];
+#pragma unroll
+        for (int n = 0; n < 3; n++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) cs[n][q] = ws[n][q] = 0.f;
+        const float4* a0 = I1 + (unsigned)((y + PAD) * a.pw + x + PAD);
+        const PixPk c1k = pack_pix(ldpix(a0));
+        PixPk c2k[3];
+        const float4* P[3];   // candidate centres in image 2 (rows that are not valid are clamped into the plane and never used)
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+            const int cy = max(-PAD, min(a.h - 1 + PAD, (int)cyc + n - 1));
+            const int cxs = max(-PAD, min(a.w - 1 + PAD, (int)cx));
+            P[n] = I2 + (unsigned)((cy + PAD) * a.pw + cxs + PAD);
+            c2k[n] = pack_pix(ldpix(P[n]));
+            asm volatile("" : "+l"(P[n]));  // keep the three centre pointers in registers: every site is then one IMAD.WIDE away
+        }
+        int s = 0;
+#pragma unroll 1
+        for (int i = -PATCH_R; i <= PATCH_R; i += 2) {
+            const int ai = i < 0 ? -i : i;
+            const int irow = i * a.pw;
+#pragma unroll 2
+            for (int j = -PATCH_R; j <= PATCH_R; j += 2, s++) {
+                const float4 p1 = ldpix(a0 + irow + j);
+                const PixPk p1k = pack_pix(p1);
+                const float d1 = max3abs_diff(c1k, p1k);
+                const float gg = lut.gg[ai][j < 0 ? -j : j];
+                const f32x2 zd1 = pk2(0.f, d1);
+                int off[4];
+                off[0] = irow + j;  // identity model: the exact integer site (cx + j, cy + i)
+#pragma unroll
+                for (int q = 0; q < 3; q++) off[q + 1] = tab.off[q][s];
+#pragma unroll
+                for (int n = 0; n < 3; n++) {
+                    if (!valid[n]) continue;
+                    if (GROUP_TINY) {
+                        float ct[4], t2[4], w[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) sample_eval(p1, p1k, ldpix(pix_at(P[n], off[q])), c2k[n], zd1, s_census, ct[q], t2[q]);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) w[q] = __fmul_rn(ex2_mufu(t2[q]), gg);
+                        if (fminf(fminf(t2[0], t2[1]), fminf(t2[2], t2[3])) < -126.0f) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++)
+                                if (t2[q] < -126.0f) w[q] = __fmul_rn(ex2_tiny(t2[q]), gg);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            cs[n][q] = __fmaf_rn(ct[q], w[q], cs[n][q]);
+                            ws[n][q] = __fadd_rn(ws[n][q], w[q]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) sample_term(p1, p1k, ldpix(pix_at(P[n], off[q])), c2k[n], zd1, gg, s_census, cs[n][q], ws[n][q]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+            if (!valid[n]) continue;
+            const float k1 = __fdiv_rn(cs[n][0], ws[n][0]), k2 = __fdiv_rn(cs[n][1], ws[n][1]);
+            const float k3 = __fdiv_rn(cs[n][2], ws[n][2]), k4 = __fdiv_rn(cs[n][3], ws[n][3]);
+            cost[n] = min_ref(k1, min_ref(k2, min_ref(k3, k4)));  // :512
+        }
+    }
+    float best = 999999.f;
+    int best_n = -1;
+#pragma unroll
+    for (int n = 0; n < 3; n++)
+        if (valid[n] && cost[n] < best) { best = cost[n]; best_n = n; }
+    s_best[m][pl] = best;
+    s_bn[m][pl] = best_n;
+    __syncthreads();
+    float bcost = 999999.f;
+    int bm = -1, bn = -1;
+#pragma unroll
+    for (int mm = 0; mm < 3; mm++) {
+        const float oc = s_best[mm][pl];
+        const int on = s_bn[mm][pl];
+        if (on >= 0 && oc < bcost) { bcost = oc; bm = mm; bn = on; }
+    }
+    if (in && m == 0) {
+        float2 out;
+        if (unknown) out = make_float2(0.f, 0.f);
+        else {
+            short bx = cxc, by = cyc;
+            if (bm >= 0) { bx = (short)(cxc + (bm - 1)); by = (short)(cyc + (bn - 1)); }
+            out = make_float2((float)(bx - x), (float)(by - y));
+        }
+        a.flow[(size_t)b * a.w * a.h + (size_t)y * a.w + x] = out;
+    }
+}
+
+// Site table of one level (pitch pw) and its proof: for every integer X in [lo, hi] that a candidate coordinate + offset can take,
+// floor(fmaf(i, Cy, fmaf(j, Cx, (float)X))) - X must equal the tabulated value.  Host fmaf is correctly rounded = the device FFMA.
+bool build_affine_tab(AffineTab& t, int pw, int w, int h) {
+    static const float pf[3][4] = {{0.177f, -0.011f, -0.003f, 0.301f}, {0.125f, -0.357f, 0.009f, 0.308f}, {0.205f, 0.370f, 0.011f, 0.296f}};
+    auto site = [](float fi, float fj, float cj, float ci, int X) { return (int)floorf(fmaf(fi, ci, fmaf(fj, cj, (float)X))) - X; };
+    const int lim = (w > h ? w : h) + PATCH_R;
+    int s = 0;
+    for (int i = -PATCH_R; i <= PATCH_R; i += 2)
+        for (int j = -PATCH_R; j <= PATCH_R; j += 2, s++)
+            for (int q = 0; q < 3; q++) {
+                // x: cx2 = fma(i, C_uy, fma(j, C_ux, float(cx + j)));  y: cy2 = fma(i, C_vy, fma(j, C_vx, float(cy + i)))
+                const int dx = site((float)i, (float)j, pf[q][0], pf[q][1], 1000), dy = site((float)i, (float)j, pf[q][2], pf[q][3], 1000);
+                for (int X = -PATCH_R; X <= lim; X++)
+                    if (site((float)i, (float)j, pf[q][0], pf[q][1], X) != dx || site((float)i, (float)j, pf[q][2], pf[q][3], X) != dy) return false;
+                if (abs(dx + j) >= PAD || abs(dy + i) >= PAD) return false;
+                t.off[q][s] = (dy + i) * pw + (dx + j);
+            }
+    return true;
 }
 
 // d_flow_bilateral_filtering (bao_pmflow_refine_kernel.cu:764-799): (2R+1)^2 joint bilateral, R = 2*sig_s, skipping unknown
@@ -356,6 +513,19 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
     a.upsample = upsample;
     a.y0 = y0;
     dim3 blk(RF_PIX * 3), grd((g.w + RF_PIX - 1) / RF_PIX, y1 - y0, n);
+    if (c->prm.patch_stride == 2 && !(c->variant & EPPM_VAR_REFINE_GENERIC)) {
+        // table-driven kernel: the site table of this pitch was built and verified at eppm_create
+        const AffineTab* tabp = nullptr;
+        for (int l = 0; l < c->n_levels; l++)
+            if (c->aff_ok[l] && c->lv[l].pw == g.pw && c->lv[l].w >= g.w && c->lv[l].h >= g.h) tabp = &c->aff_tab[l];
+        const int tab_ok = tabp != nullptr;
+        if (tab_ok) {
+            if (c->variant & EPPM_VAR_REFINE_NOGROUP) k_c2f_refine_tab<false><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+            else k_c2f_refine_tab<true><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+            EPPM_LAUNCH_COUNT(1);
+            return;
+        }
+    }
     switch (c->prm.patch_stride) {  // sample stride is a compile-time constant of the kernel
     case 1: k_c2f_refine<1><<<grd, blk, 0, c->stream>>>(a, c->cost_lut); break;
     case 3: k_c2f_refine<3><<<grd, blk, 0, c->stream>>>(a, c->cost_lut); break;
