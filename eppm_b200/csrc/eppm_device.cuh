@@ -83,11 +83,21 @@ __device__ __forceinline__ float max3abs_diff(const float4& a, const float4& b) 
 // indexed by the XOR itself avoids POPC but was measured slower: its bank conflicts cost more L1 wavefronts than POPC costs XU slots.)
 constexpr int CENSUS_LUT_N = 9;
 __device__ __forceinline__ float census_lut(const float* s_census, const float4& p1, const float4& p2) {
-    // ld.shared on the 32-bit window address: ptxas folds the table's static offset into the LDS immediate, so the lookup is
-    // LOP3 + POPC + LDS (through a generic pointer it re-derives the window base with four uniform instructions per use)
+    const unsigned off = __popc(__float_as_uint(p1.w) ^ __float_as_uint(p2.w));
+    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_census) + off);
+}
+// The same lookup through a 32-bit shared-window address the caller computed ONCE (census_lut_base) and keeps in a register: on
+// sm_100 every shared address carries the CTA's rank in its cluster, and left alone ptxas re-derives that base (S2UR SR_CgaCtaId +
+// three uniform instructions, with the S2UR latency exposed) inside every block of the sample loop.
+__device__ __forceinline__ unsigned census_lut_base(const float* s_census) {
+    unsigned b = (unsigned)__cvta_generic_to_shared(s_census);
+    asm volatile("" : "+r"(b));
+    return b;
+}
+__device__ __forceinline__ float census_lut_at(unsigned base, const float4& p1, const float4& p2) {
     const unsigned off = __popc(__float_as_uint(p1.w) ^ __float_as_uint(p2.w));
     float v;
-    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(s_census) + off));
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + off));
     return v;
 }
 __device__ __forceinline__ void load_census_lut(float* s_census, const CostLut& lut) {
@@ -124,26 +134,28 @@ __device__ __forceinline__ float max3abs_diff(const PixPk& a, const PixPk& b) {
 //   cost   = 1 - exp(-c^2/lambda_ad^2) + LUT_census[popc(census1 ^ census2)],  c = max|rgb1-rgb2|
 //   weight = exp(-(d1^2 + d2^2)/sigma_r^2) * G[|j|]*G[|i|],                     dk = max|centre_k - p_k|
 // accumulated as cost_sum = fma(cost, weight, cost_sum); weight_sum += weight, in sample order.
-// d1 (image-1 side) is passed in -- packed as (0, d1) -- so callers can hoist it across candidates.  The AD chain
+// d1 (image-1 side) is passed in so callers can hoist it across candidates.  The AD chain
 // (c^2 -> /-0.01 -> *log2e) and the weight chain (arg -> /-0.01 -> *log2e) run side by side in the two halves of packed instructions.
 // sample_eval returns the AD+census cost and the exponent t2 of the range weight; the caller forms e2 = __expf-equivalent of t2
 // (ex2 with the `t2 < -126` fix-up, which a group of samples can share one test for), w = e2*gg, and accumulates.
-__device__ __forceinline__ void sample_eval(const float4& p1, const PixPk& p1k, const float4& p2, const PixPk& c2k, f32x2 zd1, const float* s_census,
+__device__ __forceinline__ float census_lut_ref(const float* s, const float4& p1, const float4& p2) { return census_lut(s, p1, p2); }
+__device__ __forceinline__ float census_lut_ref(unsigned base, const float4& p1, const float4& p2) { return census_lut_at(base, p1, p2); }
+template <class LutRef>
+__device__ __forceinline__ void sample_eval(const float4& p1, const PixPk& p1k, const float4& p2, const PixPk& c2k, float d1, LutRef s_census,
                                             float& cost, float& t2) {
     const PixPk p2k = pack_pix(p2);
     const float c = max3abs_diff(p1k, p2k);
     const float d2 = max3abs_diff(c2k, p2k);
-    const f32x2 cd = pk2(c, d2);
-    // (c^2, d1^2 + d2^2): the second half is the reference's fma(d1, d1, d2*d2); the first adds 0*0 to c^2 >= 0, which changes nothing.
-    // Staying packed avoids the register-pair copies a scalar FFMA into one half costs.
-    const f32x2 x = fma2(zd1, zd1, mul2(cd, cd));
+    // c^2 and arg = fma(d1, d1, d2*d2) as scalar instructions whose results land directly in the two halves of one register pair
+    // (squaring (c, d2) as a pair and patching one half afterwards costs two register copies)
+    const f32x2 x = pk2(__fmul_rn(c, c), __fmaf_rn(d1, d1, __fmul_rn(d2, d2)));
     const f32x2 R = pk2(-99.99999237060546875f, -99.99999237060546875f), D = pk2(0.010000000707805156708f, 0.010000000707805156708f);
     const f32x2 q0 = fma2(x, R, pk2(0.f, 0.f));
     const f32x2 rem = fma2(q0, D, x);
     const f32x2 q = fma2(R, rem, q0);
     float t1;
     upk2(mul2(q, pk2(1.4426950216293334961f, 1.4426950216293334961f)), t1, t2);
-    cost = __fadd_rn(__fadd_rn(1.0f, -ex2_mufu(t1)), census_lut(s_census, p1, p2));
+    cost = __fadd_rn(__fadd_rn(1.0f, -ex2_mufu(t1)), census_lut_ref(s_census, p1, p2));
 }
 // __expf of an exponent already multiplied by log2e, for the rare t < -126 case (see exp_ref)
 __device__ __forceinline__ float ex2_tiny(float t) {
@@ -152,10 +164,10 @@ __device__ __forceinline__ float ex2_tiny(float t) {
 }
 
 // sample_eval + the per-sample fix-up + accumulation: the plain form of one sample
-__device__ __forceinline__ void sample_term(const float4& p1, const PixPk& p1k, const float4& p2, const PixPk& c2k, f32x2 zd1, float gg,
+__device__ __forceinline__ void sample_term(const float4& p1, const PixPk& p1k, const float4& p2, const PixPk& c2k, float d1, float gg,
                                             const float* s_census, float& cost_sum, float& weight_sum) {
     float cost, t2;
-    sample_eval(p1, p1k, p2, c2k, zd1, s_census, cost, t2);
+    sample_eval(p1, p1k, p2, c2k, d1, s_census, cost, t2);
     const bool tiny = t2 < -126.0f;   // __expf fix-up (see exp_ref)
     if (tiny) t2 = __fmul_rn(t2, 0.5f);
     float e2 = ex2_mufu(t2);
@@ -176,7 +188,7 @@ __device__ __forceinline__ void sample_group(const float4 (&p1)[G], const float4
     for (int k = 0; k < G; k++) {
         const PixPk p1k = pack_pix(p1[k]);
         const float d1 = max3abs_diff(c1k, p1k);
-        sample_eval(p1[k], p1k, p2[k], c2k, pk2(0.f, d1), s_census, ct[k], t2[k]);
+        sample_eval(p1[k], p1k, p2[k], c2k, d1, s_census, ct[k], t2[k]);
         w[k] = __fmul_rn(ex2_mufu(t2[k]), gg[k]);
         tmin = fminf(tmin, t2[k]);
     }
@@ -236,7 +248,7 @@ __device__ __forceinline__ float patch_cost(const float4* __restrict__ A, const 
                 const float4 p2 = ldpix(B + (rb + (unsigned)(j * (int)sj)));
                 const PixPk p1k = pack_pix(p1);
                 const float d1 = max3abs_diff(c1k, p1k);
-                sample_term(p1, p1k, p2, c2k, pk2(0.f, d1), lut.gg[ai][j < 0 ? -j : j], s_census, cost_sum, weight_sum);
+                sample_term(p1, p1k, p2, c2k, d1, lut.gg[ai][j < 0 ? -j : j], s_census, cost_sum, weight_sum);
             }
         }
     }

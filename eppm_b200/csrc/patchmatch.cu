@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(128) k_pm_search_joint(PmArgs a, const short2*
     if (x >= a.w) return;
     const float4 *A, *B; short2* nnf; float* cost;
     pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
+    const unsigned lut_base = census_lut_base(s_census);
     const int id = y * a.w + x;
     const short2 entry = nnf[id];
     short gx[NG], gy[NG];
@@ -259,13 +260,13 @@ __global__ void __launch_bounds__(128) k_pm_search_joint(PmArgs a, const short2*
             const unsigned off = irow + (unsigned)j;
             const float4 p1 = ldpix(A + (oa + off));
             const PixPk p1k = pack_pix(p1);
-            const f32x2 zd1 = pk2(0.f, max3abs_diff(c1k, p1k));
+            const float d1 = max3abs_diff(c1k, p1k);
             const float gg = lut.gg[ai][j < 0 ? -j : j];
             float ct[NG], t2[NG], w[NG];
             float tmin = 0.f;
 #pragma unroll
             for (int k = 0; k < NG; k++) {
-                sample_eval(p1, p1k, ldpix(B + (ob[k] + off)), c2k[k], zd1, s_census, ct[k], t2[k]);
+                sample_eval(p1, p1k, ldpix(B + (ob[k] + off)), c2k[k], d1, lut_base, ct[k], t2[k]);
                 w[k] = __fmul_rn(ex2_mufu(t2[k]), gg);
                 tmin = fminf(tmin, t2[k]);
             }

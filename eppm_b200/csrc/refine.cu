@@ -125,7 +125,6 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine(RefineA
                 const PixPk p1k = pack_pix(p1);
                 const float d1 = max3abs_diff(c1k, p1k);
                 const float gg = lut.gg[ai][j < 0 ? -j : j];
-                const f32x2 zd1 = pk2(0.f, d1);
                 // x coordinates of the 4 models: cx2 = fma(i, C_uy, fma(j, C_ux, float(x1+j) + uu))   (:402, :440, :478 as contracted)
                 const float bx = __fadd_rn(uu, (float)(x + j));
                 int sx[4];
@@ -145,7 +144,7 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine(RefineA
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const float4 p2 = ldpix(I2 + (unsigned)(sy[q] * a.pw + sx[q]));
-                        sample_term(p1, p1k, p2, c2k[n], zd1, gg, s_census, cs[n][q], ws[n][q]);
+                        sample_term(p1, p1k, p2, c2k[n], d1, gg, s_census, cs[n][q], ws[n][q]);
                     }
                 }
             }
@@ -208,6 +207,7 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine_tab(Ref
     __shared__ int s_bn[3][RF_PIX];
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
+    const unsigned lut_base = census_lut_base(s_census);
     const int m = threadIdx.x >> 5, pl = threadIdx.x & 31;
     const int x = blockIdx.x * RF_PIX + pl, y = a.y0 + blockIdx.y;
     const bool in = x < a.w;
@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine_tab(Ref
         const float4* P[3];   // candidate centres in image 2 (rows that are not valid are clamped into the plane and never used)
 #pragma unroll
         for (int n = 0; n < 3; n++) {
-            const int cy = max(-PAD, min(a.h - 1 + PAD, (int)cyc + n - 1));
-            const int cxs = max(-PAD, min(a.w - 1 + PAD, (int)cx));
+            const int cy = max(0, min(a.h - 1, (int)cyc + n - 1));   // rows that are not valid are scored at a clamped centre and never used
+            const int cxs = max(0, min(a.w - 1, (int)cx));
             P[n] = I2 + (unsigned)((cy + PAD) * a.pw + cxs + PAD);
             c2k[n] = pack_pix(ldpix(P[n]));
             asm volatile("" : "+l"(P[n]));  // keep the three centre pointers in registers: every site is then one IMAD.WIDE away
@@ -255,18 +255,19 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine_tab(Ref
                 const PixPk p1k = pack_pix(p1);
                 const float d1 = max3abs_diff(c1k, p1k);
                 const float gg = lut.gg[ai][j < 0 ? -j : j];
-                const f32x2 zd1 = pk2(0.f, d1);
                 int off[4];
                 off[0] = irow + j;  // identity model: the exact integer site (cx + j, cy + i)
 #pragma unroll
                 for (int q = 0; q < 3; q++) off[q + 1] = tab.off[q][s];
 #pragma unroll
                 for (int n = 0; n < 3; n++) {
+#ifndef RF_NOVALID
                     if (!valid[n]) continue;
+#endif
                     if (GROUP_TINY) {
                         float ct[4], t2[4], w[4];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) sample_eval(p1, p1k, ldpix(pix_at(P[n], off[q])), c2k[n], zd1, s_census, ct[q], t2[q]);
+                        for (int q = 0; q < 4; q++) sample_eval(p1, p1k, ldpix(pix_at(P[n], off[q])), c2k[n], d1, lut_base, ct[q], t2[q]);
 #pragma unroll
                         for (int q = 0; q < 4; q++) w[q] = __fmul_rn(ex2_mufu(t2[q]), gg);
                         if (fminf(fminf(t2[0], t2[1]), fminf(t2[2], t2[3])) < -126.0f) {
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine_tab(Ref
                         }
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 4; q++) sample_term(p1, p1k, ldpix(pix_at(P[n], off[q])), c2k[n], zd1, gg, s_census, cs[n][q], ws[n][q]);
+                        for (int q = 0; q < 4; q++) sample_term(p1, p1k, ldpix(pix_at(P[n], off[q])), c2k[n], d1, gg, s_census, cs[n][q], ws[n][q]);
                     }
                 }
             }
