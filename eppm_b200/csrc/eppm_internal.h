@@ -18,6 +18,7 @@ enum {
     EPPM_VAR_REFINE_GENERIC = 1,   // plane-fitting refine: coordinates computed per sample instead of the verified site table
     EPPM_VAR_REFINE_NOGROUP = 2,   // table kernel with the per-sample __expf fix-up instead of the grouped test
     EPPM_VAR_SEARCH_SERIAL = 4,    // random search: one guess at a time instead of all guesses side by side
+    EPPM_VAR_SMOOTH_2ROW = 16,     // smoothing: the generic two-rows-per-thread kernel instead of four rows in packed pairs
     EPPM_VAR_PROP_NOSKIP = 8,      // propagation: evaluate candidates that equal the current target (the reference does)
 };
 
@@ -103,6 +104,7 @@ struct eppm_context {
     eppm::WmfLut wmf_lut;
     CUtensorMap tmap_pix0[eppm::MAX_LEVELS];     // TMA descriptors of the image-1 packed planes (smoothing tile loads)
     int tmap_ok[eppm::MAX_LEVELS] = {};
+    int tmap_box_h = 0;                          // tile height the tensor maps were encoded for
     int band_y0 = 0, band_y1 = 0;                // rows of the coarsest level this context owns (whole level unless tiled across GPUs)
     eppm::AffineTab aff_tab[eppm::MAX_LEVELS];   // per level (pitch): verified sample-site tables of the plane-fitting refine
     int aff_ok[eppm::MAX_LEVELS] = {};

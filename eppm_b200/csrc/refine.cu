@@ -476,6 +476,169 @@ __global__ void __launch_bounds__(SM_TX* SM_TY) k_flow_smooth(SmoothArgs a, cons
     }
 }
 
+// ---- smoothing, four rows per thread, packed pairs (default when R = 10) ----
+// CTA = 32 x 8 threads, every thread filters FOUR vertically adjacent pixels (y .. y+3) as two pairs (A,B) and (C,D): tile row t is
+// tap row dy = t - R - k of pixel k, so one shared-memory read of a tap (16 B colour + 8 B flow) feeds four pixels, and the two
+// pixels of a pair run side by side in the halves of packed FP32x2 instructions (sub, mul, fma -- each half IEEE-rounded like the
+// scalar instruction).  Every pixel still adds its 441 taps in (dy, dx) raster order.  Branch-free inner loop:
+//  * taps outside the image or with unknown flow carry the colour SMOOTH_FAR in the tile: their range weight is exp(-huge) = +0
+//    exactly and their flow is stored as 0, so fma(+0, 0, n) = n and w + 0 = w -- the reference's `continue` (:776,:778) bit for bit;
+//  * tile rows that are out of a pixel's 21-row window (one row per pixel at either end of a pair) get a spatial weight of 0.
+constexpr int S4_TX = 32, S4_TY = 8, S4_PY = 4, S4_R = 10;
+constexpr int S4_TW = S4_TX + 2 * S4_R, S4_TH = S4_TY * S4_PY + 2 * S4_R, S4_ROWS = 2 * S4_R + S4_PY;   // 52 x 52 tile, 24 tile rows per thread
+constexpr float SMOOTH_FAR = 1.0e4f;
+constexpr size_t S4_SMEM = (size_t)S4_TW * S4_TH * (sizeof(float4) + sizeof(float2)) + 2 * S4_ROWS * (S4_R + 1) * sizeof(float2);
+
+template <bool FAST_DIV>
+__device__ __forceinline__ void smooth_tap2(const SmoothArgs& a, f32x2 cx, f32x2 cy, f32x2 cz, const float4& p, const float2& fl, f32x2 gg, f32x2 r2, f32x2 nd2,
+                                            f32x2& nx, f32x2& ny, f32x2& ws) {
+    float ax, bx, ay, by, az, bz;
+    upk2(sub2(pk2(p.x, p.x), cx), ax, bx);                                            // :757  |p - c| per channel, both pixels of the pair
+    upk2(sub2(pk2(p.y, p.y), cy), ay, by);
+    upk2(sub2(pk2(p.z, p.z), cz), az, bz);
+    const f32x2 dr = pk2(fmaxf(fmaxf(fabsf(ax), fabsf(ay)), fabsf(az)), fmaxf(fmaxf(fabsf(bx), fabsf(by)), fabsf(bz)));
+    const f32x2 xx = mul2(dr, dr);
+    float ta, tb;
+    if (FAST_DIV) {
+        const f32x2 q0 = mul2(xx, r2);
+        const f32x2 q = fma2(fma2(q0, nd2, xx), r2, q0);
+        upk2(mul2(q, pk2(1.4426950216293334961f, 1.4426950216293334961f)), ta, tb);
+    } else {
+        float xa, xb;
+        upk2(xx, xa, xb);
+        ta = __fmul_rn(__fdiv_rn(xa, a.neg_sig_r2), 1.4426950216293334961f);
+        tb = __fmul_rn(__fdiv_rn(xb, a.neg_sig_r2), 1.4426950216293334961f);
+    }
+    // exp_ref on both halves (:758)
+    const bool tinya = ta < -126.0f, tinyb = tb < -126.0f;
+    if (tinya) ta = __fmul_rn(ta, 0.5f);
+    if (tinyb) tb = __fmul_rn(tb, 0.5f);
+    float ea = ex2_mufu(ta), eb = ex2_mufu(tb);
+    if (tinya) ea = __fmul_rn(ea, ea);
+    if (tinyb) eb = __fmul_rn(eb, eb);
+    const f32x2 wgt = mul2(pk2(ea, eb), gg);                                          // :759-760
+    nx = fma2(wgt, pk2(fl.x, fl.x), nx);                                              // :782-783
+    ny = fma2(wgt, pk2(fl.y, fl.y), ny);
+    ws = add2(ws, wgt);
+}
+
+template <bool FAST_DIV>
+__global__ void __launch_bounds__(S4_TX* S4_TY) k_flow_smooth4(SmoothArgs a, const __grid_constant__ SmoothLut lut, const __grid_constant__ CUtensorMap tmap,
+                                                               int use_tma) {
+    extern __shared__ __align__(128) float4 smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    constexpr int R = S4_R, TW = S4_TW, TH = S4_TH, NT = S4_TX * S4_TY;
+    float4* s_pix = smem;                                             // [TH][TW] colours of image 1
+    float2* s_flow = reinterpret_cast<float2*>(smem + TW * TH);       // [TH][TW]
+    float2* s_gg = s_flow + TW * TH;                                  // [pair][tile row t][|dx|]: spatial weights of the pair's two pixels
+    const int b = blockIdx.z;
+    const float2* f = a.src + (size_t)b * a.w * a.h;
+    const float4* img = a.pix + (size_t)b * a.plane + (size_t)PAD * a.pw + PAD;
+    const int x0 = blockIdx.x * S4_TX - R, y0 = a.y0 + blockIdx.y * S4_TY * S4_PY - R;
+    const int tid = threadIdx.y * S4_TX + threadIdx.x;
+    if (use_tma) {
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar, (unsigned)(TW * TH * sizeof(float4)));
+            tma_load_3d(s_pix, &tmap, (x0 + PAD) * 4, y0 + PAD, b, &s_bar);
+        }
+    }
+    // cBlfGaussian[|dx|] * cBlfGaussian[|dy|] (:759) for the two pixels k = 2*pair, 2*pair+1 of a thread at its tile row t: dy = t - R - k
+    for (int i = tid; i < 2 * S4_ROWS * (R + 1); i += NT) {
+        const int adx = i % (R + 1), t = (i / (R + 1)) % S4_ROWS, pr = i / ((R + 1) * S4_ROWS);
+        const int dy0 = t - R - 2 * pr, dy1 = dy0 - 1;
+        s_gg[i] = make_float2(abs(dy0) <= R ? __fmul_rn(lut.g[adx], lut.g[abs(dy0)]) : 0.f, abs(dy1) <= R ? __fmul_rn(lut.g[adx], lut.g[abs(dy1)]) : 0.f);
+    }
+    unsigned far_mask = 0;   // tile entries of this thread that must not contribute (outside the image / unknown flow)
+    {
+        int k = 0;
+        for (int i = tid; i < TW * TH; i += NT, k++) {
+            const int ty = i / TW, tx = i - ty * TW;
+            const int cx = x0 + tx, cy = y0 + ty;
+            float2 fl = make_float2(EPPM_UNKNOWN_FLOW, EPPM_UNKNOWN_FLOW);
+            float4 p = make_float4(SMOOTH_FAR, SMOOTH_FAR, SMOOTH_FAR, 0.f);
+            const bool inside = cx >= 0 && cy >= 0 && cx < a.w && cy < a.h;
+            if (inside) fl = f[(size_t)cy * a.w + cx];
+            const bool known = !(fmaxf(fl.x, fl.y) > EPPM_UNKNOWN_FLOW_THRESH);       // :778 (same truth table as x > T || y > T)
+            if (!known) { fl = make_float2(0.f, 0.f); far_mask |= 1u << k; }
+            else if (!use_tma) p = ldpix(img + (size_t)cy * a.pw + cx);
+            s_flow[i] = fl;
+            if (!use_tma) s_pix[i] = p;
+        }
+    }
+    if (use_tma) {
+        mbar_wait(&s_bar, 0);
+        int k = 0;
+        for (int i = tid; i < TW * TH; i += NT, k++)
+            if (far_mask >> k & 1) s_pix[i] = make_float4(SMOOTH_FAR, SMOOTH_FAR, SMOOTH_FAR, 0.f);
+    }
+    __syncthreads();
+    const int x = blockIdx.x * S4_TX + threadIdx.x;
+    const int ly = threadIdx.y * S4_PY;
+    const int y = a.y0 + blockIdx.y * S4_TY * S4_PY + ly;
+    if (x >= a.w || y >= a.y1) return;
+    // centre colours from the image itself (a centre with unknown flow is still filtered with its own colour, :764-771)
+    f32x2 cx[2], cy[2], cz[2];
+#pragma unroll
+    for (int pr = 0; pr < 2; pr++) {
+        const int ya = min(y + 2 * pr, a.h - 1), yb = min(y + 2 * pr + 1, a.h - 1);
+        const float4 ca = ldpix(img + (size_t)ya * a.pw + x), cb = ldpix(img + (size_t)yb * a.pw + x);
+        cx[pr] = pk2(ca.x, cb.x); cy[pr] = pk2(ca.y, cb.y); cz[pr] = pk2(ca.z, cb.z);
+    }
+    const f32x2 r2 = pk2(a.recip, a.recip), nd2 = pk2(-a.neg_sig_r2, -a.neg_sig_r2);
+    f32x2 nx[2], ny[2], ws[2];
+#pragma unroll
+    for (int pr = 0; pr < 2; pr++) nx[pr] = ny[pr] = ws[pr] = pk2(0.f, 0.f);
+    const int col = threadIdx.x + R;
+    // tile rows 0,1: pair (A,B) only; rows 2 .. 2R+1: both pairs; rows 2R+2, 2R+3: pair (C,D) only
+#pragma unroll 1
+    for (int t = 0; t < S4_ROWS; t++) {
+        const int rowb = (ly + t) * TW + col;
+        const float2* g0 = s_gg + t * (R + 1);
+        const float2* g1 = s_gg + (S4_ROWS + t) * (R + 1);
+        if (t >= 2 && t <= 2 * R + 1) {
+#pragma unroll 3
+            for (int dx = -R; dx <= R; dx++) {
+                const float4 p = s_pix[rowb + dx];
+                const float2 fl = s_flow[rowb + dx];
+                const int adx = dx < 0 ? -dx : dx;
+                const float2 ga = g0[adx], gb = g1[adx];
+                smooth_tap2<FAST_DIV>(a, cx[0], cy[0], cz[0], p, fl, pk2(ga.x, ga.y), r2, nd2, nx[0], ny[0], ws[0]);
+                smooth_tap2<FAST_DIV>(a, cx[1], cy[1], cz[1], p, fl, pk2(gb.x, gb.y), r2, nd2, nx[1], ny[1], ws[1]);
+            }
+        } else if (t < 2) {
+#pragma unroll 3
+            for (int dx = -R; dx <= R; dx++) {
+                const float2 ga = g0[dx < 0 ? -dx : dx];
+                smooth_tap2<FAST_DIV>(a, cx[0], cy[0], cz[0], s_pix[rowb + dx], s_flow[rowb + dx], pk2(ga.x, ga.y), r2, nd2, nx[0], ny[0], ws[0]);
+            }
+        } else {
+#pragma unroll 3
+            for (int dx = -R; dx <= R; dx++) {
+                const float2 gb = g1[dx < 0 ? -dx : dx];
+                smooth_tap2<FAST_DIV>(a, cx[1], cy[1], cz[1], s_pix[rowb + dx], s_flow[rowb + dx], pk2(gb.x, gb.y), r2, nd2, nx[1], ny[1], ws[1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int pr = 0; pr < 2; pr++) {
+        float n0, n1, m0, m1, w0, w1;
+        upk2(nx[pr], n0, n1); upk2(ny[pr], m0, m1); upk2(ws[pr], w0, w1);
+        const int ya = y + 2 * pr;
+        if (ya < a.y1) {
+            float2 o = f[(size_t)ya * a.w + x];
+            if (w0 != 0.f) o = make_float2(__fdiv_rn(n0, w0), __fdiv_rn(m0, w0));     // :790-796 (untouched otherwise)
+            a.dst[(size_t)b * a.w * a.h + (size_t)ya * a.w + x] = o;
+        }
+        if (ya + 1 < a.y1) {
+            float2 o = f[(size_t)(ya + 1) * a.w + x];
+            if (w1 != 0.f) o = make_float2(__fdiv_rn(n1, w1), __fdiv_rn(m1, w1));
+            a.dst[(size_t)b * a.w * a.h + (size_t)(ya + 1) * a.w + x] = o;
+        }
+    }
+}
+
 // Exhaustive check that the 3-instruction constant division equals div.rn for every float in [lo, hi) (bit patterns).
 __global__ void k_selftest_const_div(float d, float r, unsigned lo_bits, unsigned hi_bits, unsigned long long* mismatches) {
     unsigned long long local = 0;
@@ -547,6 +710,26 @@ void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pi
     volatile float one = 1.0f;
     a.recip = one / a.neg_sig_r2;
     a.fast_div = c->smooth_fast_div;
+    // TMA path: the plane must be one of the context's own image-1 planes (a tensor map exists per level, built for one tile shape)
+    int level = -1;
+    for (int l = 0; l < c->n_levels; l++)
+        if (pix1 == c->pix[0][l]) level = l;
+    static const CUtensorMap dummy = {};
+    if (a.R == S4_R && c->prm.blf_sig_r <= 10.f && !(c->variant & EPPM_VAR_SMOOTH_2ROW)) {
+        // four rows per thread, packed pairs (SMOOTH_FAR = 1e4 needs exp(-(1e4/sig_r)^2) == 0, true for any sig_r <= 10)
+        static bool attr4 = false;
+        if (!attr4) {
+            cudaFuncSetAttribute(k_flow_smooth4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4_SMEM);
+            cudaFuncSetAttribute(k_flow_smooth4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4_SMEM);
+            attr4 = true;
+        }
+        const int use_tma = level >= 0 && c->tmap_ok[level] && c->tmap_box_h == S4_TH;
+        dim3 blk(S4_TX, S4_TY), grd((g.w + S4_TX - 1) / S4_TX, (y1 - y0 + S4_TY * S4_PY - 1) / (S4_TY * S4_PY), n);
+        if (a.fast_div) k_flow_smooth4<true><<<grd, blk, S4_SMEM, c->stream>>>(a, c->smooth_lut, use_tma ? c->tmap_pix0[level] : dummy, use_tma);
+        else k_flow_smooth4<false><<<grd, blk, S4_SMEM, c->stream>>>(a, c->smooth_lut, use_tma ? c->tmap_pix0[level] : dummy, use_tma);
+        EPPM_LAUNCH_COUNT(1);
+        return;
+    }
     const int TW = SM_TX + 2 * a.R, TH = SM_TY * SM_PY + 2 * a.R;
     const size_t smem = (size_t)TW * TH * (sizeof(float4) + sizeof(float2)) + (size_t)(a.R + 1) * (a.R + 1) * sizeof(float);
     static bool attr_set = false;
@@ -555,13 +738,7 @@ void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pi
         attr_set = true;
     }
     dim3 blk(SM_TX, SM_TY), grd((g.w + SM_TX - 1) / SM_TX, (y1 - y0 + SM_TY * SM_PY - 1) / (SM_TY * SM_PY), n);
-    // TMA path: the plane must be one of the context's own image-1 planes (a tensor map exists per level) and the box must fit
-    // the 256-element limit of a tensor-map box dimension
-    int level = -1;
-    for (int l = 0; l < c->n_levels; l++)
-        if (pix1 == c->pix[0][l]) level = l;
-    const int use_tma = level >= 0 && c->tmap_ok[level] && TW * 4 <= 256 && TH <= 256;
-    static const CUtensorMap dummy = {};
+    const int use_tma = level >= 0 && c->tmap_ok[level] && c->tmap_box_h == TH && TW * 4 <= 256 && TH <= 256;
     k_flow_smooth<<<grd, blk, smem, c->stream>>>(a, c->smooth_lut, use_tma ? c->tmap_pix0[level] : dummy, use_tma);
     EPPM_LAUNCH_COUNT(1);
 }
@@ -577,7 +754,11 @@ bool build_smooth_tensor_maps(eppm_context* c) {
         cudaGetLastError();
         return false;
     }
-    const int R = 2 * c->prm.blf_sig_s, TW = SM_TX + 2 * R, TH = SM_TY * SM_PY + 2 * R;
+    // tile of the kernel op_smooth will pick: four rows per thread when R = 10, else the generic two-row kernel
+    const int R = 2 * c->prm.blf_sig_s;
+    const bool four = R == S4_R && c->prm.blf_sig_r <= 10.f && !(c->variant & EPPM_VAR_SMOOTH_2ROW);
+    const int TW = four ? S4_TW : SM_TX + 2 * R, TH = four ? S4_TH : SM_TY * SM_PY + 2 * R;
+    c->tmap_box_h = TH;
     for (int l = 0; l < c->n_levels; l++) {
         c->tmap_ok[l] = 0;
         if (TW * 4 > 256 || TH > 256) continue;
