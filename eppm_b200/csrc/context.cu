@@ -122,6 +122,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         delete c;
         return EPPM_ERR_ARG;
     }
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->n_sm = v; }
     c->variant = getenv("EPPM_VARIANT") ? atoi(getenv("EPPM_VARIANT")) : 0;
     c->profile = getenv("EPPM_PROFILE") && atoi(getenv("EPPM_PROFILE")) != 0;
     if (!cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return EPPM_ERR_CUDA; }
@@ -165,6 +166,14 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         c->nnf_tmp = A.take<short2>(B * nc);
         c->occl_list = A.take<int>(B * nc);
         c->occl_count = A.take<int>(64);
+        {
+            const int sl = p.prop_seg_length;
+            const size_t thr_row = (size_t)gc.h * ((gc.w + sl - 1) / sl), thr_col = (size_t)gc.w * ((gc.h + sl - 1) / sl);
+            const size_t thr = 2 * B * (thr_row > thr_col ? thr_row : thr_col);
+            c->prop_prev = A.take<short2>(thr);
+            c->prop_queue = A.take<int4>(thr);
+            c->prop_count = A.take<int>((size_t)(p.num_iter > 0 ? p.num_iter : 1) * 4 * sl);
+        }
         c->rng_init = A.take<short2>(nc);
         c->rng_search = A.take<short2>((size_t)(p.num_iter > 0 ? p.num_iter : 1) * (p.num_rand_guess > 0 ? p.num_rand_guess : 1) * nc);
         for (int i = 0; i < c->n_levels; i++) c->flow[i] = A.take<float2>(B * c->lv[i].w * c->lv[i].h);

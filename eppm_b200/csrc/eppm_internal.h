@@ -19,6 +19,8 @@ enum {
     EPPM_VAR_REFINE_NOGROUP = 2,   // table kernel with the per-sample __expf fix-up instead of the grouped test
     EPPM_VAR_SEARCH_SERIAL = 4,    // random search: one guess at a time instead of all guesses side by side
     EPPM_VAR_SMOOTH_2ROW = 16,     // smoothing: the generic two-rows-per-thread kernel instead of four rows in packed pairs
+    EPPM_VAR_PROP_NOCOMPACT = 32,  // propagation: skip per thread, but no compaction of the remaining evaluations across the CTA
+    EPPM_VAR_PROP_CTA = 64,        // propagation: CTA-local lock-step kernels (with compaction) instead of the global work queue
     EPPM_VAR_PROP_NOSKIP = 8,      // propagation: evaluate candidates that equal the current target (the reference does)
 };
 
@@ -94,6 +96,10 @@ struct eppm_context {
     short2* nnf_tmp = nullptr;                   // snapshot buffer for the in-place filters
     int* occl_list = nullptr;                    // compacted occluded pixels for WMF: [B*h_c*w_c]
     int* occl_count = nullptr;                   // [2] device counters
+    short2* prop_prev = nullptr;                 // propagation work queue: running target per (pair, direction, line, segment)
+    int4* prop_queue = nullptr;                  //   evaluations of the current lock-step
+    int* prop_count = nullptr;                   //   queue length per (pass, step): [num_iter * 4 * seg_len]
+    int n_sm = 148;
     short2* rng_init = nullptr;                  // [h_c][w_c] initial targets (same for every pair/direction)
     short2* rng_search = nullptr;                // [num_iter][num_guess][h_c][w_c] raw (short(r1), short(r2))
     // flow pyramid (+ snapshot buffer)

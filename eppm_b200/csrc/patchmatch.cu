@@ -13,6 +13,7 @@
 //    which fixes the two orderings the reference leaves to warp scheduling (segment-start read before the
 //    neighbour's last write; segment 1's first write to pixel 10 before segment 0's last) -- see DESIGN.md.
 #include <curand_kernel.h>
+#include <stdlib.h>
 
 #include "eppm_internal.h"
 
@@ -179,6 +180,201 @@ __global__ void __launch_bounds__(896) k_pm_propagate(PmArgs a, int seg_len, int
     }
 }
 
+// The same passes with the evaluations COMPACTED inside the CTA.  From the third iteration on three quarters of the candidates equal
+// the pixel's current target (measured at 1080p: 23 % of the threads need the 100 samples, yet 90 % of the warps contain one that
+// does).  Per lock-step: every thread decides whether it needs an evaluation, the ones that do are packed into a queue in shared
+// memory (ballot + per-warp counts), the first ceil(n/32) warps score the queue, owners pick up their result.  The propagation
+// order, the candidates and the strict '<' are those of k_pm_propagate; only which lane computes a cost changes.
+template <int DIR, int STRIDE>
+__global__ void __launch_bounds__(896) k_pm_propagate_c(PmArgs a, int seg_len, const __grid_constant__ CostLut lut) {
+    constexpr bool ROW = (DIR == 0 || DIR == 2), FWD = (DIR < 2);
+    __shared__ float s_census[CENSUS_LUT_N];
+    __shared__ int s_wcount[32];
+    extern __shared__ int2 s_dyn[];
+    const int nthreads = blockDim.x * blockDim.y;
+    int2* s_item = s_dyn;                                        // queue: (owner thread | position along the line << 16, candidate target)
+    float* s_res = reinterpret_cast<float*>(s_dyn + nthreads);   // cost of the owner's candidate
+    load_census_lut(s_census, lut);
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = (nthreads + 31) >> 5;
+    const int line0 = (ROW ? a.y0 : 0) + blockIdx.x * blockDim.x;
+    const int line = line0 + threadIdx.x;
+    const int seg = (ROW ? 0 : a.y0 / seg_len) + threadIdx.y;
+    const int n_line = ROW ? a.y1 : a.w;
+    const int len = ROW ? a.w : a.h;
+    const float4 *A, *B; short2* nnf; float* cost;
+    pm_select<ROW>(a, blockIdx.z, A, B, nnf, cost);
+    const int pitch = ROW ? a.ph : a.pw;
+    const bool active = line < n_line;
+    int start, end, steps;
+    if (FWD) {
+        start = seg == 0 ? 0 : seg * seg_len - 1;   // :1055-1058
+        end = min(len - 1, start + seg_len);
+        steps = end - start;
+    } else {
+        start = (seg + 1) * seg_len;                // :1085-1088
+        if (start >= len) start = len - 1;
+        end = seg * seg_len;
+        steps = start - end;
+    }
+    if (!active) steps = 0;
+    auto idx = [&](int l, int i) -> int { return ROW ? l * a.w + i : i * a.w + l; };
+    short2 prev = make_short2(0, 0);
+    if (steps > 0) prev = nnf[idx(line, start)];
+    __syncthreads();  // every segment has read its start pixel before any pixel is written
+    for (int t = 1; t <= seg_len; t++) {
+        bool need = false;
+        int i = 0, id = 0;
+        short2 cur = make_short2(0, 0);
+        if (t <= steps) {
+            i = FWD ? start + t : start - t;
+            id = idx(line, i);
+            if (DIR == 0) prev.x = min(prev.x + 1, a.w - 1);   // :1065/:1095/:1125/:1155
+            if (DIR == 1) prev.y = min(prev.y + 1, a.h - 1);
+            if (DIR == 2) prev.x = max(prev.x - 1, 0);
+            if (DIR == 3) prev.y = max(prev.y - 1, 0);
+            cur = nnf[id];
+            // a candidate equal to the current target would be scored by the evaluation that produced cost[id]: never '<'
+            need = !(prev.x == cur.x && prev.y == cur.y);
+        }
+        const unsigned bal = __ballot_sync(__activemask(), need);
+        if (lane == 0) s_wcount[warp] = __popc(bal);
+        __syncthreads();
+        int base = 0, total = 0;
+        for (int w = 0; w < nwarps; w++) {
+            const int cnt = s_wcount[w];
+            if (w < warp) base += cnt;
+            total += cnt;
+        }
+        if (need) s_item[base + __popc(bal & ((1u << lane) - 1))] = make_int2(tid | (i << 16), (int)(unsigned short)prev.x | ((int)prev.y << 16));
+        __syncthreads();
+        if (tid < total) {
+            const int2 it = s_item[tid];
+            const int owner = it.x & 0xffff, oi = it.x >> 16;
+            const int ol = line0 + owner % (int)blockDim.x;
+            const int x1 = ROW ? oi : ol, y1 = ROW ? ol : oi;
+            s_res[owner] = patch_cost<STRIDE, ROW>(A, B, pitch, x1, y1, (short)(it.y & 0xffff), (short)(it.y >> 16), lut, s_census);
+        }
+        __syncthreads();
+        if (need) {
+            const float cv = s_res[tid];
+            if (cv < cost[id]) {
+                nnf[id] = prev;
+                cost[id] = cv;
+            } else {
+                prev = cur;
+            }
+        }
+        __syncthreads();  // lock-step: step t of every segment completes before step t+1 starts
+    }
+}
+
+// ---- propagation as a global work queue (default) ----
+// A lock-step of a pass is two launches over the WHOLE batch: k_prop_decide (one thread per (pair, direction, scan line, segment):
+// shift the predecessor's target, compare with the pixel's own, enqueue the evaluations that are needed) and k_prop_eval (score
+// the queue with every SM, apply the strict '<' update, leave the segment's running target in the per-thread state).  Inside one
+// step all segments touch distinct pixels, and the launch boundary is the lock-step barrier, so the order of events is exactly
+// k_pm_propagate's.  Measured at 1080p: from the third iteration on 77 % of the candidates equal the current target and are never
+// scored; the CTA-local kernels cannot profit (their step time is the latency of one evaluation, however few lanes run it).
+struct PropGeom {
+    int n_line, line0;     // scan lines of the band and the first one
+    int n_seg, seg0;       // segments per line handled here and the first one
+    int len;               // pixels along a line
+    int total;             // threads = n_z * n_seg * n_line
+};
+
+template <int DIR>
+__global__ void __launch_bounds__(256) k_prop_decide(PmArgs a, PropGeom g, int seg_len, int t, short2* __restrict__ st_prev, int4* __restrict__ queue,
+                                                     int* __restrict__ counter) {
+    constexpr bool ROW = (DIR == 0 || DIR == 2), FWD = (DIR < 2);
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    bool need = false;
+    int4 item = make_int4(0, 0, 0, 0);
+    if (gid < g.total) {
+        const int ll = gid % g.n_line, r = gid / g.n_line;
+        const int seg = g.seg0 + r % g.n_seg, z = r / g.n_seg;
+        const int line = g.line0 + ll;
+        int start, steps;
+        if (FWD) {
+            start = seg == 0 ? 0 : seg * seg_len - 1;   // :1055-1058
+            steps = min(g.len - 1, start + seg_len) - start;
+        } else {
+            start = (seg + 1) * seg_len;                // :1085-1088
+            if (start >= g.len) start = g.len - 1;
+            steps = start - seg * seg_len;
+        }
+        if (t <= steps) {
+            const int dir = a.n_dirs == 2 ? (z & 1) : 0, b = a.n_dirs == 2 ? (z >> 1) : z;
+            const short2* nnf = a.nnf[dir] + (size_t)b * a.w * a.h;
+            short2 prev = t == 1 ? nnf[ROW ? line * a.w + start : start * a.w + line] : st_prev[gid];
+            const int i = FWD ? start + t : start - t;
+            if (DIR == 0) prev.x = min(prev.x + 1, a.w - 1);   // :1065/:1095/:1125/:1155
+            if (DIR == 1) prev.y = min(prev.y + 1, a.h - 1);
+            if (DIR == 2) prev.x = max(prev.x - 1, 0);
+            if (DIR == 3) prev.y = max(prev.y - 1, 0);
+            const int x1 = ROW ? i : line, y1 = ROW ? line : i;
+            const short2 cur = nnf[y1 * a.w + x1];
+            st_prev[gid] = prev;   // a skipped candidate equals the current target; an evaluated one is settled by k_prop_eval
+            // a candidate equal to the current target would be scored by the evaluation that produced cost[id]: never '<'
+            need = !(prev.x == cur.x && prev.y == cur.y);
+            item = make_int4(z, x1 | (y1 << 16), (int)(unsigned short)prev.x | ((int)prev.y << 16), gid);
+        }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, need);
+    if (bal) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counter, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (need) queue[base + __popc(bal & ((1u << lane) - 1))] = item;
+    }
+}
+
+template <int DIR, int STRIDE>
+__global__ void __launch_bounds__(128) k_prop_eval(PmArgs a, const int4* __restrict__ queue, const int* __restrict__ counter, short2* __restrict__ st_prev,
+                                                   const __grid_constant__ CostLut lut) {
+    constexpr bool ROW = (DIR == 0 || DIR == 2);
+    __shared__ float s_census[CENSUS_LUT_N];
+    load_census_lut(s_census, lut);
+    const int n = *counter;
+    const int pitch = ROW ? a.ph : a.pw;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int4 it = queue[k];
+        const float4 *A, *B; short2* nnf; float* cost;
+        pm_select<ROW>(a, it.x, A, B, nnf, cost);
+        const int x1 = it.y & 0xffff, y1 = it.y >> 16;
+        const short2 cand = make_short2((short)(it.z & 0xffff), (short)(it.z >> 16));
+        const float cv = patch_cost<STRIDE, ROW>(A, B, pitch, x1, y1, cand.x, cand.y, lut, s_census);
+        const int id = y1 * a.w + x1;
+        if (cv < cost[id]) {
+            nnf[id] = cand;
+            cost[id] = cv;
+        } else {
+            st_prev[it.w] = nnf[id];
+        }
+    }
+}
+
+template <int DIR, int STRIDE>
+static void launch_propagate_queue(eppm_context* c, const PmArgs& a, int n, int pass_index) {
+    const bool row = (DIR == 0 || DIR == 2);
+    const int sl = c->prm.prop_seg_length;
+    PropGeom g;
+    g.n_line = row ? a.y1 - a.y0 : a.w;
+    g.line0 = row ? a.y0 : 0;
+    g.n_seg = row ? (a.w + sl - 1) / sl : (a.y1 + sl - 1) / sl - a.y0 / sl;
+    g.seg0 = row ? 0 : a.y0 / sl;
+    g.len = row ? a.w : a.h;
+    g.total = a.n_dirs * n * g.n_seg * g.n_line;
+    int* counters = c->prop_count + (size_t)pass_index * sl;
+    cudaMemsetAsync(counters, 0, sizeof(int) * sl, c->stream);
+    const int eval_blocks = min((g.total + 127) / 128, c->n_sm * 12);
+    for (int t = 1; t <= sl; t++) {
+        k_prop_decide<DIR><<<(g.total + 255) / 256, 256, 0, c->stream>>>(a, g, sl, t, c->prop_prev, c->prop_queue, counters + t - 1);
+        k_prop_eval<DIR, STRIDE><<<eval_blocks, 128, 0, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
+    }
+    EPPM_LAUNCH_COUNT(2 * sl);
+}
+
 // Random search (d_update_random_guess): num_guess candidates drawn in windows of radius 30,15,7,3,1,1 around the
 // ENTRY best target, evaluated in order with strict '<'.
 template <int STRIDE>
@@ -304,9 +500,14 @@ static void launch_propagate(eppm_context* c, const PmArgs& a, int n) {
     // segments per line: all of them for row passes; only those inside the band for column passes (bands are segment aligned)
     const int n_seg = row ? (a.w + sl - 1) / sl : (a.y1 + sl - 1) / sl - a.y0 / sl;
     int lines = 32;  // adjacent scan lines per CTA = coalescing width; all segments of a line stay in one CTA (lock-step barrier)
+    static const int env_lines = getenv("EPPM_PROP_LINES") ? atoi(getenv("EPPM_PROP_LINES")) : 0;   // tuning knob
+    if (env_lines > 0) lines = env_lines;
     while (lines > 1 && lines * n_seg > 896) lines >>= 1;
     dim3 blk(lines, n_seg), grd((n_line + lines - 1) / lines, 1, a.n_dirs * n);
-    k_pm_propagate<DIR, STRIDE><<<grd, blk, 0, c->stream>>>(a, c->prm.prop_seg_length, !(c->variant & EPPM_VAR_PROP_NOSKIP), c->cost_lut);
+    if (c->variant & (EPPM_VAR_PROP_NOSKIP | EPPM_VAR_PROP_NOCOMPACT))
+        k_pm_propagate<DIR, STRIDE><<<grd, blk, 0, c->stream>>>(a, c->prm.prop_seg_length, !(c->variant & EPPM_VAR_PROP_NOSKIP), c->cost_lut);
+    else
+        k_pm_propagate_c<DIR, STRIDE><<<grd, blk, (size_t)lines * n_seg * (sizeof(int2) + sizeof(float)), c->stream>>>(a, c->prm.prop_seg_length, c->cost_lut);
     EPPM_LAUNCH_COUNT(1);
 }
 
@@ -349,10 +550,17 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
         EPPM_LAUNCH_COUNT(1);
     }
     for (int it = 0; it < c->prm.num_iter && step < n_steps; it++) {
-        if (run()) launch_propagate<0, STRIDE>(c, a, n);
-        if (run()) launch_propagate<1, STRIDE>(c, a, n);
-        if (run()) launch_propagate<2, STRIDE>(c, a, n);
-        if (run()) launch_propagate<3, STRIDE>(c, a, n);
+        if (c->variant & (EPPM_VAR_PROP_NOSKIP | EPPM_VAR_PROP_NOCOMPACT | EPPM_VAR_PROP_CTA)) {
+            if (run()) launch_propagate<0, STRIDE>(c, a, n);
+            if (run()) launch_propagate<1, STRIDE>(c, a, n);
+            if (run()) launch_propagate<2, STRIDE>(c, a, n);
+            if (run()) launch_propagate<3, STRIDE>(c, a, n);
+        } else {
+            if (run()) launch_propagate_queue<0, STRIDE>(c, a, n, it * 4 + 0);
+            if (run()) launch_propagate_queue<1, STRIDE>(c, a, n, it * 4 + 1);
+            if (run()) launch_propagate_queue<2, STRIDE>(c, a, n, it * 4 + 2);
+            if (run()) launch_propagate_queue<3, STRIDE>(c, a, n, it * 4 + 3);
+        }
         if (!run()) continue;
         const short2* rng = c->rng_search + (size_t)it * c->prm.num_rand_guess * g.w * g.h;
         if (c->prm.num_rand_guess == 6 && !(c->variant & EPPM_VAR_SEARCH_SERIAL))
