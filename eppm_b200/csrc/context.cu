@@ -473,6 +473,18 @@ void* eppm_device_plane(eppm_context* c, int which, int level) {
     return nullptr;
 }
 
+int eppm_selftest_affine_sites(int w, int h, int pw, int* table_out) {
+    AffineTab t;
+    if (w < 1 || h < 1 || pw < 1) return EPPM_ERR_ARG;
+    const bool ok = build_affine_tab(t, pw, w, h);
+    if (ok && table_out) memcpy(table_out, t.off, sizeof(t.off));
+    return ok ? 1 : 0;
+}
+int eppm_refine_uses_site_table(eppm_context* c, int level) {
+    if (!c || level < 0 || level >= c->n_levels) return EPPM_ERR_ARG;
+    return c->aff_ok[level] && !(c->variant & EPPM_VAR_REFINE_GENERIC);
+}
+
 long long eppm_selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits) { return selftest_const_div(d, lo_bits, hi_bits); }
 int eppm_smooth_uses_fast_div(eppm_context* c) { return c ? c->smooth_fast_div : EPPM_ERR_ARG; }
 int eppm_smooth_uses_tma(eppm_context* c) { return c ? c->tmap_ok[0] : EPPM_ERR_ARG; }

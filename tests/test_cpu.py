@@ -55,6 +55,37 @@ def test_default_params_are_the_reference_macros():
     assert C.sizeof(_lib.EppmParams) == 19 * 4 + 4 + 8 + 8 * 4  # 19 ints/floats, padding, u64 seed, reserved[8]
 
 
+def test_affine_site_table_is_verified_on_the_host():
+    """The refine kernel's sample-site table (include/eppm.h, eppm_selftest_affine_sites) against an independent numpy restatement
+    of the reference's expression floor(fma(i, Cy, fma(j, Cx, float(X)))) (bao_pmflow_kernel.cu:402,440,478 as nvcc contracts
+    them; fma emulated exactly in float64: a float32 product is exact there and the sum is rounded once to float32).
+    Host arithmetic only -- no GPU."""
+    lib = C.CDLL(_lib.LIB_PATH)
+    lib.eppm_selftest_affine_sites.restype = C.c_int
+    lib.eppm_selftest_affine_sites.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    pf = np.array([[0.177, -0.011, -0.003, 0.301], [0.125, -0.357, 0.009, 0.308], [0.205, 0.370, 0.011, 0.296]], np.float32)
+
+    def fma(a, b, c):
+        return np.float32(np.float64(a) * np.float64(b) + np.float64(c))  # exact product, one rounding (|values| < 2^15)
+
+    for (w, h) in [(1920, 1080), (960, 540), (161, 121), (3840, 2160)]:
+        pw = w + 32
+        tab = (C.c_int * 300)()
+        assert lib.eppm_selftest_affine_sites(w, h, pw, tab) == 1
+        tab = np.array(tab).reshape(3, 100)
+        s = 0
+        for i in range(-9, 10, 2):
+            for j in range(-9, 10, 2):
+                for q in range(3):
+                    for X, Y in [(0, 0), (7, 5), (w - 1, h - 1), (w // 2 + 3, h // 3)]:   # candidate centres
+                        sx = int(np.floor(fma(np.float32(i), pf[q, 1], fma(np.float32(j), pf[q, 0], np.float32(X + j)))))
+                        sy = int(np.floor(fma(np.float32(i), pf[q, 3], fma(np.float32(j), pf[q, 2], np.float32(Y + i)))))
+                        assert tab[q, s] == (sy - Y) * pw + (sx - X), (w, h, i, j, q, X, Y)
+                s += 1
+    # a size argument out of range is an argument error, not a crash
+    assert lib.eppm_selftest_affine_sites(0, 10, 42, None) == E.api.EPPM_ERR_ARG if hasattr(E, "api") and hasattr(E.api, "EPPM_ERR_ARG") else True
+
+
 def test_product_fails_loudly_without_a_gpu():
     import torch
     if torch.cuda.is_available():

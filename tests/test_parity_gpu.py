@@ -394,19 +394,44 @@ def test_unmodified_main_cpp_drop_in(tmp_path):
 @needs_ref
 def test_philox_mode_epe_delta(ref):
     """Stated counter-based RNG (EPPM_RNG_PHILOX, Philox4x32-10 keyed by seed with one sub-sequence per coarse pixel): the NNF is a
-    different random realisation, so the bar is the north star's: accuracy against ground truth within 0.05 px of the reference's."""
+    different random realisation, so the bar is the north star's: MEAN accuracy against ground truth within 0.05 px of the
+    reference's.  Averaged over three pairs: a single 436x1024 pair moves by +-0.05 px with the realisation alone (and the
+    reference's own result depends on how its in-place races resolve on the box at hand)."""
     h, w = 436, 1024
-    a, b, gt, valid = synth.make_pair(h, w, 1)
+    e_ref, e_me = [], []
     rc = ref.create(h, w)
-    ref.set_data(rc, a, b)
-    fr = ref.compute_flow(rc, h, w)
     p = E.default_params()
     p.rng_mode = 1
     ctx = E.EppmContext(h, w, 1, params=p)
-    fm = ctx.compute_batch_host(a[None], b[None])[0]
-    e_ref, e_me = synth.epe(fr, gt, valid), synth.epe(fm, gt, valid)
-    assert e_me <= e_ref + 0.05, (e_me, e_ref)
+    for idx in (1, 2, 3):
+        a, b, gt, valid = synth.make_pair(h, w, idx)
+        ref.set_data(rc, a, b)
+        fr = ref.compute_flow(rc, h, w)
+        fm = ctx.compute_batch_host(a[None], b[None])[0]
+        e_ref.append(synth.epe(fr, gt, valid)); e_me.append(synth.epe(fm, gt, valid))
+    assert np.mean(e_me) <= np.mean(e_ref) + 0.05, (e_me, e_ref)
     ref.destroy(rc); ctx.close()
+
+
+def test_variant_switches_compute_the_same_bits():
+    """Every tuned kernel has its plain predecessor behind EPPM_VARIANT (eppm_internal.h): site-table vs computed coordinates in the
+    refine, grouped vs per-sample __expf fix-up, joint vs serial random search, work-queue vs CTA-local propagation with and without
+    skipping / compaction, four-row packed vs two-row smoothing.  All of them must produce the flow of the default build bit for bit."""
+    h, w = 270, 480
+    a, b, _, _ = synth.make_batch(h, w, 2, first_idx=11, distinct=2)
+    flows = {}
+    try:
+        for v in (0, 1, 2, 4, 8, 16, 32, 64, 127):
+            os.environ["EPPM_VARIANT"] = str(v)
+            ctx = E.EppmContext(h, w, 2)
+            if v == 0:
+                assert ctx.lib.eppm_refine_uses_site_table(ctx._ctx, 0) == 1
+            flows[v] = ctx.compute_batch_host(a, b).copy()
+            ctx.close()
+    finally:
+        os.environ.pop("EPPM_VARIANT", None)
+    for v, f in flows.items():
+        assert np.array_equal(f.view(np.uint32), flows[0].view(np.uint32)), f"EPPM_VARIANT={v} differs from the default kernels"
 
 
 @pytest.mark.parametrize("name,depth,iters", [("d2i5", 2, 5), ("d4i2", 4, 2)])
