@@ -204,6 +204,32 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
     build_gauss_tables(c);
     build_rng_tables(c);
     if (!getenv("EPPM_NO_TMA")) build_smooth_tensor_maps(c);
+    {
+        // linear textures over the packed planes of the PatchMatch level (both images): element type uint4, point fetch by texel index
+        int max_lin = 0;
+        cudaDeviceGetAttribute(&max_lin, cudaDevAttrMaxTexture1DLinearWidth, c->device);
+        const size_t texels = (size_t)B * gc.plane;
+        for (int img = 0; img < 2 && texels <= (size_t)max_lin; img++) {
+            const float4* base = c->pix[img][c->n_levels - 1];
+            cudaResourceDesc rd = {};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = const_cast<float4*>(base);
+            rd.res.linear.desc = cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindUnsigned);
+            rd.res.linear.sizeInBytes = texels * sizeof(float4);
+            cudaTextureDesc td = {};
+            td.readMode = cudaReadModeElementType;
+            td.filterMode = cudaFilterModePoint;
+            td.addressMode[0] = cudaAddressModeClamp;
+            td.normalizedCoords = 0;
+            if (cudaCreateTextureObject(&c->tex_pm[img], &rd, &td, nullptr) == cudaSuccess) {
+                c->tex_pm_base[img] = base;
+                c->tex_pm_texels = texels;
+            } else {
+                cudaGetLastError();
+                c->tex_pm[img] = 0;
+            }
+        }
+    }
     if (!cuda_ok(cudaStreamSynchronize(c->stream), "context setup kernels")) { eppm_destroy(c); return EPPM_ERR_CUDA; }
     *out = c;
     return EPPM_OK;
@@ -213,6 +239,8 @@ void eppm_destroy(eppm_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int img = 0; img < 2; img++)
+        if (c->tex_pm[img]) cudaDestroyTextureObject(c->tex_pm[img]);
     if (c->arena.base) cudaFree(c->arena.base);
     for (int i = 0; i < 2; i++)
         if (c->h_pinned_in[i]) cudaFreeHost(c->h_pinned_in[i]);

@@ -95,7 +95,11 @@ __device__ __forceinline__ unsigned census_lut_base(const float* s_census) {
     return b;
 }
 __device__ __forceinline__ float census_lut_at(unsigned base, const float4& p1, const float4& p2) {
+#ifdef EPPM_WHATIF_NOPOPC   // timing experiment only (wrong results): how much of the kernel time is the XU pipe's POPC?
+    const unsigned off = (__float_as_uint(p1.w) ^ __float_as_uint(p2.w)) & 0x1cu;
+#else
     const unsigned off = __popc(__float_as_uint(p1.w) ^ __float_as_uint(p2.w));
+#endif
     float v;
     asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + off));
     return v;
@@ -156,7 +160,11 @@ __device__ __forceinline__ void sample_eval(const float4& p1, const PixPk& p1k, 
     const f32x2 q = fma2(R, rem, q0);
     float t1;
     upk2(mul2(q, pk2(1.4426950216293334961f, 1.4426950216293334961f)), t1, t2);
+#ifdef EPPM_WHATIF_NOEX2   // timing experiment only (wrong results): the AD term without its MUFU.EX2
+    cost = __fadd_rn(__fadd_rn(1.0f, -t1), census_lut_ref(s_census, p1, p2));
+#else
     cost = __fadd_rn(__fadd_rn(1.0f, -ex2_mufu(t1)), census_lut_ref(s_census, p1, p2));
+#endif
 }
 // __expf of an exponent already multiplied by log2e, for the rare t < -126 case (see exp_ref)
 __device__ __forceinline__ float ex2_tiny(float t) {

@@ -21,6 +21,10 @@ enum {
     EPPM_VAR_SMOOTH_2ROW = 16,     // smoothing: the generic two-rows-per-thread kernel instead of four rows in packed pairs
     EPPM_VAR_PROP_NOCOMPACT = 32,  // propagation: skip per thread, but no compaction of the remaining evaluations across the CTA
     EPPM_VAR_PROP_CTA = 64,        // propagation: CTA-local lock-step kernels (with compaction) instead of the global work queue
+    EPPM_VAR_REFINE_9WARP3 = 256,  // table refine with one candidate (four models) per thread: nine warps per 32 pixels, 72 registers, 3 CTAs per SM
+    EPPM_VAR_SEARCH_TEX3 = 512,    // random search: the three wide-window guesses gather their target side through the texture unit
+    EPPM_VAR_SEARCH_NOTEX = 1024,  //   ... none (default: the two widest)
+    EPPM_VAR_SEARCH_SPLIT3 = 65536,  //   ... three passes of two (64 registers, 8 CTAs)
     EPPM_VAR_PROP_NOSKIP = 8,      // propagation: evaluate candidates that equal the current target (the reference does)
 };
 
@@ -89,6 +93,9 @@ struct eppm_context {
     uchar4* blur_tmp[2] = {nullptr, nullptr};    // scratch for pyramid levels beyond the 2-octave fast path
     float4* pix[2][eppm::MAX_LEVELS] = {};       // [B][ph_l][pw_l] packed float rgb + census
     float4* pixT[2] = {nullptr, nullptr};        // column-major copies of the coarsest level ([B][pw][ph]) for row propagation
+    cudaTextureObject_t tex_pm[2] = {0, 0};      // linear uint4 textures over pix[img][coarsest]: scattered gathers of the random search
+    const float4* tex_pm_base[2] = {nullptr, nullptr};
+    size_t tex_pm_texels = 0;
     eppm::GaussTab gauss[eppm::MAX_LEVELS];      // [0] pre-blur, [i] blur feeding level i
     // PatchMatch state at the coarsest level: index = dir (0 fwd, 1 bwd)
     short2* nnf[2] = {nullptr, nullptr};         // [B][h_c][w_c]

@@ -88,15 +88,26 @@ struct PmArgs {
     int w, h;
     int n_dirs;             // 2: grid.z = pair*2 + direction; 1: forward only (legacy single-direction entry point)
     int y0, y1;             // row band [y0, y1) this launch owns (whole level unless the frame is tiled across GPUs); segment aligned
+    // optional texture path for scattered target-side gathers: linear uint4 textures over the packed planes of this level;
+    // texB[dir] is the one that holds direction dir's TARGET image, texB_off[dir] the texel index of pair 0's padded origin in it
+    cudaTextureObject_t tex[2];      // per image: linear texture that holds its packed planes (0 = none)
+    unsigned tex_off[2];             // texel index of pair 0's padded origin of pix[image] inside that texture
 };
 
+__device__ __forceinline__ float4 texpix(cudaTextureObject_t t, unsigned idx) {
+    const uint4 v = tex1Dfetch<uint4>(t, (int)idx);
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
 template <bool T>
 __device__ __forceinline__ void pm_select(const PmArgs& a, int z, const float4*& A, const float4*& B, short2*& nnf, float*& cost) {
     const int dir = a.n_dirs == 2 ? (z & 1) : 0, b = a.n_dirs == 2 ? (z >> 1) : z;
-    A = (T ? a.pixT[dir] : a.pix[dir]) + (size_t)b * a.plane;  // direction 1 swaps the images (…cuda.cpp:223-224)
-    B = (T ? a.pixT[dir ^ 1] : a.pix[dir ^ 1]) + (size_t)b * a.plane;
-    nnf = a.nnf[dir] + (size_t)b * a.w * a.h;
-    cost = a.cost[dir] + (size_t)b * a.w * a.h;
+    // selects, not array indexing: a dynamically indexed kernel parameter is copied to local memory first
+    const float4* i0 = T ? a.pixT[0] : a.pix[0];
+    const float4* i1 = T ? a.pixT[1] : a.pix[1];
+    A = (dir ? i1 : i0) + (size_t)b * a.plane;  // direction 1 swaps the images (…cuda.cpp:223-224)
+    B = (dir ? i0 : i1) + (size_t)b * a.plane;
+    nnf = (dir ? a.nnf[1] : a.nnf[0]) + (size_t)b * a.w * a.h;
+    cost = (dir ? a.cost[1] : a.cost[0]) + (size_t)b * a.w * a.h;
     asm volatile("" : "+l"(A), "+l"(B));  // keep the plane bases in registers: every load is then base + u32 offset
 }
 
@@ -304,7 +315,7 @@ __global__ void __launch_bounds__(256) k_prop_decide(PmArgs a, PropGeom g, int s
         }
         if (t <= steps) {
             const int dir = a.n_dirs == 2 ? (z & 1) : 0, b = a.n_dirs == 2 ? (z >> 1) : z;
-            const short2* nnf = a.nnf[dir] + (size_t)b * a.w * a.h;
+            const short2* nnf = (dir ? a.nnf[1] : a.nnf[0]) + (size_t)b * a.w * a.h;
             short2 prev = t == 1 ? nnf[ROW ? line * a.w + start : start * a.w + line] : st_prev[gid];
             const int i = FWD ? start + t : start - t;
             if (DIR == 0) prev.x = min(prev.x + 1, a.w - 1);   // :1065/:1095/:1125/:1155
@@ -414,9 +425,16 @@ __global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __res
 // evaluations are independent; the image-1 side of each sample (load, range distance, spatial weight) is computed once for the NG
 // candidates and the scattered image-2 gathers of the guesses overlap.  Each guess still adds its samples in the reference's order,
 // and the guesses are compared in order with strict '<', so the outcome is the serial kernel's bit for bit.
-template <int STRIDE, int NG>
-__global__ void __launch_bounds__(128) k_pm_search_joint(PmArgs a, const short2* __restrict__ rng, int search_range, int radius_min,
-                                                         const __grid_constant__ CostLut lut) {
+// NTEX: the first NTEX guesses (the wide windows: every lane of a warp reads a different line) fetch their target-side samples
+// through the texture unit instead of the LSU path, which spends one L1 wavefront per lane on them.
+// NSPLIT: the NG guesses are scored in NSPLIT passes over the patch, NG / NSPLIT side by side in each: fewer live registers (centre
+// colours, offsets and accumulators of the group only), more resident warps for a kernel that waits on its gathers; the image-1 side
+// of a sample is recomputed per pass.
+template <int STRIDE, int NG, int NTEX, int NSPLIT, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_pm_search_joint(PmArgs a, const short2* __restrict__ rng, int search_range, int radius_min,
+                                                               const __grid_constant__ CostLut lut) {
+    constexpr int GS = NG / NSPLIT;
+    static_assert(GS * NSPLIT == NG, "guesses must split evenly");
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y;
@@ -424,68 +442,76 @@ __global__ void __launch_bounds__(128) k_pm_search_joint(PmArgs a, const short2*
     const float4 *A, *B; short2* nnf; float* cost;
     pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
     const unsigned lut_base = census_lut_base(s_census);
+    const int zdir = a.n_dirs == 2 ? (blockIdx.z & 1) : 0, zb = a.n_dirs == 2 ? (blockIdx.z >> 1) : blockIdx.z;
+    const cudaTextureObject_t texB = zdir ? a.tex[0] : a.tex[1];   // a select on the block-uniform direction keeps the handle uniform
+    const unsigned tb = (zdir ? a.tex_off[0] : a.tex_off[1]) + (unsigned)zb * a.plane;
     const int id = y * a.w + x;
     const short2 entry = nnf[id];
-    short gx[NG], gy[NG];
-    unsigned ob[NG];
-    PixPk c2k[NG];
-    int mag = search_range;
-#pragma unroll
-    for (int k = 0; k < NG; k++) {
-        const short2 rr = rng[(size_t)k * a.w * a.h + id];
-        const unsigned r1 = (unsigned)(int)rr.x, r2 = (unsigned)(int)rr.y;   // :1557-1563
-        const short xmin = (short)max(entry.x - mag, 0), xmax = (short)min(entry.x + mag + 1, a.w + 1);
-        const short ymin = (short)max(entry.y - mag, 0), ymax = (short)min(entry.y + mag + 1, a.h + 1);
-        gx[k] = (short)(xmin + r1 % (unsigned)(xmax - xmin));
-        gy[k] = (short)(ymin + r2 % (unsigned)(ymax - ymin));
-        if (mag / 2 >= radius_min) mag /= 2;
-        ob[k] = (unsigned)(gx[k] + PAD) + (unsigned)(gy[k] + PAD) * (unsigned)a.pw;
-        c2k[k] = pack_pix(ldpix(B + ob[k]));
-    }
     const unsigned oa = (unsigned)(x + PAD) + (unsigned)(y + PAD) * (unsigned)a.pw;
     const PixPk c1k = pack_pix(ldpix(A + oa));
-    float cs[NG], ws[NG];
-#pragma unroll
-    for (int k = 0; k < NG; k++) cs[k] = ws[k] = 0.f;
-#pragma unroll 1
-    for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
-        const int ai = i < 0 ? -i : i;
-        const unsigned irow = (unsigned)(i * a.pw);
-#pragma unroll 2
-        for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE) {
-            const unsigned off = irow + (unsigned)j;
-            const float4 p1 = ldpix(A + (oa + off));
-            const PixPk p1k = pack_pix(p1);
-            const float d1 = max3abs_diff(c1k, p1k);
-            const float gg = lut.gg[ai][j < 0 ? -j : j];
-            float ct[NG], t2[NG], w[NG];
-            float tmin = 0.f;
-#pragma unroll
-            for (int k = 0; k < NG; k++) {
-                sample_eval(p1, p1k, ldpix(B + (ob[k] + off)), c2k[k], d1, lut_base, ct[k], t2[k]);
-                w[k] = __fmul_rn(ex2_mufu(t2[k]), gg);
-                tmin = fminf(tmin, t2[k]);
-            }
-            if (tmin < -126.0f) {   // rare: the __expf fix-up (see exp_ref), one test per NG samples
-#pragma unroll
-                for (int k = 0; k < NG; k++)
-                    if (t2[k] < -126.0f) w[k] = __fmul_rn(ex2_tiny(t2[k]), gg);
-            }
-#pragma unroll
-            for (int k = 0; k < NG; k++) {
-                cs[k] = __fmaf_rn(ct[k], w[k], cs[k]);
-                ws[k] = __fadd_rn(ws[k], w[k]);
-            }
-        }
-    }
     short2 best = entry;
     float best_cost = cost[id];
+    int mag = search_range;
 #pragma unroll
-    for (int k = 0; k < NG; k++) {
-        const float cv = __fdiv_rn(cs[k], ws[k]);
-        if (cv < best_cost) {
-            best = make_short2(gx[k], gy[k]);
-            best_cost = cv;
+    for (int g = 0; g < NSPLIT; g++) {
+        short gx[GS], gy[GS];
+        unsigned ob[GS];
+        PixPk c2k[GS];
+#pragma unroll
+        for (int k = 0; k < GS; k++) {
+            const short2 rr = rng[(size_t)(g * GS + k) * a.w * a.h + id];
+            const unsigned r1 = (unsigned)(int)rr.x, r2 = (unsigned)(int)rr.y;   // :1557-1563
+            const short xmin = (short)max(entry.x - mag, 0), xmax = (short)min(entry.x + mag + 1, a.w + 1);
+            const short ymin = (short)max(entry.y - mag, 0), ymax = (short)min(entry.y + mag + 1, a.h + 1);
+            gx[k] = (short)(xmin + r1 % (unsigned)(xmax - xmin));
+            gy[k] = (short)(ymin + r2 % (unsigned)(ymax - ymin));
+            if (mag / 2 >= radius_min) mag /= 2;
+            ob[k] = (unsigned)(gx[k] + PAD) + (unsigned)(gy[k] + PAD) * (unsigned)a.pw;
+            c2k[k] = pack_pix(ldpix(B + ob[k]));
+        }
+        float cs[GS], ws[GS];
+#pragma unroll
+        for (int k = 0; k < GS; k++) cs[k] = ws[k] = 0.f;
+#pragma unroll 1
+        for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
+            const int ai = i < 0 ? -i : i;
+            const unsigned irow = (unsigned)(i * a.pw);
+#pragma unroll 2
+            for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE) {
+                const unsigned off = irow + (unsigned)j;
+                const float4 p1 = ldpix(A + (oa + off));
+                const PixPk p1k = pack_pix(p1);
+                const float d1 = max3abs_diff(c1k, p1k);
+                const float gg = lut.gg[ai][j < 0 ? -j : j];
+                float ct[GS], t2[GS], w[GS];
+                float tmin = 0.f;
+#pragma unroll
+                for (int k = 0; k < GS; k++) {
+                    const float4 p2 = g * GS + k < NTEX ? texpix(texB, tb + ob[k] + off) : ldpix(B + (ob[k] + off));
+                    sample_eval(p1, p1k, p2, c2k[k], d1, lut_base, ct[k], t2[k]);
+                    w[k] = __fmul_rn(ex2_mufu(t2[k]), gg);
+                    tmin = fminf(tmin, t2[k]);
+                }
+                if (tmin < -126.0f) {   // rare: the __expf fix-up (see exp_ref), one test per GS samples
+#pragma unroll
+                    for (int k = 0; k < GS; k++)
+                        if (t2[k] < -126.0f) w[k] = __fmul_rn(ex2_tiny(t2[k]), gg);
+                }
+#pragma unroll
+                for (int k = 0; k < GS; k++) {
+                    cs[k] = __fmaf_rn(ct[k], w[k], cs[k]);
+                    ws[k] = __fadd_rn(ws[k], w[k]);
+                }
+            }
+        }
+        // guesses are compared in their order with strict '<' (:1577); groups are visited in that order too
+#pragma unroll
+        for (int k = 0; k < GS; k++) {
+            const float cv = __fdiv_rn(cs[k], ws[k]);
+            if (cv < best_cost) {
+                best = make_short2(gx[k], gy[k]);
+                best_cost = cv;
+            }
         }
     }
     nnf[id] = best;
@@ -541,6 +567,15 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
     a.w = g.w; a.h = g.h;
     a.n_dirs = n_dirs;
     a.y0 = c->band_y0; a.y1 = c->band_y1;
+    // textures over the planes (video-stream mode aliases image 2 into image 1's allocation one plane further, hence the search)
+    for (int i = 0; i < 2; i++) {
+        a.tex[i] = 0; a.tex_off[i] = 0;
+        for (int img = 0; img < 2; img++)
+            if (c->tex_pm[img] && a.pix[i] >= c->tex_pm_base[img] && a.pix[i] + (size_t)n * g.plane <= c->tex_pm_base[img] + c->tex_pm_texels) {
+                a.tex[i] = c->tex_pm[img];
+                a.tex_off[i] = (unsigned)(a.pix[i] - c->tex_pm_base[img]);
+            }
+    }
     dim3 blk(128), grd((g.w + 127) / 128, a.y1 - a.y0, n_dirs * n);
     // steps [first_step, n_steps): 0 = random field + cost, then per iteration 4 propagation passes and 1 random search
     int step = 0;
@@ -563,8 +598,15 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
         }
         if (!run()) continue;
         const short2* rng = c->rng_search + (size_t)it * c->prm.num_rand_guess * g.w * g.h;
-        if (c->prm.num_rand_guess == 6 && !(c->variant & EPPM_VAR_SEARCH_SERIAL))
-            k_pm_search_joint<STRIDE, 6><<<grd, blk, 0, c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut);
+        const bool tex_ok = a.tex[0] && a.tex[1];
+        const int v = c->variant;
+        const bool joint = c->prm.num_rand_guess == 6 && !(v & EPPM_VAR_SEARCH_SERIAL);
+#define EPPM_SEARCH(NT, NS, MB) k_pm_search_joint<STRIDE, 6, NT, NS, MB><<<grd, blk, 0, c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut)
+        if (joint && ((v & EPPM_VAR_SEARCH_NOTEX) || !tex_ok)) EPPM_SEARCH(0, 1, 4);
+        else if (joint && (v & EPPM_VAR_SEARCH_TEX3)) EPPM_SEARCH(3, 1, 4);
+        else if (joint && (v & EPPM_VAR_SEARCH_SPLIT3)) EPPM_SEARCH(2, 3, 8);
+        else if (joint) EPPM_SEARCH(2, 1, 4);
+#undef EPPM_SEARCH
         else
             k_pm_search<STRIDE><<<grd, blk, 0, c->stream>>>(a, rng, c->prm.num_rand_guess, c->prm.search_range, c->prm.search_radius_min, c->cost_lut);
         EPPM_LAUNCH_COUNT(1);

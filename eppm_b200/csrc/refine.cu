@@ -200,15 +200,19 @@ __device__ __forceinline__ const float4* pix_at(const float4* base, int off) {
     return r;
 }
 
-template <bool GROUP_TINY>
-__global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine_tab(RefineArgs a, const __grid_constant__ CostLut lut,
-                                                                             const __grid_constant__ AffineTab tab) {
-    __shared__ float s_best[3][RF_PIX];
-    __shared__ int s_bn[3][RF_PIX];
+// NCT = candidate rows per thread.  3: CTA = 3 warps, warp m owns candidate column m (96 registers, 18 warps per SM).
+// 1: CTA = 9 warps, warp (m, n) owns ONE candidate and its four models (72 registers, 27 warps per SM): the image-1 side of a
+// sample is shared by 4 instead of 12 accumulator pairs (33.4 instead of 30.7 instructions per sample).  Measured equal (8.70 vs 8.74 ms
+// per 1080p pair at level 0; 56 registers / 36 warps: 9.27 ms) -- the kernel is not occupancy bound; kept behind EPPM_VARIANT=256.
+template <bool GROUP_TINY, int NCT, int MINB>
+__global__ void __launch_bounds__(RF_PIX * 9 / NCT, MINB)
+    k_c2f_refine_tab(RefineArgs a, const __grid_constant__ CostLut lut, const __grid_constant__ AffineTab tab) {
+    __shared__ float s_best[9][RF_PIX];
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
     const unsigned lut_base = census_lut_base(s_census);
-    const int m = threadIdx.x >> 5, pl = threadIdx.x & 31;
+    const int wq = threadIdx.x >> 5, pl = threadIdx.x & 31;
+    const int m = NCT == 3 ? wq : wq / 3, n0 = NCT == 3 ? 0 : wq - 3 * m;
     const int x = blockIdx.x * RF_PIX + pl, y = a.y0 + blockIdx.y;
     const bool in = x < a.w;
     const int b = blockIdx.z;
@@ -219,30 +223,33 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine_tab(Ref
     const bool unknown = fl.x > EPPM_UNKNOWN_FLOW_THRESH || fl.y > EPPM_UNKNOWN_FLOW_THRESH;  // :2011
     const short cxc = (short)((short)(int)fl.x + x), cyc = (short)((short)(int)fl.y + y);     // :2014-2019
     const short cx = (short)(cxc + (m - 1));
-    float cost[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
-    bool valid[3];
+    float cost[NCT];
+    bool valid[NCT];
+    bool any = false;
 #pragma unroll
-    for (int n = 0; n < 3; n++) {
-        const short cy = (short)(cyc + (n - 1));
+    for (int n = 0; n < NCT; n++) {
+        const short cy = (short)(cyc + (n0 + n - 1));
+        cost[n] = FLT_MAX;
         valid[n] = in && !unknown && !(cx < 0 || cy < 0 || cx >= a.w || cy >= a.h);  // :2029
+        any = any || valid[n];
     }
-    if (valid[0] || valid[1] || valid[2]) {
-        float cs[3][4], ws[3][4];
+    if (any) {
+        float cs[NCT][4], ws[NCT][4];
 #pragma unroll
-        for (int n = 0; n < 3; n++)
+        for (int n = 0; n < NCT; n++)
 #pragma unroll
             for (int q = 0; q < 4; q++) cs[n][q] = ws[n][q] = 0.f;
         const float4* a0 = I1 + (unsigned)((y + PAD) * a.pw + x + PAD);
         const PixPk c1k = pack_pix(ldpix(a0));
-        PixPk c2k[3];
-        const float4* P[3];   // candidate centres in image 2 (rows that are not valid are clamped into the plane and never used)
+        PixPk c2k[NCT];
+        const float4* P[NCT];   // candidate centres in image 2 (rows that are not valid are clamped into the plane and never used)
 #pragma unroll
-        for (int n = 0; n < 3; n++) {
-            const int cy = max(0, min(a.h - 1, (int)cyc + n - 1));   // rows that are not valid are scored at a clamped centre and never used
+        for (int n = 0; n < NCT; n++) {
+            const int cy = max(0, min(a.h - 1, (int)cyc + n0 + n - 1));   // rows that are not valid are scored at a clamped centre and never used
             const int cxs = max(0, min(a.w - 1, (int)cx));
             P[n] = I2 + (unsigned)((cy + PAD) * a.pw + cxs + PAD);
             c2k[n] = pack_pix(ldpix(P[n]));
-            asm volatile("" : "+l"(P[n]));  // keep the three centre pointers in registers: every site is then one IMAD.WIDE away
+            asm volatile("" : "+l"(P[n]));  // keep the centre pointers in registers: every site is then one IMAD.WIDE away
         }
         int s = 0;
 #pragma unroll 1
@@ -260,9 +267,9 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine_tab(Ref
 #pragma unroll
                 for (int q = 0; q < 3; q++) off[q + 1] = tab.off[q][s];
 #pragma unroll
-                for (int n = 0; n < 3; n++) {
+                for (int n = 0; n < NCT; n++) {
 #ifndef RF_NOVALID
-                    if (!valid[n]) continue;
+                    if (NCT > 1 && !valid[n]) continue;
 #endif
                     if (GROUP_TINY) {
                         float ct[4], t2[4], w[4];
@@ -288,36 +295,32 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine_tab(Ref
             }
         }
 #pragma unroll
-        for (int n = 0; n < 3; n++) {
+        for (int n = 0; n < NCT; n++) {
             if (!valid[n]) continue;
             const float k1 = __fdiv_rn(cs[n][0], ws[n][0]), k2 = __fdiv_rn(cs[n][1], ws[n][1]);
             const float k3 = __fdiv_rn(cs[n][2], ws[n][2]), k4 = __fdiv_rn(cs[n][3], ws[n][3]);
             cost[n] = min_ref(k1, min_ref(k2, min_ref(k3, k4)));  // :512
         }
     }
-    float best = 999999.f;
-    int best_n = -1;
+    // candidates that are not valid never win: the reference skips them (:2029), here they carry +inf against the strict '<' below
 #pragma unroll
-    for (int n = 0; n < 3; n++)
-        if (valid[n] && cost[n] < best) { best = cost[n]; best_n = n; }
-    s_best[m][pl] = best;
-    s_bn[m][pl] = best_n;
+    for (int n = 0; n < NCT; n++) s_best[m * 3 + n0 + n][pl] = valid[n] ? cost[n] : __int_as_float(0x7f800000);
     __syncthreads();
-    float bcost = 999999.f;
-    int bm = -1, bn = -1;
-#pragma unroll
-    for (int mm = 0; mm < 3; mm++) {
-        const float oc = s_best[mm][pl];
-        const int on = s_bn[mm][pl];
-        if (on >= 0 && oc < bcost) { bcost = oc; bm = mm; bn = on; }
-    }
-    if (in && m == 0) {
+    if (in && wq == 0) {
         float2 out;
         if (unknown) out = make_float2(0.f, 0.f);
         else {
-            short bx = cxc, by = cyc;
-            if (bm >= 0) { bx = (short)(cxc + (bm - 1)); by = (short)(cyc + (bn - 1)); }
-            out = make_float2((float)(bx - x), (float)(by - y));
+            // arg-min in the reference's order: m outer, n inner, strict '<' against 999999 (:2024,:2031)
+            float bcost = 999999.f;
+            int bk = -1;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const float oc = s_best[k][pl];
+                if (oc < bcost) { bcost = oc; bk = k; }
+            }
+            short bx = cxc, by = cyc;   // :2020-2022 default = centre candidate
+            if (bk >= 0) { bx = (short)(cxc + (bk / 3 - 1)); by = (short)(cyc + (bk % 3 - 1)); }
+            out = make_float2((float)(bx - x), (float)(by - y));  // :2038-2039
         }
         a.flow[(size_t)b * a.w * a.h + (size_t)y * a.w + x] = out;
     }
@@ -684,8 +687,11 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
             if (c->aff_ok[l] && c->lv[l].pw == g.pw && c->lv[l].w >= g.w && c->lv[l].h >= g.h) tabp = &c->aff_tab[l];
         const int tab_ok = tabp != nullptr;
         if (tab_ok) {
-            if (c->variant & EPPM_VAR_REFINE_NOGROUP) k_c2f_refine_tab<false><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
-            else k_c2f_refine_tab<true><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+            const dim3 blk9(RF_PIX * 9);
+            const int v = c->variant;
+            if (v & EPPM_VAR_REFINE_NOGROUP) k_c2f_refine_tab<false, 3, RF_MINBLOCKS><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+            else if (v & EPPM_VAR_REFINE_9WARP3) k_c2f_refine_tab<true, 1, 3><<<grd, blk9, 0, c->stream>>>(a, c->cost_lut, *tabp);
+            else k_c2f_refine_tab<true, 3, RF_MINBLOCKS><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
             EPPM_LAUNCH_COUNT(1);
             return;
         }
