@@ -69,6 +69,12 @@ LEGACY_SYMBOLS = {
     "baoCudaBLF_C2F": (None, [_P] * 11 + [_I]),
     "baoCudaBLFCostFilterRefine": (None, [_P] * 5 + [_I, _I, _S, _S]),
     "baoCudaFlowSmoothing": (None, [_P, _P, _I, _I, _S, _S]),
+    "baoCudaLeftRightCheck_Buffered": (None, [_P] * 6 + [_I, _I, _S, _S]),
+    "baoCudaFlow2NNF": (None, [_P, _P, _I, _I, _S, _S]),
+    "baoCudaFlowCutoff": (None, [_P, _I, _I, _S, C.c_float]),
+    "baoEliminateStillRegionFlow": (None, [_P, _P, _P, _I, _I, _S]),
+    "baoCudaCensusTransform_Bicubic": (None, [_P, _P, _I, _I, _S, _P, _P, _I, _I, _S]),
+    "baoCudaSubpixRefine": (None, [_P] * 6 + [_I, _I, _S, _S, _S, _S]),
 }
 
 _lib = None

@@ -72,6 +72,9 @@ __device__ __forceinline__ float one_minus_exp_ref(float x) {
     return __fadd_rn(1.0f, -ex2_mufu(__fmul_rn(x, 1.4426950216293334961f)));
 }
 
+// the AD term 1 - __expf(-(c*c) / (LAMBDA_AD*LAMBDA_AD)) of one sample (bao_pmflow_kernel.cu:282-283, :576), scalar form
+__device__ __forceinline__ float exp_ad_cost(float c) { return one_minus_exp_ref(div_neg_0p01(__fmul_rn(c, c))); }
+
 __device__ __forceinline__ float max3abs_diff(const float4& a, const float4& b) {
     float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
     return fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));

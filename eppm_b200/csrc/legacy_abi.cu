@@ -2,6 +2,7 @@
 // uchar4 / u8 planes with a byte pitch, dense short2 / float / float2 planes.  Each entry point converts the foreign
 // image planes into this library's packed planes (one small kernel), runs the same kernels the eppm_* API runs, and
 // writes the result back in the foreign layout.  A context per (h, w) is created on first use and cached.
+#include <float.h>
 #include <stdio.h>
 
 #include <map>
@@ -55,6 +56,74 @@ void copy_in(eppm_context* c, T* dense, const T* foreign, size_t pitch, int w, i
 template <class T>
 void copy_out(eppm_context* c, T* foreign, size_t pitch, const T* dense, int w, int h) {
     cudaMemcpy2DAsync(foreign, pitch, dense, (size_t)w * sizeof(T), (size_t)w * sizeof(T), h, cudaMemcpyDeviceToDevice, c->stream);
+}
+
+// ---- stage functions the reference declares but compute_flow never calls (…cuda.cpp:40-62): small per-pixel kernels working
+// directly on the caller's (pitched) buffers
+
+// d_left_right_check_buffered (bao_pmflow_refine_kernel.cu:93-122): like the in-place check but with the looser threshold 50 and
+// the result written to a second buffer
+__global__ void k_lr_check_buffered(short2* __restrict__ out_nnf, float* __restrict__ out_cost, const short2* nnf, const float* cost,
+                                    const short2* __restrict__ nnf2, int w, int h, size_t cost_w, size_t disp_w) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const short2 d = nnf[y * disp_w + x];
+    short2 o = make_short2((short)INVALID_LOCATION, (short)INVALID_LOCATION);
+    float oc = FLT_MAX;
+    if (!(d.y < 0 || d.y >= h || d.x < 0 || d.x >= w)) {
+        const short2 d2 = nnf2[d.y * disp_w + d.x];
+        if (!(abs(d2.x - (short)x) > 50 || abs(d2.y - (short)y) > 50)) {   // DIFF_THRESH_2 (:93)
+            o = d;
+            oc = cost[y * cost_w + x];
+        }
+    }
+    out_nnf[y * disp_w + x] = o;
+    out_cost[y * cost_w + x] = oc;
+}
+
+// d_convert_flow_to_nnf (bao_pmflow_refine_kernel.cu:657-676)
+__global__ void k_flow_to_nnf(short2* __restrict__ nnf, const float2* __restrict__ flow, int w, int h, size_t flow_w, size_t disp_w) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const float2 f = flow[y * flow_w + x];
+    short2 d;
+    if (f.x > EPPM_UNKNOWN_FLOW_THRESH || f.y > EPPM_UNKNOWN_FLOW_THRESH) {
+        d = make_short2((short)INVALID_LOCATION, (short)INVALID_LOCATION);
+    } else {
+        d.x = short(__fadd_rn(f.x, (float)x));   // short(curFlow.x+id_x)
+        d.y = short(__fadd_rn(f.y, (float)y));
+    }
+    nnf[y * disp_w + x] = d;
+}
+
+// d_flow_cutoff (bao_pmflow_refine_kernel.cu:891-900) with the reference's __min/__max macros (basic/bao_basic_cuda.h:44-45)
+__global__ void k_flow_cutoff(float2* __restrict__ flow, int w, int h, size_t flow_w, float m) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float2 f = flow[y * flow_w + x];
+    const float nm = -m;
+    const float ax = (m < f.x) ? m : f.x, ay = (m < f.y) ? m : f.y;
+    f.x = (nm > ax) ? nm : ax;
+    f.y = (nm > ay) ? nm : ay;
+    flow[y * flow_w + x] = f;
+}
+
+// d_eliminate_still_region_flow + _d_compute_patch_dist_ad_L2 (bao_pmflow_kernel.cu:555-586, 2071-2081): unweighted mean of the
+// AD term over the 100 stride-2 samples of the patch at ZERO displacement; flow := 0 where it is <= 0.1
+__global__ void k_eliminate_still(float2* __restrict__ flow, const float4* __restrict__ A, const float4* __restrict__ B, int pw, int w, int h) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const unsigned o = (unsigned)(y + PAD) * pw + x + PAD;
+    float cs = 0.f, ws = 0.f;
+    for (int i = -PATCH_R; i <= PATCH_R; i += 2)
+        for (int j = -PATCH_R; j <= PATCH_R; j += 2) {
+            const float4 p1 = ldpix(A + (o + i * pw + j)), p2 = ldpix(B + (o + i * pw + j));
+            const float c = max3abs_diff(p1, p2);
+            cs = __fadd_rn(cs, exp_ad_cost(c));
+            ws = __fadd_rn(ws, 1.0f);
+        }
+    const float cost = __fdiv_rn(cs, ws);
+    if ((double)cost <= 0.1) flow[(size_t)y * w + x] = make_float2(0.f, 0.f);   // SIMILAR_MIN_COST is a double literal (:2071)
 }
 
 }  // namespace
@@ -204,6 +273,49 @@ void baoCudaFlowSmoothing(float2* d_flow, uchar4* d_img, int w, int h, size_t im
     copy_in(c, c->flow[0], d_flow, flow_pitch, w, h);
     op_smooth(c, c->flow[0], c->flow_tmp, c->pix[0][0], g, 1);
     copy_out(c, d_flow, flow_pitch, c->flow_tmp, w, h);
+}
+
+void baoCudaLeftRightCheck_Buffered(short2* d_disp_vec, float* d_cost, short2* d_disp_vec2, float* d_cost2, short2* d_disp_vec_temp,
+                                    float* d_cost_temp, int w, int h, size_t cost_pitch, size_t disp_pitch) {
+    // bao_pmflow_refine_kernel.cu:124-140: forward into the temp buffers, backward in place (a pixel only rewrites itself), then the
+    // temp buffers are copied back as DENSE h*w arrays (bao_cuda_copy_d2d) -- exact only for dense planes, like the reference
+    cudaStreamSynchronize(0);
+    const size_t cw = cost_pitch / sizeof(float), dw = disp_pitch / sizeof(short2);
+    dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
+    k_lr_check_buffered<<<grd, blk>>>(d_disp_vec_temp, d_cost_temp, d_disp_vec, d_cost, d_disp_vec2, w, h, cw, dw);
+    k_lr_check_buffered<<<grd, blk>>>(d_disp_vec2, d_cost2, d_disp_vec2, d_cost2, d_disp_vec, w, h, cw, dw);
+    cudaMemcpyAsync(d_disp_vec, d_disp_vec_temp, sizeof(short2) * (size_t)w * h, cudaMemcpyDeviceToDevice, 0);
+    cudaMemcpyAsync(d_cost, d_cost_temp, sizeof(float) * (size_t)w * h, cudaMemcpyDeviceToDevice, 0);
+    EPPM_LAUNCH_COUNT(2);
+    if (!cuda_ok(cudaStreamSynchronize(0), "baoCudaLeftRightCheck_Buffered")) complain("baoCudaLeftRightCheck_Buffered");
+}
+
+void baoCudaFlow2NNF(short2* d_disp_vec, float2* d_flow, int w, int h, size_t disp_pitch, size_t flow_pitch) {
+    cudaStreamSynchronize(0);
+    dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
+    k_flow_to_nnf<<<grd, blk>>>(d_disp_vec, d_flow, w, h, flow_pitch / sizeof(float2), disp_pitch / sizeof(short2));
+    EPPM_LAUNCH_COUNT(1);
+    if (!cuda_ok(cudaStreamSynchronize(0), "baoCudaFlow2NNF")) complain("baoCudaFlow2NNF");
+}
+
+void baoCudaFlowCutoff(float2* d_flow, int w, int h, size_t flow_pitch, float max_flow_val) {
+    cudaStreamSynchronize(0);
+    dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
+    k_flow_cutoff<<<grd, blk>>>(d_flow, w, h, flow_pitch / sizeof(float2), max_flow_val);
+    EPPM_LAUNCH_COUNT(1);
+    if (!cuda_ok(cudaStreamSynchronize(0), "baoCudaFlowCutoff")) complain("baoCudaFlowCutoff");
+}
+
+void baoEliminateStillRegionFlow(float2* d_flow, uchar4* d_img1, uchar4* d_img2, int w, int h, size_t img_pitch) {
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoEliminateStillRegionFlow");
+    const LevelGeom& g = c->lv[0];
+    op_pack_foreign(c->stream, d_img1, img_pitch, nullptr, 0, c->pix[0][0], g);
+    op_pack_foreign(c->stream, d_img2, img_pitch, nullptr, 0, c->pix[1][0], g);
+    dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
+    k_eliminate_still<<<grd, blk, 0, c->stream>>>(d_flow, c->pix[0][0], c->pix[1][0], g.pw, w, h);   // the flow plane is dense (:2090)
+    EPPM_LAUNCH_COUNT(1);
 }
 
 }  // extern "C"

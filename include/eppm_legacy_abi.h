@@ -48,6 +48,25 @@ void baoCudaBLFCostFilterRefine(float2* d_flow_vec, uchar4* d_img1, uchar4* d_im
 /* bao_pmflow_refine_kernel.cu:801-826 */
 void baoCudaFlowSmoothing(float2* d_flow, uchar4* d_img, int w, int h, size_t img_pitch, size_t flow_pitch);
 
+/* ---- declared by the reference's host class (…cuda.cpp:40-62) but not called by compute_flow ---- */
+/* bao_pmflow_refine_kernel.cu:93-140: left-right check with threshold 50 through caller-provided temp planes (dense h*w) */
+void baoCudaLeftRightCheck_Buffered(short2* d_disp_vec, float* d_cost, short2* d_disp_vec2, float* d_cost2, short2* d_disp_vec_temp,
+                                    float* d_cost_temp, int w, int h, size_t cost_pitch, size_t disp_pitch);
+/* bao_pmflow_refine_kernel.cu:657-676, 736-746: flow -> absolute targets, unknown flow -> INVALID_LOCATION */
+void baoCudaFlow2NNF(short2* d_disp_vec, float2* d_flow, int w, int h, size_t disp_pitch, size_t flow_pitch);
+/* bao_pmflow_refine_kernel.cu:891-912: clamp both components to [-max_flow_val, max_flow_val] */
+void baoCudaFlowCutoff(float2* d_flow, int w, int h, size_t flow_pitch, float max_flow_val);
+/* bao_pmflow_kernel.cu:555-586, 2071-2095: zero the flow where the two images already agree (mean AD term of the patch <= 0.1); dense flow plane */
+void baoEliminateStillRegionFlow(float2* d_flow, uchar4* d_img1, uchar4* d_img2, int w, int h, size_t img_pitch);
+/* bao_pmflow_census_kernel.cu:115-181: 3x3 census of the bicubic (B-spline) upsampled images, [h_up][w_up] u8 planes */
+void baoCudaCensusTransform_Bicubic(unsigned char* d_census1, unsigned char* d_census2, int w_up, int h_up, size_t census_pitch, uchar4* d_img1,
+                                    uchar4* d_img2, int w, int h, size_t img_pitch);
+/* bao_pmflow_refine_kernel.cu:395-634, 678-722: sub-pixel refinement of valid integer targets (5x5 half-pixel cost samples, least-squares
+ * quadric, <= 5 conjugate-gradient steps); census planes are those of baoCudaCensusTransform_Bicubic at [2h][2w]; pixels whose target is
+ * out of range, or whose quadric has no stationary point within 3 half-pixels, keep their flow */
+void baoCudaSubpixRefine(float2* d_flow, short2* d_disp_vec, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1_up, unsigned char* d_census2_up,
+                         int w, int h, size_t img_pitch, size_t census_pitch_up, size_t disp_pitch, size_t flow_pitch);
+
 #ifdef __cplusplus
 }
 #endif

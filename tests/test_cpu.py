@@ -31,7 +31,7 @@ def golden():
 def _declared(header):
     txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:eppm_|baoCuda)\w+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b((?:eppm_|bao[A-Z])\w+)\s*\(", txt)))
 
 
 def test_library_exports_every_declared_symbol():

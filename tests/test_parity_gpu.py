@@ -196,6 +196,100 @@ def test_consistency_and_c2f_stage_by_stage(ref, mine, chain):
 
 
 @needs_ref
+def test_uncalled_stage_functions_bit_exact(ref, mine, chain):
+    """Stage functions the reference's host class declares but compute_flow never calls (…cuda.cpp:40-62): buffered left-right check,
+    flow -> NNF, flow cut-off, still-region elimination.  All deterministic -> bit-exact against the reference build on identical buffers."""
+    img, dims, wc, hc = chain["img"], chain["dims"], chain["wc"], chain["hc"]
+    (nf, cf), (nb, cb) = chain["pm_ref"]
+    S, I, V = C.c_size_t, C.c_int, C.c_void_p
+    for lib in (ref.lib, mine):
+        lib.baoCudaLeftRightCheck_Buffered.argtypes = [V] * 6 + [I, I, S, S]; lib.baoCudaLeftRightCheck_Buffered.restype = None
+        lib.baoCudaFlow2NNF.argtypes = [V, V, I, I, S, S]; lib.baoCudaFlow2NNF.restype = None
+        lib.baoCudaFlowCutoff.argtypes = [V, I, I, S, C.c_float]; lib.baoCudaFlowCutoff.restype = None
+        lib.baoEliminateStillRegionFlow.argtypes = [V, V, V, I, I, S]; lib.baoEliminateStillRegionFlow.restype = None
+    tn, tc = torch.zeros_like(nf), torch.zeros_like(cf)
+    r, m = _both(ref, mine, lambda lib, t: lib.baoCudaLeftRightCheck_Buffered(P(t[0]), P(t[1]), P(t[2]), P(t[3]), P(t[4]), P(t[5]), wc, hc, wc * 4, wc * 4),
+                 [nf, cf, nb, cb, tn, tc])
+    for x, y in zip(r[:4], m[:4]):
+        assert same_bits(x.cpu().numpy(), y.cpu().numpy())
+    assert (r[0] < 0).any().item() and (r[0] >= 0).any().item()   # the check rejected some pixels and kept others
+    # flow -> NNF on a flow with fractional, negative, out-of-range and unknown entries
+    g = torch.Generator(device="cpu").manual_seed(5)
+    fl = (torch.rand((hc, wc, 2), generator=g) * 200 - 100)
+    fl[3:9, 5:40] = 1e10
+    fl[10, :] = 40000.0   # beyond the short range: the conversion saturates / wraps exactly like the reference's
+    fl = fl.cuda()
+    out = torch.zeros((hc, wc, 2), dtype=torch.int16, device="cuda")
+    r, m = _both(ref, mine, lambda lib, t: lib.baoCudaFlow2NNF(P(t[0]), P(t[1]), wc, hc, wc * 4, wc * 8), [out, fl])
+    assert torch.equal(r[0], m[0])
+    # cut-off (NaN and infinities included: the macros' comparison order decides what survives)
+    fl2 = fl.clone(); fl2[0, 0, 0] = float("nan"); fl2[0, 1, 1] = float("inf"); fl2[0, 2, 0] = float("-inf")
+    r, m = _both(ref, mine, lambda lib, t: lib.baoCudaFlowCutoff(P(t[0]), wc, hc, wc * 8, 37.5), [fl2])
+    assert same_bits(r[0].cpu().numpy(), m[0].cpu().numpy())
+    # still-region elimination at level 1: image 2 := image 1 on the left half, the real second frame on the right
+    h1, w1 = dims[1]
+    a1, pitch = img[0][1]
+    b1 = img[1][1][0].clone()
+    b1[:, : (w1 // 2) * 4] = a1[:, : (w1 // 2) * 4]
+    fl3 = torch.full((h1, w1, 2), 3.25, dtype=torch.float32, device="cuda")
+    r, m = _both(ref, mine, lambda lib, t: lib.baoEliminateStillRegionFlow(P(t[0]), P(a1), P(b1), w1, h1, pitch), [fl3])
+    assert same_bits(r[0].cpu().numpy(), m[0].cpu().numpy())
+    z = (r[0] == 0).all(-1)
+    assert z[:, : w1 // 2 - 12].all().item() and not z[:, w1 // 2 + 12:].all().item()
+
+
+@needs_ref
+def test_subpixel_refine_and_bicubic_census_vs_reference(mine, chain, tmp_path):
+    """baoCudaCensusTransform_Bicubic + baoCudaSubpixRefine (declared by the reference's host class, not called by
+    compute_flow).  Both are deterministic -> bit-exact on identical buffers.  The reference build is loaded from a PRIVATE copy of its
+    library: its sub-pixel entry point switches the file-scope image texture reference to linear filtering and never switches it back,
+    which would change the reference's own weighted-median / hole-filling results for every later test in this process."""
+    import shutil, time
+    priv = os.path.join(str(tmp_path), "libeppm_ref_subpix.so")
+    shutil.copy(refharness.REF_LIB, priv)
+    rlib = C.CDLL(priv)
+    S, I, V = C.c_size_t, C.c_int, C.c_void_p
+    for lib in (rlib, mine):
+        lib.baoCudaCensusTransform_Bicubic.argtypes = [V, V, I, I, S, V, V, I, I, S]; lib.baoCudaCensusTransform_Bicubic.restype = None
+        lib.baoCudaSubpixRefine.argtypes = [V] * 6 + [I, I, S, S, S, S]; lib.baoCudaSubpixRefine.restype = None
+        lib.baoCudaNNF2Flow.argtypes = [V, V, I, I, S, S]; lib.baoCudaNNF2Flow.restype = None
+    img, wc, hc = chain["img"], chain["wc"], chain["hc"]
+    (nf, cf), _ = chain["pm_ref"]
+    i1, pitch = img[0][2]
+    i2 = img[1][2][0]
+    wu, hu = 2 * wc, 2 * hc
+    cpitch = (wu + 511) // 512 * 512
+    res = {}
+    for name, lib in (("ref", rlib), ("mine", mine)):
+        c1 = torch.zeros((hu, cpitch), dtype=torch.uint8, device="cuda"); c2 = torch.zeros_like(c1)
+        lib.baoCudaCensusTransform_Bicubic(P(c1), P(c2), wu, hu, cpitch, P(i1), P(i2), wc, hc, pitch)
+        torch.cuda.synchronize()
+        res[name] = (c1, c2)
+    for k in range(2):
+        assert torch.equal(res["ref"][k][:, :wu], res["mine"][k][:, :wu]), f"bicubic census of image {k + 1} differs"
+    assert len(torch.unique(res["ref"][0][:, :wu])) > 100
+    c1, c2 = res["ref"]
+    flows, ms = {}, {}
+    for name, lib in (("ref", rlib), ("mine", mine)):
+        fl = torch.zeros((hc, wc, 2), dtype=torch.float32, device="cuda")
+        lib.baoCudaNNF2Flow(P(fl), P(nf), wc, hc, wc * 4, wc * 8)
+        base = fl.clone()
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        lib.baoCudaSubpixRefine(P(fl), P(nf), P(i1), P(i2), P(c1), P(c2), wc, hc, pitch, cpitch, wc * 4, wc * 8)
+        torch.cuda.synchronize(); ms[name] = (time.perf_counter() - t0) * 1e3
+        flows[name] = (fl.cpu().numpy(), base.cpu().numpy())
+    fr, base = flows["ref"]
+    fm, _ = flows["mine"]
+    changed = (fr != base).any(-1)
+    assert 0.2 < changed.mean() < 1.0, changed.mean()          # the stage really moved a good part of the field off the integer grid
+    assert np.abs(fr - base)[changed].max() <= 1.5 + 1e-6      # by at most 3 half-pixels
+    diff = fr.view(np.uint32) != fm.view(np.uint32)
+    print(f"subpix refine {wc}x{hc}: reference {ms['ref']:.2f} ms, this library {ms['mine']:.2f} ms, {changed.mean() * 100:.1f} % of the pixels refined, "
+          f"{int(diff.sum())} floats differ")
+    assert not diff.any(), f"{int(diff.sum())} of {diff.size} floats differ, max abs {np.abs(fr - fm).max()}"
+
+
+@needs_ref
 def test_flow_smoothing_bit_exact_single_warp(ref, mine):
     """A 16x2 image is one warp of the reference's kernel: lock-step execution = all reads before all writes, so its in-place
     filter is race-free there and must equal the snapshot filter bit for bit (exercises every |dx| <= 10 weight, |dy| <= 1)."""
@@ -416,12 +510,13 @@ def test_philox_mode_epe_delta(ref):
 def test_variant_switches_compute_the_same_bits():
     """Every tuned kernel has its plain predecessor behind EPPM_VARIANT (eppm_internal.h): site-table vs computed coordinates in the
     refine, grouped vs per-sample __expf fix-up, joint vs serial random search, work-queue vs CTA-local propagation with and without
-    skipping / compaction, four-row packed vs two-row smoothing.  All of them must produce the flow of the default build bit for bit."""
+    skipping / compaction, four-row packed vs two-row smoothing, three- vs nine-warp refine, texture vs LSU gathers and one vs three
+    passes in the random search.  All of them must produce the flow of the default build bit for bit."""
     h, w = 270, 480
     a, b, _, _ = synth.make_batch(h, w, 2, first_idx=11, distinct=2)
     flows = {}
     try:
-        for v in (0, 1, 2, 4, 8, 16, 32, 64, 127):
+        for v in (0, 1, 2, 4, 8, 16, 32, 64, 127, 256, 512, 1024, 65536):
             os.environ["EPPM_VARIANT"] = str(v)
             ctx = E.EppmContext(h, w, 2)
             if v == 0:
