@@ -231,8 +231,8 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": "k_c2f_refine_tab (level 0)", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
                          "frac": round(achieved / hbm_peak, 5),
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from `ncu --set full` (profiles/r01_ncu_refine_tab_l0_summary.txt:
-                         # 287.72 + 57.03 MB for a 4-pair launch), scaled to the pairs of the timed launch; algorithmic = 87.1 MB / pair
-                         "traffic": int(round((287.722240e6 + 57.033728e6) / 4 * n_last)) if (H, W) == (1080, 1920) else None,
+                         # 288.36 + 59.46 MB for a 4-pair launch), scaled to the pairs of the timed launch; algorithmic = 87.1 MB / pair
+                         "traffic": int(round((288.360192e6 + 59.462144e6) / 4 * n_last)) if (H, W) == (1080, 1920) else None,
                          "peak_source": peak_src,
                          "note": "the path is FP32-issue bound, not HBM bound (SURVEY.md §8d); see roofline_alu"},
             "roofline_alu": {"bound": "fp32 issue", "kernel_samples_per_s": round(cnt["refine_l0_samples"] * n_last / (k_ms / 1e3), 1),

@@ -289,6 +289,27 @@ def test_subpixel_refine_and_bicubic_census_vs_reference(mine, chain, tmp_path):
     assert not diff.any(), f"{int(diff.sum())} of {diff.size} floats differ, max abs {np.abs(fr - fm).max()}"
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "refsub_*.npz"))))
+def test_subpixel_refine_against_committed_reference_fixture(mine, path):
+    """The same stage against outputs of the reference build committed under tests/golden (tools/gen_golden_subpix.py): runs without oracle/_ref."""
+    z = np.load(path)
+    h, w = int(z["h"]), int(z["w"])
+    S, I, V = C.c_size_t, C.c_int, C.c_void_p
+    mine.baoCudaCensusTransform_Bicubic.argtypes = [V, V, I, I, S, V, V, I, I, S]; mine.baoCudaCensusTransform_Bicubic.restype = None
+    mine.baoCudaSubpixRefine.argtypes = [V] * 6 + [I, I, S, S, S, S]; mine.baoCudaSubpixRefine.restype = None
+    i1, pitch = refharness.pitched(z["rgba1"]); i2, _ = refharness.pitched(z["rgba2"])
+    wu, hu = 2 * w, 2 * h
+    cp = (wu + 511) // 512 * 512
+    u1 = torch.zeros((hu, cp), dtype=torch.uint8, device="cuda"); u2 = torch.zeros_like(u1)
+    mine.baoCudaCensusTransform_Bicubic(P(u1), P(u2), wu, hu, cp, P(i1), P(i2), w, h, pitch)
+    torch.cuda.synchronize()
+    assert np.array_equal(u1[:, :wu].cpu().numpy(), z["census1_up"]) and np.array_equal(u2[:, :wu].cpu().numpy(), z["census2_up"])
+    fl = dev(z["flow_in"]); nnf = dev(z["nnf"])
+    mine.baoCudaSubpixRefine(P(fl), P(nnf), P(i1), P(i2), P(u1), P(u2), w, h, pitch, cp, w * 4, w * 8)
+    torch.cuda.synchronize()
+    assert same_bits(fl.cpu().numpy(), z["flow_out"])
+
+
 @needs_ref
 def test_flow_smoothing_bit_exact_single_warp(ref, mine):
     """A 16x2 image is one warp of the reference's kernel: lock-step execution = all reads before all writes, so its in-place
