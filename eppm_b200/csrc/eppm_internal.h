@@ -135,6 +135,7 @@ extern unsigned long long g_launches;
 void run_prepare(eppm_context* c, const uint8_t* d_img1, const uint8_t* d_img2, int n);
 void run_patchmatch(eppm_context* c);
 void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps = 1 << 30, int first_step = 0);
+bool run_patchmatch_planefitting(eppm_context* c);   // baoCudaPatchMatch_PlaneFitting: forward direction of pair 0, coarsest-level planes
 void run_c2f_step(eppm_context* c, int level, int kind, float2* out);
 bool build_smooth_tensor_maps(eppm_context* c);
 void band_rows(const eppm_context* c, int level, int* y0, int* y1);
@@ -151,6 +152,7 @@ void wmf_sweeps(eppm_context* c, short2*& cur, short2*& other, const float4* pix
                 bool only_occlusion);
 void op_fill_holes(cudaStream_t s, const short2* src, short2* dst, const float4* pix, size_t plane, int pw, int w, int h, int n);
 void op_nnf_to_flow(cudaStream_t s, const short2* nnf, float2* flow, int w, int h, int n);
+void op_flow_bilateral_upsample(eppm_context* c, float2* dst, const float4* pix1, const eppm::LevelGeom& g, const float2* small, int ws, float ratio);
 void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const LevelGeom& g, const float2* coarse, int ws, int hs, int upsample,
                float2* out, int n, int y0 = 0, int y1 = -1);
 long long selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits);

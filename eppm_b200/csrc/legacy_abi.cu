@@ -175,6 +175,19 @@ void baoCudaPatchMatch(short2* d_disp_vec, float* d_cost, uchar4* d_img1, uchar4
     copy_out(c, d_cost, cost_pitch, c->cost[0], w, h);
 }
 
+void baoCudaPatchMatch_PlaneFitting(short2* d_disp_vec, float* d_cost, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1,
+                                    unsigned char* d_census2, int w, int h, size_t img_pitch, size_t cost_pitch, size_t disp_pitch, size_t census_pitch) {
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaPatchMatch_PlaneFitting");
+    const LevelGeom& g = c->lv[0];
+    op_pack_foreign(c->stream, d_img1, img_pitch, d_census1, census_pitch, c->pix[0][0], g);
+    op_pack_foreign(c->stream, d_img2, img_pitch, d_census2, census_pitch, c->pix[1][0], g);
+    if (!run_patchmatch_planefitting(c)) { complain("baoCudaPatchMatch_PlaneFitting"); return; }
+    copy_out(c, d_disp_vec, disp_pitch, c->nnf[0], w, h);
+    copy_out(c, d_cost, cost_pitch, c->cost[0], w, h);
+}
+
 void baoCudaLeftRightCheck(short2* d_disp_vec, float* d_cost, short2* d_disp_vec2, float* d_cost2, int w, int h, size_t cost_pitch,
                            size_t disp_pitch) {
     eppm_context* c = get_ctx(g_single, h, w, 1);
@@ -262,6 +275,17 @@ void baoCudaBLF_C2F(float2** pFlowPyr, uchar4** pImgPyr1, uchar4** pImgPyr2, uns
     op_pack_foreign(c->stream, pImgPyr1[l], arrPitchUchar4[l], pCensusPyr1[l], arrPitchUchar1[l], c->pix[0][0], g);
     op_pack_foreign(c->stream, pImgPyr2[l], arrPitchUchar4[l], pCensusPyr2[l], arrPitchUchar1[l], c->pix[1][0], g);
     op_refine(c, c->pix[0][0], c->pix[1][0], g, pFlowPyr[l + 1], arrW[l + 1], arrH[l + 1], 1, pFlowPyr[l], 1);
+}
+
+void baoCudaFlowBilteralUpsampling(float2* d_flow_vec, uchar4* d_img, int w, int h, size_t img_pitch, float2* d_flow_vec_small, int w_s, int h_s,
+                                   float ratio_up) {
+    (void)h_s;
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaFlowBilteralUpsampling");
+    const LevelGeom& g = c->lv[0];
+    op_pack_foreign(c->stream, d_img, img_pitch, nullptr, 0, c->pix[0][0], g);
+    op_flow_bilateral_upsample(c, d_flow_vec, c->pix[0][0], g, d_flow_vec_small, w_s, ratio_up);   // both flow planes dense (:883-884)
 }
 
 void baoCudaFlowSmoothing(float2* d_flow, uchar4* d_img, int w, int h, size_t img_pitch, size_t flow_pitch) {

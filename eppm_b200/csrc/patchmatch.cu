@@ -537,6 +537,166 @@ static void launch_propagate(eppm_context* c, const PmArgs& a, int n) {
     EPPM_LAUNCH_COUNT(1);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// baoCudaPatchMatch_PlaneFitting (bao_pmflow_kernel.cu:1897-1963): the same PatchMatch with the plane-fitting cost of the refine
+// stage, _d_compute_patch_dist_planefitting (:334-513) = min over the identity and three fixed affine patch models.  Declared by the
+// reference's host class, called nowhere; one direction, one pair (legacy stage ABI only), plain one-thread-per-evaluation kernels.
+__constant__ float c_pf_pm[3][4] = {
+    {0.177f, -0.011f, -0.003f, 0.301f},   // COEF_FL_{U_X,U_Y,V_X,V_Y} (:319-332)
+    {0.125f, -0.357f, 0.009f, 0.308f},    // COEF_LEFT_*
+    {0.205f, 0.370f, 0.011f, 0.296f},     // COEF_RIGHT_*
+};
+
+__device__ float patch_cost_pf(const float4* __restrict__ A, const float4* __restrict__ B, int pw, int x1, int y1, int x2, int y2, const CostLut& lut,
+                               const float* s_census) {
+    const float4* a0 = A + (unsigned)((y1 + PAD) * pw + x1 + PAD);
+    const PixPk c1k = pack_pix(ldpix(a0));
+    const PixPk c2k = pack_pix(ldpix(B + (unsigned)((y2 + PAD) * pw + x2 + PAD)));
+    const float uu = (float)(x2 - x1), vv = (float)(y2 - y1);   // :350-351
+    float cs[4] = {0.f, 0.f, 0.f, 0.f}, ws[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int i = -PATCH_R; i <= PATCH_R; i += 2) {
+        const float fi = (float)i;
+        const int ai = i < 0 ? -i : i;
+        const float by = __fadd_rn((float)(y1 + i), vv);
+#pragma unroll 2
+        for (int j = -PATCH_R; j <= PATCH_R; j += 2) {
+            const float fj = (float)j;
+            const float4 p1 = ldpix(a0 + i * pw + j);
+            const PixPk p1k = pack_pix(p1);
+            const float d1 = max3abs_diff(c1k, p1k);
+            const float gg = lut.gg[ai][j < 0 ? -j : j];
+            const float bx = __fadd_rn(uu, (float)(x1 + j));
+            int sx[4], sy[4];
+            sx[0] = x2 + j; sy[0] = y2 + i;   // identity model: exact integers
+#pragma unroll
+            for (int q = 0; q < 3; q++) {     // cx2 = fma(i, C_uy, fma(j, C_ux, bx)), point fetch = floor (:402,:440,:478 as contracted)
+                sx[q + 1] = __float2int_rd(__fmaf_rn(fi, c_pf_pm[q][1], __fmaf_rn(fj, c_pf_pm[q][0], bx)));
+                sy[q + 1] = __float2int_rd(__fmaf_rn(fi, c_pf_pm[q][3], __fmaf_rn(fj, c_pf_pm[q][2], by)));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                sample_term(p1, p1k, ldpix(B + (unsigned)((sy[q] + PAD) * pw + sx[q] + PAD)), c2k, d1, gg, s_census, cs[q], ws[q]);
+        }
+    }
+    const float k1 = __fdiv_rn(cs[0], ws[0]), k2 = __fdiv_rn(cs[1], ws[1]), k3 = __fdiv_rn(cs[2], ws[2]), k4 = __fdiv_rn(cs[3], ws[3]);
+    const float m34 = k3 < k4 ? k3 : k4, m234 = k2 < m34 ? k2 : m34;   // :512 __min(cost1,__min(cost2,__min(cost3,cost4)))
+    return k1 < m234 ? k1 : m234;
+}
+
+__global__ void __launch_bounds__(128) k_pf_init(PmArgs a, const short2* __restrict__ rng_init, const __grid_constant__ CostLut lut) {
+    __shared__ float s_census[CENSUS_LUT_N];
+    load_census_lut(s_census, lut);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.w) return;
+    const short2 t = rng_init[y * a.w + x];
+    a.nnf[0][y * a.w + x] = t;
+    a.cost[0][y * a.w + x] = patch_cost_pf(a.pix[0], a.pix[1], a.pw, x, y, t.x, t.y, lut, s_census);
+}
+
+// the four segment passes, CTA lock-step like k_pm_propagate (same barriers, same skip of candidates equal to the current target)
+template <int DIR>
+__global__ void __launch_bounds__(896) k_pf_propagate(PmArgs a, int seg_len, const __grid_constant__ CostLut lut) {
+    constexpr bool ROW = (DIR == 0 || DIR == 2), FWD = (DIR < 2);
+    __shared__ float s_census[CENSUS_LUT_N];
+    load_census_lut(s_census, lut);
+    const int line = blockIdx.x * blockDim.x + threadIdx.x, seg = threadIdx.y;
+    const int n_line = ROW ? a.h : a.w, len = ROW ? a.w : a.h;
+    short2* nnf = a.nnf[0];
+    float* cost = a.cost[0];
+    int start, steps;
+    if (FWD) {
+        start = seg == 0 ? 0 : seg * seg_len - 1;   // :1340-1343
+        steps = min(len - 1, start + seg_len) - start;
+    } else {
+        start = (seg + 1) * seg_len;
+        if (start >= len) start = len - 1;
+        steps = start - seg * seg_len;
+    }
+    if (line >= n_line) steps = 0;
+    auto idx = [&](int i) -> int { return ROW ? line * a.w + i : i * a.w + line; };
+    short2 prev = make_short2(0, 0);
+    if (steps > 0) prev = nnf[idx(start)];
+    __syncthreads();
+    for (int t = 1; t <= seg_len; t++) {
+        if (t <= steps) {
+            const int i = FWD ? start + t : start - t, id = idx(i);
+            if (DIR == 0) prev.x = min(prev.x + 1, a.w - 1);
+            if (DIR == 1) prev.y = min(prev.y + 1, a.h - 1);
+            if (DIR == 2) prev.x = max(prev.x - 1, 0);
+            if (DIR == 3) prev.y = max(prev.y - 1, 0);
+            const short2 cur = nnf[id];
+            if (!(prev.x == cur.x && prev.y == cur.y)) {
+                const float cv = patch_cost_pf(a.pix[0], a.pix[1], a.pw, ROW ? i : line, ROW ? line : i, prev.x, prev.y, lut, s_census);
+                if (cv < cost[id]) { nnf[id] = prev; cost[id] = cv; }
+                else prev = cur;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pf_search(PmArgs a, const short2* __restrict__ rng, int num_guess, int search_range, int radius_min,
+                                                   const __grid_constant__ CostLut lut) {
+    __shared__ float s_census[CENSUS_LUT_N];
+    load_census_lut(s_census, lut);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.w) return;
+    const int id = y * a.w + x;
+    short2 best = a.nnf[0][id];
+    float best_cost = a.cost[0][id];
+    const short2 entry = best;
+    int mag = search_range;
+    for (int k = 0; k < num_guess; k++) {
+        const short2 rr = rng[(size_t)k * a.w * a.h + id];
+        const unsigned r1 = (unsigned)(int)rr.x, r2 = (unsigned)(int)rr.y;   // :1719-1726
+        const short xmin = (short)max(entry.x - mag, 0), xmax = (short)min(entry.x + mag + 1, a.w + 1);
+        const short ymin = (short)max(entry.y - mag, 0), ymax = (short)min(entry.y + mag + 1, a.h + 1);
+        const short gx = (short)(xmin + r1 % (unsigned)(xmax - xmin)), gy = (short)(ymin + r2 % (unsigned)(ymax - ymin));
+        if (mag / 2 >= radius_min) mag /= 2;
+        const float cv = patch_cost_pf(a.pix[0], a.pix[1], a.pw, x, y, gx, gy, lut, s_census);
+        if (cv < best_cost) { best = make_short2(gx, gy); best_cost = cv; }
+    }
+    a.nnf[0][id] = best;
+    a.cost[0][id] = best_cost;
+}
+
+template <int DIR>
+static void launch_pf_propagate(eppm_context* c, const PmArgs& a) {
+    const bool row = (DIR == 0 || DIR == 2);
+    const int sl = c->prm.prop_seg_length;
+    const int n_line = row ? a.h : a.w, n_seg = ((row ? a.w : a.h) + sl - 1) / sl;
+    int lines = 32;
+    while (lines > 1 && lines * n_seg > 896) lines >>= 1;
+    k_pf_propagate<DIR><<<dim3((n_line + lines - 1) / lines), dim3(lines, n_seg), 0, c->stream>>>(a, sl, c->cost_lut);
+    EPPM_LAUNCH_COUNT(1);
+}
+
+// forward direction of pair 0 on the context's coarsest-level planes; patch stride 2 only (the reference's compile-time stride)
+bool run_patchmatch_planefitting(eppm_context* c) {
+    if (c->prm.patch_stride != 2) { set_error("plane-fitting PatchMatch is built for patch stride 2"); return false; }
+    const int L = c->n_levels - 1;
+    const LevelGeom& g = c->lv[L];
+    PmArgs a = {};
+    a.pix[0] = c->pix[0][L]; a.pix[1] = c->pix[1][L];
+    a.plane = (unsigned)g.plane; a.pw = g.pw; a.ph = g.ph;
+    a.nnf[0] = c->nnf[0]; a.cost[0] = c->cost[0];
+    a.w = g.w; a.h = g.h; a.n_dirs = 1; a.y0 = 0; a.y1 = g.h;
+    dim3 blk(128), grd((g.w + 127) / 128, g.h);
+    k_pf_init<<<grd, blk, 0, c->stream>>>(a, c->rng_init, c->cost_lut);
+    EPPM_LAUNCH_COUNT(1);
+    for (int it = 0; it < c->prm.num_iter; it++) {
+        launch_pf_propagate<0>(c, a);
+        launch_pf_propagate<1>(c, a);
+        launch_pf_propagate<2>(c, a);
+        launch_pf_propagate<3>(c, a);
+        k_pf_search<<<grd, blk, 0, c->stream>>>(a, c->rng_search + (size_t)it * c->prm.num_rand_guess * g.w * g.h, c->prm.num_rand_guess, c->prm.search_range,
+                                                c->prm.search_radius_min, c->cost_lut);
+        EPPM_LAUNCH_COUNT(1);
+    }
+    return true;
+}
+
 void run_patchmatch(eppm_context* c) { run_patchmatch_dirs(c, 2); }
 
 template <int STRIDE>

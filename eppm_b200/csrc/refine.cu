@@ -749,6 +749,48 @@ void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pi
     EPPM_LAUNCH_COUNT(1);
 }
 
+// d_bilateral_upsample_flow (bao_pmflow_refine_kernel.cu:829-865), declared but never called by the reference's pipeline (its call in
+// baoCudaBLF_C2F is commented out, :1080): joint-bilateral UPSAMPLING of a coarser flow -- the taps of the smoothing filter, but each tap
+// reads the small flow at (int(cy / ratio), int(cx / ratio)) and the result is scaled by the ratio.  Out of place, hence deterministic.
+__global__ void __launch_bounds__(256) k_flow_bilateral_upsample(SmoothArgs a, const __grid_constant__ SmoothLut lut, const float2* __restrict__ small, int ws,
+                                                                 float ratio) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= a.w || y >= a.h) return;
+    const float4* img = a.pix + (size_t)PAD * a.pw + PAD;
+    const float4 c = ldpix(img + (size_t)y * a.pw + x);
+    const float r = a.recip, nd = -a.neg_sig_r2;
+    float nx = 0.f, ny = 0.f, wsum = 0.f;
+    for (int dy = -a.R; dy <= a.R; dy++) {
+        const int cy = y + dy;
+        if (cy < 0 || cy >= a.h) continue;
+        const int sy = __float2int_rz(__fdiv_rn((float)cy, ratio));
+        const float gy = lut.g[abs(dy)];
+        for (int dx = -a.R; dx <= a.R; dx++) {
+            const int cx = x + dx;
+            if (cx < 0 || cx >= a.w) continue;
+            const float2 fl = small[(size_t)sy * ws + __float2int_rz(__fdiv_rn((float)cx, ratio))];
+            if (fl.x > EPPM_UNKNOWN_FLOW_THRESH || fl.y > EPPM_UNKNOWN_FLOW_THRESH) continue;
+            smooth_tap(a, c, ldpix(img + (size_t)cy * a.pw + cx), fl, __fmul_rn(lut.g[abs(dx)], gy), r, nd, nx, ny, wsum);
+        }
+    }
+    if (wsum != 0.f)
+        a.dst[(size_t)y * a.w + x] = make_float2(__fmul_rn(__fdiv_rn(nx, wsum), ratio), __fmul_rn(__fdiv_rn(ny, wsum), ratio));
+}
+
+void op_flow_bilateral_upsample(eppm_context* c, float2* dst, const float4* pix1, const LevelGeom& g, const float2* small, int ws, float ratio) {
+    SmoothArgs a = {};
+    a.dst = dst; a.pix = pix1;
+    a.plane = g.plane; a.pw = g.pw; a.w = g.w; a.h = g.h;
+    a.R = 2 * c->prm.blf_sig_s;
+    a.neg_sig_r2 = -(c->prm.blf_sig_r * c->prm.blf_sig_r);
+    volatile float one = 1.0f;
+    a.recip = one / a.neg_sig_r2;
+    a.fast_div = c->smooth_fast_div;
+    a.y0 = 0; a.y1 = g.h;
+    k_flow_bilateral_upsample<<<dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(32, 8), 0, c->stream>>>(a, c->smooth_lut, small, ws, ratio);
+    EPPM_LAUNCH_COUNT(1);
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link dependency on libcuda).
 // Map of the image-1 packed planes of one level: dims (x in floats = pw*4, y = ph, z = plane index), box = smoothing tile.
 bool build_smooth_tensor_maps(eppm_context* c) {

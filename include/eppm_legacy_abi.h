@@ -58,6 +58,13 @@ void baoCudaFlow2NNF(short2* d_disp_vec, float2* d_flow, int w, int h, size_t di
 void baoCudaFlowCutoff(float2* d_flow, int w, int h, size_t flow_pitch, float max_flow_val);
 /* bao_pmflow_kernel.cu:555-586, 2071-2095: zero the flow where the two images already agree (mean AD term of the patch <= 0.1); dense flow plane */
 void baoEliminateStillRegionFlow(float2* d_flow, uchar4* d_img1, uchar4* d_img2, int w, int h, size_t img_pitch);
+/* bao_pmflow_refine_kernel.cu:829-888: joint-bilateral upsampling of a coarser flow (dense planes), values scaled by ratio_up; pixels
+ * without any known tap keep their content (the spelling of the name is the reference's) */
+void baoCudaFlowBilteralUpsampling(float2* d_flow_vec, uchar4* d_img, int w, int h, size_t img_pitch, float2* d_flow_vec_small, int w_s, int h_s,
+                                   float ratio_up);
+/* bao_pmflow_kernel.cu:1897-1963: PatchMatch scored with the plane-fitting cost of the refine stage (min over four affine patch models) */
+void baoCudaPatchMatch_PlaneFitting(short2* d_disp_vec, float* d_cost, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1,
+                                    unsigned char* d_census2, int w, int h, size_t img_pitch, size_t cost_pitch, size_t disp_pitch, size_t census_pitch);
 /* bao_pmflow_census_kernel.cu:115-181: 3x3 census of the bicubic (B-spline) upsampled images, [h_up][w_up] u8 planes */
 void baoCudaCensusTransform_Bicubic(unsigned char* d_census1, unsigned char* d_census2, int w_up, int h_up, size_t census_pitch, uchar4* d_img1,
                                     uchar4* d_img2, int w, int h, size_t img_pitch);

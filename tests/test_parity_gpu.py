@@ -239,6 +239,47 @@ def test_uncalled_stage_functions_bit_exact(ref, mine, chain):
 
 
 @needs_ref
+def test_flow_bilateral_upsampling_bit_exact(ref, mine, chain):
+    """baoCudaFlowBilteralUpsampling (its only call site is commented out upstream): out of place -> deterministic -> bit-exact."""
+    img, dims = chain["img"], chain["dims"]
+    (h1, w1), (h2, w2) = dims[1], dims[2]
+    S, I, V = C.c_size_t, C.c_int, C.c_void_p
+    g = torch.Generator(device="cpu").manual_seed(9)
+    small = torch.randn((h2, w2, 2), generator=g) * 4
+    small[5:20, 10:60] = 1e10                       # a block of unknown flow wider than the filter radius at the fine level
+    small = small.cuda()
+    outs = []
+    for lib in (ref.lib, mine):
+        lib.baoCudaFlowBilteralUpsampling.argtypes = [V, V, I, I, S, V, I, I, C.c_float]; lib.baoCudaFlowBilteralUpsampling.restype = None
+        out = torch.full((h1, w1, 2), -7.0, dtype=torch.float32, device="cuda")
+        lib.baoCudaFlowBilteralUpsampling(P(out), P(img[0][1][0]), w1, h1, img[0][1][1], P(small), w2, h2, 2.0)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    assert same_bits(outs[0], outs[1]), f"{(outs[0].view(np.uint32) != outs[1].view(np.uint32)).sum()} floats differ"
+    assert (outs[0] == -7.0).all(-1).any() and (outs[0] != -7.0).any()   # untouched where every tap is unknown, written elsewhere
+
+
+@needs_ref
+def test_patchmatch_planefitting_bit_exact(ref, mine, chain):
+    """baoCudaPatchMatch_PlaneFitting (declared, never called by the reference's host class): the whole PatchMatch scored with the
+    four-model plane-fitting cost.  Same random stream, same lock-step order -> NNF and cost bit-exact."""
+    img, cen, wc, hc = chain["img"], chain["cen"], chain["wc"], chain["hc"]
+    S, I, V = C.c_size_t, C.c_int, C.c_void_p
+    outs = {}
+    for name, lib in (("ref", ref.lib), ("mine", mine)):
+        lib.baoCudaPatchMatch_PlaneFitting.argtypes = [V] * 6 + [I, I, S, S, S, S]; lib.baoCudaPatchMatch_PlaneFitting.restype = None
+        nnf = torch.zeros((hc, wc, 2), dtype=torch.int16, device="cuda"); cost = torch.zeros((hc, wc), dtype=torch.float32, device="cuda")
+        lib.baoCudaPatchMatch_PlaneFitting(P(nnf), P(cost), P(img[0][2][0]), P(img[1][2][0]), P(cen[0][2][0]), P(cen[1][2][0]), wc, hc,
+                                           img[0][2][1], wc * 4, wc * 4, cen[0][2][1])
+        torch.cuda.synchronize()
+        outs[name] = (nnf.cpu().numpy(), cost.cpu().numpy())
+    assert np.array_equal(outs["ref"][0], outs["mine"][0]), f"{(outs['ref'][0] != outs['mine'][0]).any(-1).sum()} targets differ"
+    assert same_bits(outs["ref"][1], outs["mine"][1])
+    (nf, _), _ = chain["pm_ref"]
+    assert (outs["ref"][0] != nf.cpu().numpy()).any()   # and it is not the plain PatchMatch
+
+
+@needs_ref
 def test_subpixel_refine_and_bicubic_census_vs_reference(mine, chain, tmp_path):
     """baoCudaCensusTransform_Bicubic + baoCudaSubpixRefine (declared by the reference's host class, not called by
     compute_flow).  Both are deterministic -> bit-exact on identical buffers.  The reference build is loaded from a PRIVATE copy of its
