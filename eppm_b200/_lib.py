@@ -73,6 +73,7 @@ LEGACY_SYMBOLS = {
     "baoCudaFlow2NNF": (None, [_P, _P, _I, _I, _S, _S]),
     "baoCudaFlowCutoff": (None, [_P, _I, _I, _S, C.c_float]),
     "baoEliminateStillRegionFlow": (None, [_P, _P, _P, _I, _I, _S]),
+    "baoCudaImageSmoothing": (None, [_P, _P, _I, _I, _S]),
     "baoCudaFlowBilteralUpsampling": (None, [_P, _P, _I, _I, _S, _P, _I, _I, C.c_float]),
     "baoCudaPatchMatch_PlaneFitting": (None, [_P] * 6 + [_I, _I, _S, _S, _S, _S]),
     "baoCudaCensusTransform_Bicubic": (None, [_P, _P, _I, _I, _S, _P, _P, _I, _I, _S]),

@@ -152,6 +152,7 @@ void wmf_sweeps(eppm_context* c, short2*& cur, short2*& other, const float4* pix
                 bool only_occlusion);
 void op_fill_holes(cudaStream_t s, const short2* src, short2* dst, const float4* pix, size_t plane, int pw, int w, int h, int n);
 void op_nnf_to_flow(cudaStream_t s, const short2* nnf, float2* flow, int w, int h, int n);
+void op_image_bilateral(eppm_context* c, uchar4* dst, const uchar4* src, size_t pitch_bytes, const float4* pix1, const eppm::LevelGeom& g);
 void op_flow_bilateral_upsample(eppm_context* c, float2* dst, const float4* pix1, const eppm::LevelGeom& g, const float2* small, int ws, float ratio);
 void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const LevelGeom& g, const float2* coarse, int ws, int hs, int upsample,
                float2* out, int n, int y0 = 0, int y1 = -1);

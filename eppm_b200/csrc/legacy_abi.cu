@@ -277,6 +277,15 @@ void baoCudaBLF_C2F(float2** pFlowPyr, uchar4** pImgPyr1, uchar4** pImgPyr2, uns
     op_refine(c, c->pix[0][0], c->pix[1][0], g, pFlowPyr[l + 1], arrW[l + 1], arrH[l + 1], 1, pFlowPyr[l], 1);
 }
 
+void baoCudaImageSmoothing(uchar4* d_img_smoothed, uchar4* d_img, int w, int h, size_t img_pitch) {
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaImageSmoothing");
+    const LevelGeom& g = c->lv[0];
+    op_pack_foreign(c->stream, d_img, img_pitch, nullptr, 0, c->pix[0][0], g);
+    op_image_bilateral(c, d_img_smoothed, d_img, img_pitch, c->pix[0][0], g);
+}
+
 void baoCudaFlowBilteralUpsampling(float2* d_flow_vec, uchar4* d_img, int w, int h, size_t img_pitch, float2* d_flow_vec_small, int w_s, int h_s,
                                    float ratio_up) {
     (void)h_s;

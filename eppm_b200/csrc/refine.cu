@@ -777,6 +777,61 @@ __global__ void __launch_bounds__(256) k_flow_bilateral_upsample(SmoothArgs a, c
         a.dst[(size_t)y * a.w + x] = make_float2(__fmul_rn(__fdiv_rn(nx, wsum), ratio), __fmul_rn(__fdiv_rn(ny, wsum), ratio));
 }
 
+// d_image_bilateral_filtering (bao_pmflow_refine_kernel.cu:976-1020): the guide image filtered by its own joint-bilateral weights.
+// baoCudaImageSmoothing (:1022-1057) runs a 5x5 median into the same output first; the bilateral pass reads the ORIGINAL image and
+// overwrites every pixel, so the median is dead work and is not executed here.  Alpha is left uninitialised by the reference; 0 here.
+__global__ void __launch_bounds__(256) k_image_bilateral(SmoothArgs a, const __grid_constant__ SmoothLut lut, const uchar4* __restrict__ src,
+                                                         uchar4* __restrict__ dst, size_t img_w) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= a.w || y >= a.h) return;
+    const float4* img = a.pix + (size_t)PAD * a.pw + PAD;
+    const float4 c = ldpix(img + (size_t)y * a.pw + x);
+    const float r = a.recip, nd = -a.neg_sig_r2;
+    float nr = 0.f, ng = 0.f, nb = 0.f, wsum = 0.f;
+    for (int dy = -a.R; dy <= a.R; dy++) {
+        const int cy = y + dy;
+        if (cy < 0 || cy >= a.h) continue;
+        const float gy = lut.g[abs(dy)];
+        for (int dx = -a.R; dx <= a.R; dx++) {
+            const int cx = x + dx;
+            if (cx < 0 || cx >= a.w) continue;
+            const float dr = max3abs_diff(ldpix(img + (size_t)cy * a.pw + cx), c);    // :757
+            const float xx = __fmul_rn(dr, dr);
+            float q;
+            if (a.fast_div) {
+                const float q0 = __fmul_rn(xx, r);
+                q = __fmaf_rn(__fmaf_rn(q0, nd, xx), r, q0);
+            } else {
+                q = __fdiv_rn(xx, a.neg_sig_r2);
+            }
+            const float wgt = __fmul_rn(exp_ref(q), __fmul_rn(lut.g[abs(dx)], gy));   // :758-760
+            const uchar4 p = src[(size_t)cy * img_w + cx];
+            nr = __fmaf_rn(wgt, (float)p.x, nr);                                         // :995-997
+            ng = __fmaf_rn(wgt, (float)p.y, ng);
+            nb = __fmaf_rn(wgt, (float)p.z, nb);
+            wsum = __fadd_rn(wsum, wgt);
+        }
+    }
+    uchar4 o = src[(size_t)y * img_w + x];
+    if (wsum != 0.f)
+        o = make_uchar4((unsigned char)__float2uint_rz(__fdiv_rn(nr, wsum)), (unsigned char)__float2uint_rz(__fdiv_rn(ng, wsum)),
+                        (unsigned char)__float2uint_rz(__fdiv_rn(nb, wsum)), 0);
+    dst[(size_t)y * img_w + x] = o;
+}
+
+void op_image_bilateral(eppm_context* c, uchar4* dst, const uchar4* src, size_t pitch_bytes, const float4* pix1, const LevelGeom& g) {
+    SmoothArgs a = {};
+    a.pix = pix1;
+    a.plane = g.plane; a.pw = g.pw; a.w = g.w; a.h = g.h;
+    a.R = 2 * c->prm.blf_sig_s;
+    a.neg_sig_r2 = -(c->prm.blf_sig_r * c->prm.blf_sig_r);
+    volatile float one = 1.0f;
+    a.recip = one / a.neg_sig_r2;
+    a.fast_div = c->smooth_fast_div;
+    k_image_bilateral<<<dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(32, 8), 0, c->stream>>>(a, c->smooth_lut, src, dst, pitch_bytes / sizeof(uchar4));
+    EPPM_LAUNCH_COUNT(1);
+}
+
 void op_flow_bilateral_upsample(eppm_context* c, float2* dst, const float4* pix1, const LevelGeom& g, const float2* small, int ws, float ratio) {
     SmoothArgs a = {};
     a.dst = dst; a.pix = pix1;

@@ -36,20 +36,24 @@ def _value_noise(rng, h, w, octaves=6):
     return np.clip((img - lo) / max(hi - lo, 1e-6), 0, 1)
 
 
-def make_pair(h, w, pair_idx=0, scale_to=None):
-    """Returns (img1 u8 [h,w,3], img2 u8 [h,w,3], flow f32 [h,w,2] (u,v), valid bool [h,w] = not occluded and target inside)."""
+def make_pair(h, w, pair_idx=0, scale_to=None, base=None):
+    """Returns (img1 u8 [h,w,3], img2 u8 [h,w,3], flow f32 [h,w,2] (u,v), valid bool [h,w] = not occluded and target inside).
+    `base` (u8 or float [h,w,3]) replaces the generated texture as frame 1: make_stream chains pairs into a video that way."""
     rng = _rng(pair_idx)
     s = (w / 1920.0) if scale_to is None else scale_to  # motion magnitudes scale with the frame width
-    tex = _value_noise(rng, h, w)
     yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
-    # flat shapes that add edges to the texture itself
-    for _ in range(8):
-        cy, cx = rng.uniform(0, h), rng.uniform(0, w)
-        ry, rx = rng.uniform(0.03, 0.12) * h, rng.uniform(0.03, 0.12) * w
-        col = rng.uniform(0.1, 0.9, 3).astype(np.float32)
-        m = (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1) if rng.random() < 0.5 else ((np.abs(yy - cy) <= ry) & (np.abs(xx - cx) <= rx))
-        tex[m] = 0.75 * col + 0.25 * tex[m]
-    img1f = 16.0 + 224.0 * tex
+    if base is None:
+        tex = _value_noise(rng, h, w)
+        # flat shapes that add edges to the texture itself
+        for _ in range(8):
+            cy, cx = rng.uniform(0, h), rng.uniform(0, w)
+            ry, rx = rng.uniform(0.03, 0.12) * h, rng.uniform(0.03, 0.12) * w
+            col = rng.uniform(0.1, 0.9, 3).astype(np.float32)
+            m = (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1) if rng.random() < 0.5 else ((np.abs(yy - cy) <= ry) & (np.abs(xx - cx) <= rx))
+            tex[m] = 0.75 * col + 0.25 * tex[m]
+        img1f = 16.0 + 224.0 * tex
+    else:
+        img1f = np.asarray(base, np.float32)
 
     # layers: index 0 = background, later = nearer
     layers = []
@@ -103,6 +107,20 @@ def make_pair(h, w, pair_idx=0, scale_to=None):
     valid = inside.copy()
     valid[inside] = lid2[ty[inside], tx[inside]] == lid1[inside]
     return img1, img2, flow, valid
+
+
+def make_stream(h, w, n_frames, first_idx=0, scale_to=None):
+    """A short video: frame t+1 is frame t moved by a fresh piecewise-smooth motion (BASELINE config 5 cycles such a clip).
+    Returns (frames u8 [n,h,w,3], flows f32 [n-1,h,w,2], valid bool [n-1,h,w])."""
+    frames, flows, valids = [], [], []
+    cur = None
+    for t in range(n_frames - 1):
+        a, b, fl, va = make_pair(h, w, first_idx + t, scale_to=scale_to, base=cur)
+        if t == 0:
+            frames.append(a)
+        frames.append(b); flows.append(fl); valids.append(va)
+        cur = b
+    return np.stack(frames), np.stack(flows), np.stack(valids)
 
 
 def make_batch(h, w, n, first_idx=0, distinct=None):

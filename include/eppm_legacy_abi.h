@@ -58,6 +58,9 @@ void baoCudaFlow2NNF(short2* d_disp_vec, float2* d_flow, int w, int h, size_t di
 void baoCudaFlowCutoff(float2* d_flow, int w, int h, size_t flow_pitch, float max_flow_val);
 /* bao_pmflow_kernel.cu:555-586, 2071-2095: zero the flow where the two images already agree (mean AD term of the patch <= 0.1); dense flow plane */
 void baoEliminateStillRegionFlow(float2* d_flow, uchar4* d_img1, uchar4* d_img2, int w, int h, size_t img_pitch);
+/* bao_pmflow_refine_kernel.cu:976-1057: the guide image filtered with its own joint-bilateral weights (the reference's preceding 5x5 median
+ * is overwritten by it and not executed here); alpha of the output is 0 (uninitialised in the reference) */
+void baoCudaImageSmoothing(uchar4* d_img_smoothed, uchar4* d_img, int w, int h, size_t img_pitch);
 /* bao_pmflow_refine_kernel.cu:829-888: joint-bilateral upsampling of a coarser flow (dense planes), values scaled by ratio_up; pixels
  * without any known tap keep their content (the spelling of the name is the reference's) */
 void baoCudaFlowBilteralUpsampling(float2* d_flow_vec, uchar4* d_img, int w, int h, size_t img_pitch, float2* d_flow_vec_small, int w_s, int h_s,

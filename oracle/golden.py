@@ -34,6 +34,8 @@ def lib():
         l.golden_xorwow.argtypes = [C.c_ulonglong, C.c_ulonglong, I, P]
         l.golden_level_dims_for.argtypes = [I, I, I, C.POINTER(I), C.POINTER(I)]
         l.golden_patch_cost.restype = C.c_float; l.golden_patch_cost.argtypes = [P, I, I, I, I, I]
+        l.golden_census_bicubic.argtypes = [P, I, I, I, I, P]
+        l.golden_subpix_refine.argtypes = [P, P, P, P, P, P, I, I, I, I]
         _lib = l
     return _lib
 
@@ -41,6 +43,25 @@ def lib():
 def xorwow(seed, subsequence, n):
     out = np.zeros(n, np.uint32)
     lib().golden_xorwow(seed, subsequence, n, out.ctypes.data)
+    return out
+
+
+def census_bicubic(rgba, w_up, h_up):
+    """baoCudaCensusTransform_Bicubic on one image: rgba u8 [h,w,4] -> census u8 [h_up,w_up] (oracle/golden_subpix.cpp)."""
+    rgba = np.ascontiguousarray(rgba, np.uint8)
+    h, w = rgba.shape[:2]
+    out = np.zeros((h_up, w_up), np.uint8)
+    lib().golden_census_bicubic(rgba.ctypes.data, w, h, w_up, h_up, out.ctypes.data)
+    return out
+
+
+def subpix_refine(rgba1, rgba2, cen1_up, cen2_up, nnf, flow, y0, y1):
+    """baoCudaSubpixRefine on rows [y0, y1): returns a refined copy of flow f32 [h,w,2] (oracle/golden_subpix.cpp)."""
+    a = [np.ascontiguousarray(x, np.uint8) for x in (rgba1, rgba2, cen1_up, cen2_up)]
+    nnf = np.ascontiguousarray(nnf, np.int16)
+    out = np.array(flow, np.float32, copy=True, order="C")
+    h, w = out.shape[:2]
+    lib().golden_subpix_refine(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, nnf.ctypes.data, out.ctypes.data, w, h, y0, y1)
     return out
 
 

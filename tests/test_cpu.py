@@ -153,6 +153,26 @@ def test_oracle_against_reference_fixtures(golden, path):
         assert abs(synth.epe(fl, gt, valid) - synth.epe(z["flow"], gt, valid)) <= 0.05
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "refsub_*.npz"))))
+def test_oracle_subpixel_stage_against_reference_fixture(golden, path):
+    """SURVEY.md §8 a21 in the CPU oracle (oracle/golden_subpix.cpp) against outputs of the reference build (tools/gen_golden_subpix.py):
+    the bicubic census is pure IEEE arithmetic -> bit-exact; the quadric refinement goes through the texture unit's bilinear filter and
+    MUFU.EX2 on the GPU, which the CPU restates approximately -> same pixels refined, sub-pixel positions within a stated tolerance."""
+    z = np.load(path)
+    h, w = int(z["h"]), int(z["w"])
+    assert np.array_equal(golden.census_bicubic(z["rgba1"], 2 * w, 2 * h), z["census1_up"])
+    assert np.array_equal(golden.census_bicubic(z["rgba2"], 2 * w, 2 * h), z["census2_up"])
+    y0, y1 = h // 2 - 2, h // 2 + 2                      # a band: the restatement evaluates 80 000 filtered fetches per pixel
+    out = golden.subpix_refine(z["rgba1"], z["rgba2"], z["census1_up"], z["census2_up"], z["nnf"], z["flow_in"], y0, y1)
+    ref, mine, base = z["flow_out"][y0:y1], out[y0:y1], z["flow_in"][y0:y1]
+    assert np.array_equal((ref != base).any(-1), (mine != base).any(-1))          # the same pixels left the integer grid
+    assert (ref != base).any(-1).mean() > 0.5
+    d = np.abs(ref - mine).max(-1)
+    # tolerance (px): the stationary point of a flat quadric amplifies the last bits of the 25 costs it is fitted to
+    assert d.mean() <= 2e-3 and np.quantile(d, 0.95) <= 5e-3 and d.max() <= 0.1, (d.mean(), np.quantile(d, 0.95), d.max())
+    assert np.array_equal(out[:y0], z["flow_in"][:y0]) and np.array_equal(out[y1:], z["flow_in"][y1:])
+
+
 def test_oracle_stage_injection_is_deterministic(golden):
     """LR check / outlier removal / hole filling / NNF->flow given the reference's own PatchMatch output.  The backward field after
     the LR check is deterministic in the reference and must match bit for bit.  In the forward field, pixels that survive the

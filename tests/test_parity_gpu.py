@@ -260,6 +260,24 @@ def test_flow_bilateral_upsampling_bit_exact(ref, mine, chain):
 
 
 @needs_ref
+def test_image_smoothing_bit_exact(ref, mine, chain):
+    """baoCudaImageSmoothing (never called upstream): out of place -> deterministic; r, g, b bit-exact (the reference leaves alpha uninitialised)."""
+    img, dims = chain["img"], chain["dims"]
+    h2, w2 = dims[2]
+    src, pitch = img[0][2]
+    S, I, V = C.c_size_t, C.c_int, C.c_void_p
+    outs = []
+    for lib in (ref.lib, mine):
+        lib.baoCudaImageSmoothing.argtypes = [V, V, I, I, S]; lib.baoCudaImageSmoothing.restype = None
+        out = torch.zeros_like(src)
+        lib.baoCudaImageSmoothing(P(out), P(src), w2, h2, pitch)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy()[:, : w2 * 4].reshape(h2, w2, 4)[..., :3])
+    assert np.array_equal(outs[0], outs[1]), f"{(outs[0] != outs[1]).sum()} bytes differ"
+    assert (outs[0] != src.cpu().numpy()[:, : w2 * 4].reshape(h2, w2, 4)[..., :3]).mean() > 0.05   # it really filtered
+
+
+@needs_ref
 def test_patchmatch_planefitting_bit_exact(ref, mine, chain):
     """baoCudaPatchMatch_PlaneFitting (declared, never called by the reference's host class): the whole PatchMatch scored with the
     four-model plane-fitting cost.  Same random stream, same lock-step order -> NNF and cost bit-exact."""
