@@ -49,6 +49,7 @@ EPPM_SYMBOLS = {
     "eppm_smooth_uses_fast_div": (C.c_int, [C.c_void_p]),
     "eppm_smooth_uses_tma": (C.c_int, [C.c_void_p]),
     "eppm_selftest_affine_sites": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "eppm_selftest_affine_sites_stride": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "eppm_refine_uses_site_table": (C.c_int, [C.c_void_p, C.c_int]),
     "eppm_launch_count": (C.c_ulonglong, [C.c_int]),
     "eppm_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 5)]),

@@ -200,7 +200,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         }
         c->smooth_fast_div = checked_ok;
     }
-    for (int l = 0; l + 1 < c->n_levels; l++) c->aff_ok[l] = p.patch_stride == 2 && build_affine_tab(c->aff_tab[l], c->lv[l].pw, c->lv[l].w, c->lv[l].h);
+    for (int l = 0; l + 1 < c->n_levels; l++) c->aff_ok[l] = build_affine_tab(c->aff_tab[l], c->lv[l].pw, c->lv[l].w, c->lv[l].h, p.patch_stride);
     build_gauss_tables(c);
     build_rng_tables(c);
     if (!getenv("EPPM_NO_TMA")) build_smooth_tensor_maps(c);
@@ -505,7 +505,17 @@ int eppm_selftest_affine_sites(int w, int h, int pw, int* table_out) {
     AffineTab t;
     if (w < 1 || h < 1 || pw < 1) return EPPM_ERR_ARG;
     const bool ok = build_affine_tab(t, pw, w, h);
-    if (ok && table_out) memcpy(table_out, t.off, sizeof(t.off));
+    if (ok && table_out)
+        for (int q = 0; q < 3; q++) memcpy(table_out + q * 100, t.off[q], 100 * sizeof(int));   // stride 2: [3][100]
+    return ok ? 1 : 0;
+}
+int eppm_selftest_affine_sites_stride(int w, int h, int pw, int stride, int* table_out) {
+    AffineTab t;
+    if (w < 1 || h < 1 || pw < 1 || stride < 1 || stride > 3) return EPPM_ERR_ARG;
+    const bool ok = build_affine_tab(t, pw, w, h, stride);
+    const int n = (2 * PATCH_R) / stride + 1;
+    if (ok && table_out)
+        for (int q = 0; q < 3; q++) memcpy(table_out + q * n * n, t.off[q], (size_t)n * n * sizeof(int));
     return ok ? 1 : 0;
 }
 int eppm_refine_uses_site_table(eppm_context* c, int level) {

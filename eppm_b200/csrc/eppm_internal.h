@@ -52,7 +52,7 @@ struct Arena {
 };
 
 struct AffineTab {
-    int off[3][100];   // dy * pw + dx of affine model 1..3 at sample (i, j) of the stride-2 patch, relative to the candidate centre; i outer, j inner
+    int off[3][361];   // dy * pw + dx of affine model 1..3 at sample (i, j) of the patch (100 samples at stride 2, 361 at 1, 49 at 3), relative to the candidate centre; i outer, j inner
 };
 
 struct SmoothLut {
@@ -143,7 +143,7 @@ void run_consistency(eppm_context* c);
 void run_c2f(eppm_context* c, float* d_flow_out);
 void build_rng_tables(eppm_context* c);
 void build_gauss_tables(eppm_context* c);
-bool build_affine_tab(AffineTab& t, int pw, int w, int h);
+bool build_affine_tab(AffineTab& t, int pw, int w, int h, int stride = 2);
 
 // building blocks reused by the legacy stage ABI (foreign buffers)
 void op_lr_check(cudaStream_t s, short2* nnf, float* cost, const short2* nnf2, int w, int h, int n);

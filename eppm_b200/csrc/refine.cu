@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine(RefineA
 // The sample sites of the three affine models are floor(fma(i, C_y, fma(j, C_x, float(X)))) with X = cx + j an exact integer
 // (bao_pmflow_kernel.cu:402,440,478 as contracted by nvcc).  For odd (i, j) the real value j*C_x + i*C_y never comes closer than
 // 1e-3 to an integer, far more than the two FFMA roundings can move it at any |X| < 2^15, so site - X is a function of (i, j, model)
-// alone.  build_affine_tab() tabulates it and CHECKS that claim for every X the level can produce with the host's correctly rounded
+// alone.  The same holds at stride 3; at stride 1 one site (model 3, (i, j) = (-7, -2): -2*0.205 - 7*0.370 = -3.00000003) does depend
+// on X, the check below rejects the table and the computing kernel k_c2f_refine runs instead.  build_affine_tab() tabulates it and CHECKS that claim for every X the level can produce with the host's correctly rounded
 // fmaf; only then is this kernel used.  It replaces 2 FFMA + F2I + IADD + IMAD per coordinate by one table read per site,
 // and groups the `t2 < -126` fix-up of __expf (taken by ~1 % of the samples) of the four models of a candidate into one test.
 // base + off pixels as ONE IMAD.WIDE (left to itself the compiler sign-extends and shifts with three ALU instructions)
@@ -204,7 +205,7 @@ __device__ __forceinline__ const float4* pix_at(const float4* base, int off) {
 // 1: CTA = 9 warps, warp (m, n) owns ONE candidate and its four models (72 registers, 27 warps per SM): the image-1 side of a
 // sample is shared by 4 instead of 12 accumulator pairs (33.4 instead of 30.7 instructions per sample).  Measured equal (8.70 vs 8.74 ms
 // per 1080p pair at level 0; 56 registers / 36 warps: 9.27 ms) -- the kernel is not occupancy bound; kept behind EPPM_VARIANT=256.
-template <bool GROUP_TINY, int NCT, int MINB>
+template <bool GROUP_TINY, int NCT, int MINB, int STRIDE>
 __global__ void __launch_bounds__(RF_PIX * 9 / NCT, MINB)
     k_c2f_refine_tab(RefineArgs a, const __grid_constant__ CostLut lut, const __grid_constant__ AffineTab tab) {
     __shared__ float s_best[9][RF_PIX];
@@ -253,11 +254,11 @@ __global__ void __launch_bounds__(RF_PIX * 9 / NCT, MINB)
         }
         int s = 0;
 #pragma unroll 1
-        for (int i = -PATCH_R; i <= PATCH_R; i += 2) {
+        for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
             const int ai = i < 0 ? -i : i;
             const int irow = i * a.pw;
 #pragma unroll 2
-            for (int j = -PATCH_R; j <= PATCH_R; j += 2, s++) {
+            for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE, s++) {
                 const float4 p1 = ldpix(a0 + irow + j);
                 const PixPk p1k = pack_pix(p1);
                 const float d1 = max3abs_diff(c1k, p1k);
@@ -328,13 +329,14 @@ __global__ void __launch_bounds__(RF_PIX * 9 / NCT, MINB)
 
 // Site table of one level (pitch pw) and its proof: for every integer X in [lo, hi] that a candidate coordinate + offset can take,
 // floor(fmaf(i, Cy, fmaf(j, Cx, (float)X))) - X must equal the tabulated value.  Host fmaf is correctly rounded = the device FFMA.
-bool build_affine_tab(AffineTab& t, int pw, int w, int h) {
+bool build_affine_tab(AffineTab& t, int pw, int w, int h, int stride) {
     static const float pf[3][4] = {{0.177f, -0.011f, -0.003f, 0.301f}, {0.125f, -0.357f, 0.009f, 0.308f}, {0.205f, 0.370f, 0.011f, 0.296f}};
     auto site = [](float fi, float fj, float cj, float ci, int X) { return (int)floorf(fmaf(fi, ci, fmaf(fj, cj, (float)X))) - X; };
+    if (stride < 1 || stride > 3) return false;
     const int lim = (w > h ? w : h) + PATCH_R;
     int s = 0;
-    for (int i = -PATCH_R; i <= PATCH_R; i += 2)
-        for (int j = -PATCH_R; j <= PATCH_R; j += 2, s++)
+    for (int i = -PATCH_R; i <= PATCH_R; i += stride)
+        for (int j = -PATCH_R; j <= PATCH_R; j += stride, s++)
             for (int q = 0; q < 3; q++) {
                 // x: cx2 = fma(i, C_uy, fma(j, C_ux, float(cx + j)));  y: cy2 = fma(i, C_vy, fma(j, C_vx, float(cy + i)))
                 const int dx = site((float)i, (float)j, pf[q][0], pf[q][1], 1000), dy = site((float)i, (float)j, pf[q][2], pf[q][3], 1000);
@@ -680,18 +682,22 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
     a.upsample = upsample;
     a.y0 = y0;
     dim3 blk(RF_PIX * 3), grd((g.w + RF_PIX - 1) / RF_PIX, y1 - y0, n);
-    if (c->prm.patch_stride == 2 && !(c->variant & EPPM_VAR_REFINE_GENERIC)) {
-        // table-driven kernel: the site table of this pitch was built and verified at eppm_create
+    if (!(c->variant & EPPM_VAR_REFINE_GENERIC)) {
+        // table-driven kernel: the site table of this pitch and stride was built and verified at eppm_create
         const AffineTab* tabp = nullptr;
         for (int l = 0; l < c->n_levels; l++)
             if (c->aff_ok[l] && c->lv[l].pw == g.pw && c->lv[l].w >= g.w && c->lv[l].h >= g.h) tabp = &c->aff_tab[l];
-        const int tab_ok = tabp != nullptr;
-        if (tab_ok) {
+        if (tabp) {
             const dim3 blk9(RF_PIX * 9);
             const int v = c->variant;
-            if (v & EPPM_VAR_REFINE_NOGROUP) k_c2f_refine_tab<false, 3, RF_MINBLOCKS><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
-            else if (v & EPPM_VAR_REFINE_9WARP3) k_c2f_refine_tab<true, 1, 3><<<grd, blk9, 0, c->stream>>>(a, c->cost_lut, *tabp);
-            else k_c2f_refine_tab<true, 3, RF_MINBLOCKS><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+            switch (c->prm.patch_stride) {
+            case 1: k_c2f_refine_tab<true, 3, RF_MINBLOCKS, 1><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp); break;
+            case 3: k_c2f_refine_tab<true, 3, RF_MINBLOCKS, 3><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp); break;
+            default:
+                if (v & EPPM_VAR_REFINE_NOGROUP) k_c2f_refine_tab<false, 3, RF_MINBLOCKS, 2><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+                else if (v & EPPM_VAR_REFINE_9WARP3) k_c2f_refine_tab<true, 1, 3, 2><<<grd, blk9, 0, c->stream>>>(a, c->cost_lut, *tabp);
+                else k_c2f_refine_tab<true, 3, RF_MINBLOCKS, 2><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+            }
             EPPM_LAUNCH_COUNT(1);
             return;
         }

@@ -154,13 +154,16 @@ int eppm_smooth_uses_fast_div(eppm_context* ctx);
 int eppm_smooth_uses_tma(eppm_context* ctx);
 
 /* The plane-fitting refine (d_bilateral_refine_flow_planefitting, bao_pmflow_kernel.cu:2005-2069) samples the three affine patch
- * models at floor(fma(i, Cy, fma(j, Cx, float(X)))).  At patch stride 2 those sites are tabulated per (i, j, model) relative to the
+ * models at floor(fma(i, Cy, fma(j, Cx, float(X)))).  Those sites are tabulated per (i, j, model) relative to the
  * candidate centre; the table is used only after eppm_create has checked, with the host's correctly rounded fmaf, that it
  * reproduces the expression for EVERY coordinate X the level can produce.  eppm_selftest_affine_sites runs that check on the host
  * (no GPU needed) for a level of w x h with plane pitch pw: returns 1 and writes the 3 x 100 element offsets (dy * pw + dx) to
  * table_out (may be NULL) when the table is exact, 0 when it is not (the refine then computes the coordinates per sample).
  * eppm_refine_uses_site_table reports what a context's refine kernel does at `level`. */
 int eppm_selftest_affine_sites(int w, int h, int pw, int* table_out);
+/* The same for patch stride 1, 2 or 3: n = 19, 10 or 7 samples per patch row, table_out = 3 x n*n offsets.  Strides 2 and 3 verify at
+ * every size; stride 1 does not (one site, model 3 at (i, j) = (-7, -2), lies 3e-8 from an integer) and keeps the computing kernel. */
+int eppm_selftest_affine_sites_stride(int w, int h, int pw, int stride, int* table_out);
 int eppm_refine_uses_site_table(eppm_context* ctx, int level);
 
 /* Number of kernel launches issued by this library since the counter was last reset (bench.py's gpu_launches). */

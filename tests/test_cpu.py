@@ -68,14 +68,24 @@ def test_affine_site_table_is_verified_on_the_host():
     def fma(a, b, c):
         return np.float32(np.float64(a) * np.float64(b) + np.float64(c))  # exact product, one rounding (|values| < 2^15)
 
-    for (w, h) in [(1920, 1080), (960, 540), (161, 121), (3840, 2160)]:
+    lib.eppm_selftest_affine_sites_stride.restype = C.c_int
+    lib.eppm_selftest_affine_sites_stride.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    # stride 1 has ONE site whose offset is not a function of (i, j, model) alone: model 3 at (i, j) = (-7, -2), x = X - 2*0.205 - 7*0.370 =
+    # X - 3.00000003: the two FFMA roundings decide between X - 4 and X - 3 depending on X.  The check must reject that table.
+    assert lib.eppm_selftest_affine_sites_stride(1920, 1080, 1952, 1, None) == 0
+    assert lib.eppm_selftest_affine_sites_stride(161, 121, 193, 1, None) == 0
+    for (w, h, stride) in [(1920, 1080, 2), (960, 540, 2), (161, 121, 2), (3840, 2160, 2), (1920, 1080, 3), (960, 540, 3), (161, 121, 3), (3840, 2160, 3)]:
         pw = w + 32
-        tab = (C.c_int * 300)()
-        assert lib.eppm_selftest_affine_sites(w, h, pw, tab) == 1
-        tab = np.array(tab).reshape(3, 100)
+        n = 18 // stride + 1
+        tab = (C.c_int * (3 * n * n))()
+        if stride == 2:
+            assert lib.eppm_selftest_affine_sites(w, h, pw, tab) == 1
+        else:
+            assert lib.eppm_selftest_affine_sites_stride(w, h, pw, stride, tab) == 1
+        tab = np.array(tab).reshape(3, n * n)
         s = 0
-        for i in range(-9, 10, 2):
-            for j in range(-9, 10, 2):
+        for i in range(-9, 10, stride):
+            for j in range(-9, 10, stride):
                 for q in range(3):
                     for X, Y in [(0, 0), (7, 5), (w - 1, h - 1), (w // 2 + 3, h // 3)]:   # candidate centres
                         sx = int(np.floor(fma(np.float32(i), pf[q, 1], fma(np.float32(j), pf[q, 0], np.float32(X + j)))))

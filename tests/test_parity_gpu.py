@@ -69,6 +69,35 @@ def test_prepare_bit_exact_vs_reference(ref, h, w, idx, scale):
     ref.destroy(rc); ctx.close()
 
 
+@needs_ref
+@pytest.mark.parametrize("h,w,idx", [(40, 56, 21), (24, 40, 22), (33, 17, 23), (20, 200, 24)])
+def test_tiny_and_extreme_shapes_vs_reference(ref, mine, h, w, idx):
+    """Frames smaller than the patch and the search window, odd and strongly non-square: pyramid, census and the whole PatchMatch at
+    the coarsest level (a handful of pixels, every sample in the clamped border) stay bit-exact; end to end the flow shows the
+    reference's own degenerate behaviour."""
+    a, b, _, _ = synth.make_pair(h, w, idx, scale_to=0.1)
+    rc, dims, img, cen = _ref_level_planes(ref, h, w, a, b)
+    ctx = E.EppmContext(h, w, 1)
+    ctx.stage_prepare(dev(a[None]), dev(b[None]), 1)
+    for l in range(3):
+        assert ctx.level_dims(l) == tuple(dims[l])
+        for which in (E.PLANE_RGBA1, E.PLANE_CENSUS1, E.PLANE_CENSUS2):
+            assert same_bits(ctx.read_plane(which, l), ref.read_plane(rc, which, l)), (which, l)
+    hc, wc = dims[2]
+    for swap in (False, True):
+        (nr, cr), (nm, cm) = _pm(ref.lib, img, cen, 2, wc, hc, swap), _pm(mine, img, cen, 2, wc, hc, swap)
+        assert torch.equal(nr, nm) and same_bits(cr.cpu().numpy(), cm.cpu().numpy()), (h, w, swap)
+    fr = ref.compute_flow(rc, h, w)
+    fm = ctx.compute_batch_host(a[None], b[None])[0]
+    # End to end the reference degenerates on such frames (its 13x13 outlier vote spans the whole coarsest level and rejects every
+    # pixel, the 1e10 unknown marker then leaks through the x2 bilinear upsampling as values of 2e4..3e4 px): the drop-in must
+    # degenerate the same way -- same share of blown-up pixels, same extreme value -- not "fix" it.
+    assert fm.shape == fr.shape == (h, w, 2) and np.isfinite(fm).all()
+    assert abs((np.abs(fm) > 1e3).mean() - (np.abs(fr) > 1e3).mean()) <= 0.02
+    assert abs(np.abs(fm).max() - np.abs(fr).max()) <= 0.01 * np.abs(fr).max()
+    ref.destroy(rc); ctx.close()
+
+
 def _ref_level_planes(ref, h, w, a, b):
     rc = ref.create(h, w)
     ref.set_data(rc, a, b)

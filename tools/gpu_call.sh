@@ -1,6 +1,2 @@
-set -x
 mkdir -p gpurun_out
-( time timeout 600 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
-head -4 gpurun_out/pytest_gpu.log
-timeout 900 python tools/stream_sweep.py 300 60 > gpurun_out/stream_sweep.log 2>&1
-tail -32 gpurun_out/stream_sweep.log | cut -c1-330
+timeout 300 python tools/tiny_dev.py > gpurun_out/tiny.log 2>&1; cat gpurun_out/tiny.log | tail -30
