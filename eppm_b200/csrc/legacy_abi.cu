@@ -352,3 +352,58 @@ void baoEliminateStillRegionFlow(float2* d_flow, uchar4* d_img1, uchar4* d_img2,
 }
 
 }  // extern "C"
+
+// ---- C++ linkage, like the reference: the one non-extern-"C" symbol its host class needs (…cuda.cpp:64, :311) ----
+// bao_cuda_convert_flow_to_colorshow (basic/bao_basic_cuda.cuh:745-849): Middlebury colour wheel on the device.  Visualisation only;
+// arithmetic follows the reference's expressions (double where its literals are double), libdevice atan2f like the reference.
+namespace {
+__constant__ unsigned char c_wheel[55][3];
+
+__global__ void k_flow_to_color(uchar4* __restrict__ rgb, const float2* __restrict__ flow, int h, int w, float max_rad) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const float2 v = flow[(size_t)y * w + x];
+    uchar4 o = make_uchar4(0, 0, 0, 0);
+    if (fabsf(v.x) < 999999.f && fabsf(v.y) < 999999.f) {                  // :823 unknown flow stays black
+        const float fx = v.x / max_rad, fy = v.y / max_rad;
+        const float rad = __fsqrt_rn(fx * fx + fy * fy);                  // :780
+        const float a = atan2f(-fy, -fx) / 3.14159f;
+        const float fk = (a + 1.0f) / 2.0f * (55 - 1);
+        const int k0 = (int)fk, k1 = (k0 + 1) % 55;
+        const float f = fk - k0;
+        unsigned char pv[3];
+        for (int b = 0; b < 3; b++) {
+            const float col0 = c_wheel[k0][b] / 255.0f, col1 = c_wheel[k1][b] / 255.0f;
+            float col = (1 - f) * col0 + f * col1;
+            if (rad <= 1) col = 1 - rad * (1 - col);                       // increase saturation with radius
+            else col *= .75;                                               // out of range (double literal in the reference)
+            pv[b] = (unsigned char)(int)(255.0 * col);
+        }
+        o = make_uchar4(pv[0], pv[1], pv[2], 0);
+    }
+    rgb[(size_t)y * w + x] = o;
+}
+}  // namespace
+
+void bao_cuda_convert_flow_to_colorshow(uchar4* rgbflow, float2* flow_vec, int h, int w, float max_disp_x, float max_disp_y) {
+    static bool wheel_ready = false;
+    cudaStreamSynchronize(0);
+    if (!wheel_ready) {
+        unsigned char wh[55][3];
+        const int RY = 15, YG = 6, GC = 4, CB = 11, BM = 13, MR = 6;     // :760-773
+        int k = 0;
+        for (int i = 0; i < RY; i++, k++) { wh[k][0] = 255; wh[k][1] = 255 * i / RY; wh[k][2] = 0; }
+        for (int i = 0; i < YG; i++, k++) { wh[k][0] = 255 - 255 * i / YG; wh[k][1] = 255; wh[k][2] = 0; }
+        for (int i = 0; i < GC; i++, k++) { wh[k][0] = 0; wh[k][1] = 255; wh[k][2] = 255 * i / GC; }
+        for (int i = 0; i < CB; i++, k++) { wh[k][0] = 0; wh[k][1] = 255 - 255 * i / CB; wh[k][2] = 255; }
+        for (int i = 0; i < BM; i++, k++) { wh[k][0] = 255 * i / BM; wh[k][1] = 0; wh[k][2] = 255; }
+        for (int i = 0; i < MR; i++, k++) { wh[k][0] = 255; wh[k][1] = 0; wh[k][2] = 255 - 255 * i / MR; }
+        cudaMemcpyToSymbol(c_wheel, wh, sizeof(wh));
+        wheel_ready = true;
+    }
+    const float max_rad = sqrt(max_disp_x * max_disp_x + max_disp_y * max_disp_y);   // :841
+    k_flow_to_color<<<dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8)>>>(rgbflow, flow_vec, h, w, max_rad);
+    EPPM_LAUNCH_COUNT(1);
+    if (!cuda_ok(cudaStreamSynchronize(0), "bao_cuda_convert_flow_to_colorshow")) complain("bao_cuda_convert_flow_to_colorshow");
+}
+

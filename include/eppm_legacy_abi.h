@@ -79,5 +79,8 @@ void baoCudaSubpixRefine(float2* d_flow, short2* d_disp_vec, uchar4* d_img1, uch
 
 #ifdef __cplusplus
 }
+/* C++ linkage like the reference (basic/bao_basic_cuda.cuh:838-849; declared at …cuda.cpp:64 and called at :311 when compute_flow is
+ * given a colour buffer): Middlebury colour coding of a dense flow plane on the device, unknown flow = black. */
+void bao_cuda_convert_flow_to_colorshow(uchar4* rgbflow, float2* flow_vec, int h, int w, float max_disp_x = 100, float max_disp_y = 100);
 #endif
 #endif

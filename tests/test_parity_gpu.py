@@ -594,6 +594,53 @@ def test_unmodified_main_cpp_drop_in(tmp_path):
     assert dd.mean() <= 0.05, dd.mean()
 
 
+def test_reference_host_class_on_this_library(tmp_path):
+    """the reference's UNMODIFIED main.cpp AND host class (bao_flow_patchmatch_multiscale_cuda.cpp, basic/*,
+    middlebury/*; objects compiled from the sources where they lie) linked against libeppm_b200.so instead of the reference's three .cu
+    files (oracle/_ref/runeppm_hostclass, `make -C oracle hostclass`): every stage goes through include/eppm_legacy_abi.h on the
+    reference's own pitched buffers.  Compared with the reference's own executable on the shipped pair."""
+    import shutil, subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "runeppm_hostclass")
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "runeppm")
+    if not (os.path.exists(exe) and os.path.exists(ref_exe) and os.path.exists(os.path.join(refharness.REF_DATA, "frame10.ppm"))):
+        pytest.skip("reference host objects not built")
+    flows = []
+    for k, binary in enumerate((ref_exe, exe)):
+        d = tmp_path / f"run{k}"
+        d.mkdir()
+        for f in ("frame10.ppm", "frame11.ppm"):
+            shutil.copy(os.path.join(refharness.REF_DATA, f), d / f)
+        subprocess.run([binary], cwd=d, check=True, stdout=subprocess.DEVNULL, timeout=300)
+        flows.append(synth.read_flo(str(d / "flow.flo")))
+    assert flows[0].shape == flows[1].shape == (480, 640, 2)
+    dd = np.sqrt(((flows[0] - flows[1]) ** 2).sum(-1))
+    assert dd.mean() <= 0.05, dd.mean()
+
+
+@needs_ref
+def test_flow_colour_coding_vs_reference(ref, mine):
+    """bao_cuda_convert_flow_to_colorshow (C++ linkage; compute_flow's optional colour output): visualisation, compared per channel --
+    libdevice atan2f and a float->double->int chain leave room for one 8-bit level at a rounding boundary."""
+    sym = "_Z34bao_cuda_convert_flow_to_colorshowP6uchar4P6float2iiff"
+    h, w = 120, 160
+    g = torch.Generator(device="cpu").manual_seed(3)
+    fl = torch.randn((h, w, 2), generator=g) * 12
+    fl[:10, :20] = 1e10                         # unknown flow -> black
+    fl[20, :] = 0.0
+    fl = fl.cuda()
+    outs = []
+    for lib in (ref.lib, mine):
+        fn = getattr(lib, sym)
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float]; fn.restype = None
+        out = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+        fn(P(out), P(fl), h, w, 20.0, 20.0)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy()[..., :3].astype(np.int32))
+    d = np.abs(outs[0] - outs[1])
+    assert d.max() <= 1 and (d == 0).mean() >= 0.999, (d.max(), (d == 0).mean())
+    assert (outs[0][:10, :20] == 0).all() and outs[0].std() > 20
+
+
 @needs_ref
 def test_philox_mode_epe_delta(ref):
     """Stated counter-based RNG (EPPM_RNG_PHILOX, Philox4x32-10 keyed by seed with one sub-sequence per coarse pixel): the NNF is a

@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 300 python tools/tiny_dev.py > gpurun_out/tiny.log 2>&1; cat gpurun_out/tiny.log | tail -30
+( timeout 600 python -m pytest tests -m gpu -x -q -rs -k "tiny or host_class or colour or stride" ) > gpurun_out/pytest_new.log 2>&1
+tail -15 gpurun_out/pytest_new.log
