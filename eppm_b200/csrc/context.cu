@@ -200,7 +200,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         }
         c->smooth_fast_div = checked_ok;
     }
-    for (int l = 0; l + 1 < c->n_levels; l++) c->aff_ok[l] = build_affine_tab(c->aff_tab[l], c->lv[l].pw, c->lv[l].w, c->lv[l].h, p.patch_stride);
+    for (int l = 0; l + 1 < c->n_levels; l++) c->aff_ok[l] = build_affine_tab(c->aff_tab[l], c->lv[l].pw, c->lv[l].w, c->lv[l].h, p.patch_stride, true);
     build_gauss_tables(c);
     build_rng_tables(c);
     if (!getenv("EPPM_NO_TMA")) build_smooth_tensor_maps(c);

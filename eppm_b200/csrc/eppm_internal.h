@@ -44,7 +44,7 @@ struct Arena {
     size_t size = 0, used = 0;
     template <class T>
     T* take(size_t n) {
-        size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+        size_t bytes = (n * sizeof(T) + 511) & ~size_t(511);   // 512 B: the texture alignment (linear textures are bound over arena planes)
         T* p = reinterpret_cast<T*>(base + used);
         used += bytes;
         return p;
@@ -53,6 +53,11 @@ struct Arena {
 
 struct AffineTab {
     int off[3][361];   // dy * pw + dx of affine model 1..3 at sample (i, j) of the patch (100 samples at stride 2, 361 at 1, 49 at 3), relative to the candidate centre; i outer, j inner
+    // at most one site whose x offset is NOT a function of (i, j, model) alone (stride 1: model 3 at (-7, -2) lies 3e-8 from an integer):
+    // the table holds its offset without dx and the kernel computes dx = floor(fma(i, exc_ci, fma(j, exc_cj, float(X)))) - X per thread
+    int exc_s;         // sample index of that site, -1 = none
+    int exc_q;         // its model (0..2)
+    float exc_cj, exc_ci;
 };
 
 struct SmoothLut {
@@ -143,7 +148,7 @@ void run_consistency(eppm_context* c);
 void run_c2f(eppm_context* c, float* d_flow_out);
 void build_rng_tables(eppm_context* c);
 void build_gauss_tables(eppm_context* c);
-bool build_affine_tab(AffineTab& t, int pw, int w, int h, int stride = 2);
+bool build_affine_tab(AffineTab& t, int pw, int w, int h, int stride = 2, bool allow_exception = false);
 
 // building blocks reused by the legacy stage ABI (foreign buffers)
 void op_lr_check(cudaStream_t s, short2* nnf, float* cost, const short2* nnf2, int w, int h, int n);

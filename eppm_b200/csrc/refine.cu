@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(RF_PIX * 3, RF_MINBLOCKS) k_c2f_refine(RefineA
 // (bao_pmflow_kernel.cu:402,440,478 as contracted by nvcc).  For odd (i, j) the real value j*C_x + i*C_y never comes closer than
 // 1e-3 to an integer, far more than the two FFMA roundings can move it at any |X| < 2^15, so site - X is a function of (i, j, model)
 // alone.  The same holds at stride 3; at stride 1 one site (model 3, (i, j) = (-7, -2): -2*0.205 - 7*0.370 = -3.00000003) does depend
-// on X, the check below rejects the table and the computing kernel k_c2f_refine runs instead.  build_affine_tab() tabulates it and CHECKS that claim for every X the level can produce with the host's correctly rounded
+// on X: the table holds that site without its dx and the kernel computes dx with the reference's two FFMAs (AffineTab::exc_*).  build_affine_tab() tabulates it and CHECKS that claim for every X the level can produce with the host's correctly rounded
 // fmaf; only then is this kernel used.  It replaces 2 FFMA + F2I + IADD + IMAD per coordinate by one table read per site,
 // and groups the `t2 < -126` fix-up of __expf (taken by ~1 % of the samples) of the four models of a candidate into one test.
 // base + off pixels as ONE IMAD.WIDE (left to itself the compiler sign-extends and shifts with three ALU instructions)
@@ -267,6 +267,13 @@ __global__ void __launch_bounds__(RF_PIX * 9 / NCT, MINB)
                 off[0] = irow + j;  // identity model: the exact integer site (cx + j, cy + i)
 #pragma unroll
                 for (int q = 0; q < 3; q++) off[q + 1] = tab.off[q][s];
+                if (STRIDE == 1 && s == tab.exc_s) {   // the one site of stride 1 whose x offset depends on the coordinate itself (see AffineTab)
+                    const int X = (int)cx + j;
+                    const int dx = __float2int_rd(__fmaf_rn((float)i, tab.exc_ci, __fmaf_rn((float)j, tab.exc_cj, (float)X))) - X;
+#pragma unroll
+                    for (int q = 0; q < 3; q++)
+                        if (q == tab.exc_q) off[q + 1] += dx;
+                }
 #pragma unroll
                 for (int n = 0; n < NCT; n++) {
 #ifndef RF_NOVALID
@@ -329,20 +336,32 @@ __global__ void __launch_bounds__(RF_PIX * 9 / NCT, MINB)
 
 // Site table of one level (pitch pw) and its proof: for every integer X in [lo, hi] that a candidate coordinate + offset can take,
 // floor(fmaf(i, Cy, fmaf(j, Cx, (float)X))) - X must equal the tabulated value.  Host fmaf is correctly rounded = the device FFMA.
-bool build_affine_tab(AffineTab& t, int pw, int w, int h, int stride) {
+bool build_affine_tab(AffineTab& t, int pw, int w, int h, int stride, bool allow_exception) {
     static const float pf[3][4] = {{0.177f, -0.011f, -0.003f, 0.301f}, {0.125f, -0.357f, 0.009f, 0.308f}, {0.205f, 0.370f, 0.011f, 0.296f}};
     auto site = [](float fi, float fj, float cj, float ci, int X) { return (int)floorf(fmaf(fi, ci, fmaf(fj, cj, (float)X))) - X; };
     if (stride < 1 || stride > 3) return false;
     const int lim = (w > h ? w : h) + PATCH_R;
+    t.exc_s = -1; t.exc_q = 0; t.exc_cj = t.exc_ci = 0.f;
     int s = 0;
     for (int i = -PATCH_R; i <= PATCH_R; i += stride)
         for (int j = -PATCH_R; j <= PATCH_R; j += stride, s++)
             for (int q = 0; q < 3; q++) {
                 // x: cx2 = fma(i, C_uy, fma(j, C_ux, float(cx + j)));  y: cy2 = fma(i, C_vy, fma(j, C_vx, float(cy + i)))
-                const int dx = site((float)i, (float)j, pf[q][0], pf[q][1], 1000), dy = site((float)i, (float)j, pf[q][2], pf[q][3], 1000);
-                for (int X = -PATCH_R; X <= lim; X++)
-                    if (site((float)i, (float)j, pf[q][0], pf[q][1], X) != dx || site((float)i, (float)j, pf[q][2], pf[q][3], X) != dy) return false;
-                if (abs(dx + j) >= PAD || abs(dy + i) >= PAD) return false;
+                int dx = site((float)i, (float)j, pf[q][0], pf[q][1], 1000);
+                const int dy = site((float)i, (float)j, pf[q][2], pf[q][3], 1000);
+                bool x_ok = true;
+                for (int X = -PATCH_R; X <= lim; X++) {
+                    if (site((float)i, (float)j, pf[q][2], pf[q][3], X) != dy) return false;
+                    const int d = site((float)i, (float)j, pf[q][0], pf[q][1], X);
+                    if (d != dx) x_ok = false;
+                    if (abs(d + j) >= PAD) return false;
+                }
+                if (!x_ok) {   // the x offset of this site depends on X: one such site may be left to the kernel
+                    if (!allow_exception || t.exc_s >= 0) return false;
+                    t.exc_s = s; t.exc_q = q; t.exc_cj = pf[q][0]; t.exc_ci = pf[q][1];
+                    dx = 0;
+                }
+                if (abs(dy + i) >= PAD) return false;
                 t.off[q][s] = (dy + i) * pw + (dx + j);
             }
     return true;

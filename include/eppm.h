@@ -162,7 +162,8 @@ int eppm_smooth_uses_tma(eppm_context* ctx);
  * eppm_refine_uses_site_table reports what a context's refine kernel does at `level`. */
 int eppm_selftest_affine_sites(int w, int h, int pw, int* table_out);
 /* The same for patch stride 1, 2 or 3: n = 19, 10 or 7 samples per patch row, table_out = 3 x n*n offsets.  Strides 2 and 3 verify at
- * every size; stride 1 does not (one site, model 3 at (i, j) = (-7, -2), lies 3e-8 from an integer) and keeps the computing kernel. */
+ * every size; stride 1 does not as a pure table (returns 0): one site, model 3 at (i, j) = (-7, -2), lies 3e-8 from an integer -- a
+ * context at stride 1 tabulates the other 1082 sites and computes that one per thread with the reference's arithmetic. */
 int eppm_selftest_affine_sites_stride(int w, int h, int pw, int stride, int* table_out);
 int eppm_refine_uses_site_table(eppm_context* ctx, int level);
 
