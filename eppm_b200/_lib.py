@@ -76,6 +76,7 @@ LEGACY_SYMBOLS = {
     "baoEliminateStillRegionFlow": (None, [_P, _P, _P, _I, _I, _S]),
     "baoCudaImageSmoothing": (None, [_P, _P, _I, _I, _S]),
     "baoCudaFlowBilteralUpsampling": (None, [_P, _P, _I, _I, _S, _P, _I, _I, C.c_float]),
+    "baoCudaPatchMatch_Scaled": (None, [_P] * 7 + [_I, _I, _S, _S, _S, _S, _S]),
     "baoCudaPatchMatch_PlaneFitting": (None, [_P] * 6 + [_I, _I, _S, _S, _S, _S]),
     "baoCudaCensusTransform_Bicubic": (None, [_P, _P, _I, _I, _S, _P, _P, _I, _I, _S]),
     "baoCudaSubpixRefine": (None, [_P] * 6 + [_I, _I, _S, _S, _S, _S]),

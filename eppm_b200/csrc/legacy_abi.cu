@@ -175,6 +175,17 @@ void baoCudaPatchMatch(short2* d_disp_vec, float* d_cost, uchar4* d_img1, uchar4
     copy_out(c, d_cost, cost_pitch, c->cost[0], w, h);
 }
 
+// Declared by the reference's host class, called nowhere, and unfinished upstream (its row pass stores the candidate's scale into the cost
+// plane, bao_pmflow_kernel.cu:1207; its cost ignores the census planes it is given): exported so that any caller links, refuses loudly.
+void baoCudaPatchMatch_Scaled(short2* d_disp_vec, float* d_scale, float* d_cost, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1,
+                              unsigned char* d_census2, int w, int h, size_t img_pitch, size_t cost_pitch, size_t disp_pitch, size_t scale_pitch,
+                              size_t census_pitch) {
+    (void)d_disp_vec; (void)d_scale; (void)d_cost; (void)d_img1; (void)d_img2; (void)d_census1; (void)d_census2; (void)w; (void)h;
+    (void)img_pitch; (void)cost_pitch; (void)disp_pitch; (void)scale_pitch; (void)census_pitch;
+    set_error("baoCudaPatchMatch_Scaled is not implemented (unfinished in the reference); outputs untouched");
+    complain("baoCudaPatchMatch_Scaled");
+}
+
 void baoCudaPatchMatch_PlaneFitting(short2* d_disp_vec, float* d_cost, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1,
                                     unsigned char* d_census2, int w, int h, size_t img_pitch, size_t cost_pitch, size_t disp_pitch, size_t census_pitch) {
     eppm_context* c = get_ctx(g_single, h, w, 1);

@@ -65,6 +65,11 @@ void baoCudaImageSmoothing(uchar4* d_img_smoothed, uchar4* d_img, int w, int h, 
  * without any known tap keep their content (the spelling of the name is the reference's) */
 void baoCudaFlowBilteralUpsampling(float2* d_flow_vec, uchar4* d_img, int w, int h, size_t img_pitch, float2* d_flow_vec_small, int w_s, int h_s,
                                    float ratio_up);
+/* bao_pmflow_kernel.cu:1828-1895: NOT IMPLEMENTED -- exported so that callers link; prints to stderr, sets eppm_last_error() and leaves the
+ * outputs untouched.  The upstream function is unfinished (its row pass writes the candidate's scale into the cost plane, :1207). */
+void baoCudaPatchMatch_Scaled(short2* d_disp_vec, float* d_scale, float* d_cost, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1,
+                              unsigned char* d_census2, int w, int h, size_t img_pitch, size_t cost_pitch, size_t disp_pitch, size_t scale_pitch,
+                              size_t census_pitch);
 /* bao_pmflow_kernel.cu:1897-1963: PatchMatch scored with the plane-fitting cost of the refine stage (min over four affine patch models) */
 void baoCudaPatchMatch_PlaneFitting(short2* d_disp_vec, float* d_cost, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1,
                                     unsigned char* d_census2, int w, int h, size_t img_pitch, size_t cost_pitch, size_t disp_pitch, size_t census_pitch);

@@ -45,6 +45,16 @@ def test_library_exports_every_declared_symbol():
     assert set(_declared("eppm_legacy_abi.h")) == set(_lib.LEGACY_SYMBOLS)
 
 
+def test_unimplemented_stage_function_refuses_loudly(capfd):
+    """baoCudaPatchMatch_Scaled (unfinished upstream) is exported so that callers link, but must not pretend to work: it reports on stderr and
+    through eppm_last_error() and touches nothing.  No GPU needed: it returns before any CUDA call."""
+    lib = _lib.load()
+    lib.eppm_last_error.restype = C.c_char_p
+    lib.baoCudaPatchMatch_Scaled(*([None] * 7), 8, 8, 0, 0, 0, 0, 0)
+    assert b"not implemented" in lib.eppm_last_error()
+    assert "baoCudaPatchMatch_Scaled" in capfd.readouterr().err
+
+
 def test_default_params_are_the_reference_macros():
     p = E.default_params()  # defs.h:31-76
     assert (p.pyr_levels, p.num_iter, p.patch_r, p.patch_stride) == (3, 10, 9, 2)

@@ -95,9 +95,10 @@ REF_POINTS = {(3, 10, 2): refharness.REF_LIB, (2, 5, 2): refharness.variant_lib(
               (3, 10, 3): refharness.variant_lib("s3"), (3, 10, 1): refharness.variant_lib("s1")}
 res = {"workload": f"{W}x{H} stream, clip of {CLIP} chained synthetic frames cycled; {n_full} frames at the default point, {n_other} elsewhere",
        "points": []}
+STRIDES = tuple(int(x) for x in os.environ.get("SS_STRIDES", "1,2,3").split(","))   # SS_STRIDES=1,3 re-measures two columns only
 for depth in (2, 3, 4):
     for iters in (2, 5, 10):
-        for stride in (1, 2, 3):
+        for stride in STRIDES:
             key = (depth, iters, stride)
             r = run_point(depth, iters, stride, n_full if key == (3, 10, 2) else n_other)
             row = {"pyr_depth": depth, "num_iter": iters, "patch_stride": stride, **r}
@@ -106,4 +107,15 @@ for depth in (2, 3, 4):
             res["points"].append(row)
             print(row, flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "stream_sweep.json"), "w"), indent=1)
+out_path = os.path.join(ROOT, "gpurun_out", "stream_sweep.json")
+if len(STRIDES) < 3 and os.path.exists(os.path.join(ROOT, "profiles", "r01_stream_sweep.json")):   # merge into the committed table
+    old = json.load(open(os.path.join(ROOT, "profiles", "r01_stream_sweep.json")))
+    new = {(p["pyr_depth"], p["num_iter"], p["patch_stride"]): p for p in res["points"]}
+    merged = []
+    for p in old["points"]:
+        q = new.get((p["pyr_depth"], p["num_iter"], p["patch_stride"]), p)
+        if "reference" in p and "reference" not in q:
+            q["reference"] = p["reference"]   # the reference build did not change
+        merged.append(q)
+    res["points"] = merged
+json.dump(res, open(out_path, "w"), indent=1)
