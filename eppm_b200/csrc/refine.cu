@@ -748,11 +748,12 @@ void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pi
     static const CUtensorMap dummy = {};
     if (a.R == S4_R && c->prm.blf_sig_r <= 10.f && !(c->variant & EPPM_VAR_SMOOTH_2ROW)) {
         // four rows per thread, packed pairs (SMOOTH_FAR = 1e4 needs exp(-(1e4/sig_r)^2) == 0, true for any sig_r <= 10)
-        static bool attr4 = false;
-        if (!attr4) {
+        // the opt-in to > 48 KB of dynamic shared memory is per device: once per device the library has seen (a process may hold contexts on several)
+        static bool attr4[64] = {};
+        if (c->device < 0 || c->device >= 64 || !attr4[c->device]) {
             cudaFuncSetAttribute(k_flow_smooth4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4_SMEM);
             cudaFuncSetAttribute(k_flow_smooth4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4_SMEM);
-            attr4 = true;
+            if (c->device >= 0 && c->device < 64) attr4[c->device] = true;
         }
         const int use_tma = level >= 0 && c->tmap_ok[level] && c->tmap_box_h == S4_TH;
         dim3 blk(S4_TX, S4_TY), grd((g.w + S4_TX - 1) / S4_TX, (y1 - y0 + S4_TY * S4_PY - 1) / (S4_TY * S4_PY), n);
@@ -763,10 +764,10 @@ void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pi
     }
     const int TW = SM_TX + 2 * a.R, TH = SM_TY * SM_PY + 2 * a.R;
     const size_t smem = (size_t)TW * TH * (sizeof(float4) + sizeof(float2)) + (size_t)(a.R + 1) * (a.R + 1) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (c->device < 0 || c->device >= 64 || !attr_set[c->device]) {
         cudaFuncSetAttribute(k_flow_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
+        if (c->device >= 0 && c->device < 64) attr_set[c->device] = true;
     }
     dim3 blk(SM_TX, SM_TY), grd((g.w + SM_TX - 1) / SM_TX, (y1 - y0 + SM_TY * SM_PY - 1) / (SM_TY * SM_PY), n);
     const int use_tma = level >= 0 && c->tmap_ok[level] && c->tmap_box_h == TH && TW * 4 <= 256 && TH <= 256;

@@ -363,8 +363,7 @@ void baoCudaSubpixRefine(float2* d_flow, short2* d_disp_vec, uchar4* d_img1, uch
             }
             lut.ata[p][q] = (float)s;
         }
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_subpix_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM); attr = true; }
+    cudaFuncSetAttribute(k_subpix_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM);   // per device; cheap next to the stage
     dim3 grd((w + SP_WARPS - 1) / SP_WARPS, h);
     k_subpix_refine<<<grd, SP_WARPS * 32, SP_SMEM>>>(a, lut);
     EPPM_LAUNCH_COUNT(1);
