@@ -146,10 +146,17 @@ def run_b200(args):
     a, b, gt, va = make_inputs(args.batch, args.distinct, rank)
     d = a.shape[0]
     chunk = min(args.chunk, args.batch)
+    if args.stream_priorities:
+        os.environ["EPPM_STREAM_PRIORITY"] = str(-5)
     ctx = E.EppmContext(H, W, chunk, device=local)
     # optional second context on its own stream: alternate chunks so that one chunk's PatchMatch (L1-bound) can overlap the
     # other's refine (issue-bound) on the same SMs
-    ctxs = [ctx] + [E.EppmContext(H, W, chunk, device=local) for _ in range(args.streams - 1)]
+    ctxs = [ctx]
+    for k in range(1, args.streams):
+        if args.stream_priorities:   # later contexts less urgent: their kernels fill the SMs the first context's leave idle
+            os.environ["EPPM_STREAM_PRIORITY"] = str(0)
+        ctxs.append(E.EppmContext(H, W, chunk, device=local))
+    os.environ.pop("EPPM_STREAM_PRIORITY", None)
     # pinned host batch (cycled distinct pairs) and device-resident copy
     idx = [i % d for i in range(args.batch)]
     h_a = torch.empty((args.batch, H, W, 3), dtype=torch.uint8).pin_memory()
@@ -334,6 +341,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic pairs generated and cycled through the batch")
     ap.add_argument("--ref-sample", type=int, default=8, help="pairs per step for --impl reference")
     ap.add_argument("--streams", type=int, default=1, help="contexts/streams alternating over the chunks of a step")
+    ap.add_argument("--stream-priorities", action="store_true", help="with --streams 2: first context urgent, the others at the lowest priority")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

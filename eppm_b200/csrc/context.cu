@@ -125,7 +125,14 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->n_sm = v; }
     c->variant = getenv("EPPM_VARIANT") ? atoi(getenv("EPPM_VARIANT")) : 0;
     c->profile = getenv("EPPM_PROFILE") && atoi(getenv("EPPM_PROFILE")) != 0;
-    if (!cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return EPPM_ERR_CUDA; }
+    {
+        // EPPM_STREAM_PRIORITY (measurement knob): CUDA stream priority of this context's compute stream (lower = more urgent), so that
+        // two contexts on one device can be ranked when their kernels compete for SMs
+        int lo = 0, hi = 0, pr = getenv("EPPM_STREAM_PRIORITY") ? atoi(getenv("EPPM_STREAM_PRIORITY")) : 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        pr = pr < hi ? hi : (pr > lo ? lo : pr);
+        if (!cuda_ok(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, pr), "cudaStreamCreate")) { delete c; return EPPM_ERR_CUDA; }
+    }
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev_k[i]);
