@@ -1,31 +1,5 @@
 mkdir -p gpurun_out
-bash tools/config1_times.sh > gpurun_out/config1_times.txt 2>&1; cat gpurun_out/config1_times.txt
-cat > /tmp/subpix_step.py <<'PY'
-import os, sys, ctypes as C
-sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
-import numpy as np, torch
-from eppm_b200 import _lib
-import refharness
-z = np.load("tests/golden/refsub_s128x96.npz"); h, w = int(z["h"]), int(z["w"])
-# tile the fixture to a 1080p-coarsest-level sized problem (480x270) so the kernel fills the GPU
-ry, rx = 3, 4
-til = lambda a: np.ascontiguousarray(np.tile(a, (ry, rx) + (1,) * (a.ndim - 2))[:270, :480])
-rg1, rg2 = til(z["rgba1"]), til(z["rgba2"]); H, W = rg1.shape[:2]
-nnf = til(z["nnf"]).copy()
-yy, xx = np.mgrid[0:H, 0:W]
-nnf[..., 0] = np.clip(nnf[..., 0] % w + (xx // w) * w, 0, W - 1); nnf[..., 1] = np.clip(nnf[..., 1] % h + (yy // h) * h, 0, H - 1)
-lib = _lib.load()
-S, I, V = C.c_size_t, C.c_int, C.c_void_p
-lib.baoCudaCensusTransform_Bicubic.argtypes = [V, V, I, I, S, V, V, I, I, S]; lib.baoCudaSubpixRefine.argtypes = [V] * 6 + [I, I, S, S, S, S]
-i1, pitch = refharness.pitched(rg1); i2, _ = refharness.pitched(rg2)
-cp = (2 * W + 511) // 512 * 512
-u1 = torch.zeros((2 * H, cp), dtype=torch.uint8, device="cuda"); u2 = torch.zeros_like(u1)
-dn = torch.from_numpy(nnf).cuda(); fl = torch.zeros((H, W, 2), dtype=torch.float32, device="cuda")
-for _ in range(2):
-    lib.baoCudaCensusTransform_Bicubic(u1.data_ptr(), u2.data_ptr(), 2 * W, 2 * H, cp, i1.data_ptr(), i2.data_ptr(), W, H, pitch)
-    lib.baoCudaSubpixRefine(fl.data_ptr(), dn.data_ptr(), i1.data_ptr(), i2.data_ptr(), u1.data_ptr(), u2.data_ptr(), W, H, pitch, cp, W * 4, W * 8)
-torch.cuda.synchronize(); print("done")
-PY
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_subpix_refine|k_census_bicubic' --launch-skip 2 -c 2 -o gpurun_out/subpix -f python /tmp/subpix_step.py > gpurun_out/ncu_subpix.log 2>&1; tail -2 gpurun_out/ncu_subpix.log
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_flow_smooth4|k_wmf' --launch-skip 10 -c 3 -o gpurun_out/smooth_wmf -f python tools/ncu_step.py 4 1 > gpurun_out/ncu_sw.log 2>&1; tail -2 gpurun_out/ncu_sw.log
-( time timeout 600 python -m pytest tests -m gpu -q -rs ) > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
+for mode in "--streams 1" "--streams 2" "--streams 2 --stream-priorities"; do
+  timeout 300 python bench.py --batch 128 --steps 2 --warmup 2 --no-cpu-baseline $mode > gpurun_out/bench_streams.json 2> gpurun_out/bench_streams.err
+  echo "$mode: $(python -c "import json;d=json.load(open('gpurun_out/bench_streams.json'));print(d['value'], d['e2e']['value'])")"
+done
