@@ -74,9 +74,14 @@ static void flow_to_color(const float* uv, unsigned char*** out, int h, int w, f
     const float maxrad = sqrtf(max_x * max_x + max_y * max_y);
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
-            float fx = uv[2 * ((size_t)y * w + x)] / maxrad, fy = uv[2 * ((size_t)y * w + x) + 1] / maxrad;
+            const float ux = uv[2 * ((size_t)y * w + x)], uy = uv[2 * ((size_t)y * w + x) + 1];
+            if (!(fabsf(ux) < 999999.f && fabsf(uy) < 999999.f)) {   // unknown flow stays black (basic/bao_basic_cuda.cuh:823)
+                out[y][x][0] = out[y][x][1] = out[y][x][2] = 0;
+                continue;
+            }
+            const float fx = ux / maxrad, fy = uy / maxrad;
             const float rad = sqrtf(fx * fx + fy * fy);
-            const float a = atan2f(-fy, -fx) / 3.14159265358979f;
+            const float a = atan2f(-fy, -fx) / 3.14159f;   // the reference's constant (:781)
             const float fk = (a + 1.0f) / 2.0f * (ncols - 1);
             const int k0 = (int)fk, k1 = (k0 + 1) % ncols;
             const float f = fk - k0;
