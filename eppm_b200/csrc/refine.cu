@@ -205,6 +205,15 @@ __device__ __forceinline__ const float4* pix_at(const float4* base, int off) {
 // 1: CTA = 9 warps, warp (m, n) owns ONE candidate and its four models (72 registers, 27 warps per SM): the image-1 side of a
 // sample is shared by 4 instead of 12 accumulator pairs (33.4 instead of 30.7 instructions per sample).  Measured equal (8.70 vs 8.74 ms
 // per 1080p pair at level 0; 56 registers / 36 warps: 9.27 ms) -- the kernel is not occupancy bound; kept behind EPPM_VARIANT=256.
+#ifndef RF_TAB2_MINBLOCKS
+#define RF_TAB2_MINBLOCKS 7   // the default (stride-2, table) instantiation: 80 registers, 7 CTAs = 21 warps per SM, 80 B of spill outside the sample
+                              // loop; measured 8.46 ms per 1080p pair at level 0 against 8.75 (6 CTAs, 96 registers), 9.26 (5), 8.83 (8)
+#endif
+#ifndef RF_JUNROLL
+#define RF_JUNROLL 2   // samples of a patch row handled per iteration of the inner loop (tuning knob)
+#endif
+#define EPPM_PRAGMA_(x) _Pragma(#x)
+#define EPPM_PRAGMA(x) EPPM_PRAGMA_(x)
 template <bool GROUP_TINY, int NCT, int MINB, int STRIDE>
 __global__ void __launch_bounds__(RF_PIX * 9 / NCT, MINB)
     k_c2f_refine_tab(RefineArgs a, const __grid_constant__ CostLut lut, const __grid_constant__ AffineTab tab) {
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(RF_PIX * 9 / NCT, MINB)
         for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
             const int ai = i < 0 ? -i : i;
             const int irow = i * a.pw;
-#pragma unroll 2
+EPPM_PRAGMA(unroll RF_JUNROLL)
             for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE, s++) {
                 const float4 p1 = ldpix(a0 + irow + j);
                 const PixPk p1k = pack_pix(p1);
@@ -715,7 +724,7 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
             default:
                 if (v & EPPM_VAR_REFINE_NOGROUP) k_c2f_refine_tab<false, 3, RF_MINBLOCKS, 2><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else if (v & EPPM_VAR_REFINE_9WARP3) k_c2f_refine_tab<true, 1, 3, 2><<<grd, blk9, 0, c->stream>>>(a, c->cost_lut, *tabp);
-                else k_c2f_refine_tab<true, 3, RF_MINBLOCKS, 2><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+                else k_c2f_refine_tab<true, 3, RF_TAB2_MINBLOCKS, 2><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
             }
             EPPM_LAUNCH_COUNT(1);
             return;

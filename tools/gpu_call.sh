@@ -6,5 +6,6 @@ mkdir -p gpurun_out
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 timeout 400 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 cut -c1-400 gpurun_out/bench.json; cut -c1-200 gpurun_out/bench_ref.json
+[ -n "$SKIP_LAUNCH_LIST" ] && exit 0
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --batch 16 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
