@@ -234,6 +234,25 @@ def test_synth_is_deterministic_and_consistent():
     assert np.median(d[v1]) <= 6  # valid pixels really correspond
 
 
+def test_stream_generator_chains_pairs():
+    """synth.make_stream (BASELINE config 5 clip): frame t+1 is frame t moved by a fresh seeded motion; deterministic; the first pair is the
+    stand-alone pair of the same index."""
+    fr, fl, va = synth.make_stream(48, 64, 4, first_idx=9, scale_to=0.1)
+    fr2, fl2, va2 = synth.make_stream(48, 64, 4, first_idx=9, scale_to=0.1)
+    assert fr.shape == (4, 48, 64, 3) and fl.shape == (3, 48, 64, 2) and va.shape == (3, 48, 64)
+    assert np.array_equal(fr, fr2) and np.array_equal(fl, fl2) and np.array_equal(va, va2)
+    a, b, f0, v0 = synth.make_pair(48, 64, 9, scale_to=0.1)
+    assert np.array_equal(fr[0], a) and np.array_equal(fr[1], b) and np.array_equal(fl[0], f0)
+    a1, _, _, _ = synth.make_pair(48, 64, 10, scale_to=0.1)
+    assert not np.array_equal(fr[1], a1)                                   # later frames continue the clip, they are not fresh textures
+    # the ground truth really maps frame t onto frame t+1 where it is valid: warping back recovers the colours up to interpolation + noise
+    t = 1
+    yy, xx = np.mgrid[0:48, 0:64]
+    tx = np.clip(np.rint(xx + fl[t, ..., 0]).astype(int), 0, 63); ty = np.clip(np.rint(yy + fl[t, ..., 1]).astype(int), 0, 47)
+    err = np.abs(fr[t + 1][ty, tx].astype(np.float32) - fr[t].astype(np.float32)).max(-1)
+    assert np.median(err[va[t]]) <= 12
+
+
 def test_flo_and_ppm_io(tmp_path):
     fl = np.random.default_rng(0).normal(size=(7, 9, 2)).astype(np.float32)
     p = str(tmp_path / "x.flo")
