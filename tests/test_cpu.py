@@ -40,6 +40,8 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 30
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ but not exported by libeppm_b200.so"
+    # the one C++-linkage function of the legacy header (mangled like the reference's own definition, so that its host class links)
+    assert hasattr(lib, "_Z34bao_cuda_convert_flow_to_colorshowP6uchar4P6float2iiff")
     # and the Python prototype tables cover the same set
     assert set(_declared("eppm.h")) == set(_lib.EPPM_SYMBOLS)
     assert set(_declared("eppm_legacy_abi.h")) == set(_lib.LEGACY_SYMBOLS)
