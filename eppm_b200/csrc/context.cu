@@ -209,7 +209,8 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
     }
     for (int l = 0; l + 1 < c->n_levels; l++) c->aff_ok[l] = build_affine_tab(c->aff_tab[l], c->lv[l].pw, c->lv[l].w, c->lv[l].h, p.patch_stride, true);
     build_gauss_tables(c);
-    build_rng_tables(c);
+    // the random tables are expanded on the first PatchMatch of the context (ensure_rng_tables): the legacy stage functions create
+    // contexts for levels that never run PatchMatch
     if (!getenv("EPPM_NO_TMA")) build_smooth_tensor_maps(c);
     {
         // linear textures over the packed planes of the PatchMatch level (both images): element type uint4, point fetch by texel index

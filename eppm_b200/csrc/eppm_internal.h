@@ -128,6 +128,7 @@ struct eppm_context {
     int aff_ok[eppm::MAX_LEVELS] = {};
     int variant = 0;                             // EPPM_VARIANT bit mask (A/B switches for measurements, see EPPM_VAR_*)
     int smooth_fast_div = 0;                     // set at create time when the constant-division fast path was verified exact
+    int rng_ready = 0;                           // rng_init / rng_search expanded (lazily, before the first PatchMatch)
 };
 
 namespace eppm {
@@ -147,6 +148,7 @@ void band_rows(const eppm_context* c, int level, int* y0, int* y1);
 void run_consistency(eppm_context* c);
 void run_c2f(eppm_context* c, float* d_flow_out);
 void build_rng_tables(eppm_context* c);
+void ensure_rng_tables(eppm_context* c);   // builds them on the context's stream the first time a PatchMatch is queued
 void build_gauss_tables(eppm_context* c);
 bool build_affine_tab(AffineTab& t, int pw, int w, int h, int stride = 2, bool allow_exception = false);
 

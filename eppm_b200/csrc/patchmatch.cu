@@ -78,6 +78,12 @@ void build_rng_tables(eppm_context* c) {
     EPPM_LAUNCH_COUNT(1);
 }
 
+void ensure_rng_tables(eppm_context* c) {
+    if (c->rng_ready) return;
+    build_rng_tables(c);   // same stream as the PatchMatch kernels that follow
+    c->rng_ready = 1;
+}
+
 struct PmArgs {
     const float4* pix[2];   // packed planes of image 1 / image 2 at the PatchMatch level, padded origin of pair 0
     const float4* pixT[2];  // column-major copies (pixel (x,y) at (x+PAD)*ph + (y+PAD)), padded origin of pair 0
@@ -678,6 +684,7 @@ static void launch_pf_propagate(eppm_context* c, const PmArgs& a) {
 // forward direction of pair 0 on the context's coarsest-level planes; patch stride 2 only (the reference's compile-time stride)
 bool run_patchmatch_planefitting(eppm_context* c) {
     if (c->prm.patch_stride != 2) { set_error("plane-fitting PatchMatch is built for patch stride 2"); return false; }
+    ensure_rng_tables(c);
     const int L = c->n_levels - 1;
     const LevelGeom& g = c->lv[L];
     PmArgs a = {};
@@ -706,6 +713,7 @@ template <int STRIDE>
 static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first_step);
 
 void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps, int first_step) {
+    ensure_rng_tables(c);
     // the sample stride of the patch ("pixel skipping", bao_pmflow_kernel.cu:269,272) is a compile-time constant of the kernels
     switch (c->prm.patch_stride) {
     case 1: run_patchmatch_t<1>(c, n_dirs, n_steps, first_step); break;
