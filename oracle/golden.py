@@ -36,6 +36,12 @@ def lib():
         l.golden_patch_cost.restype = C.c_float; l.golden_patch_cost.argtypes = [P, I, I, I, I, I]
         l.golden_census_bicubic.argtypes = [P, I, I, I, I, P]
         l.golden_subpix_refine.argtypes = [P, P, P, P, P, P, I, I, I, I]
+        l.golden_lr_check_buffered.argtypes = [P, P, P, P, I, I]
+        l.golden_flow_to_nnf.argtypes = [P, P, I, I]
+        l.golden_flow_cutoff.argtypes = [P, I, I, C.c_float]
+        l.golden_eliminate_still.argtypes = [P, P, P, I, I]
+        l.golden_image_smoothing.argtypes = [P, P, I, I]
+        l.golden_flow_bilateral_upsample.argtypes = [P, P, I, I, P, I, C.c_float]
         _lib = l
     return _lib
 
@@ -63,6 +69,50 @@ def subpix_refine(rgba1, rgba2, cen1_up, cen2_up, nnf, flow, y0, y1):
     h, w = out.shape[:2]
     lib().golden_subpix_refine(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, nnf.ctypes.data, out.ctypes.data, w, h, y0, y1)
     return out
+
+
+def _c(a, dt):
+    return np.array(a, dt, copy=True, order="C")
+
+
+def lr_check_buffered(nnf, cost, nnf2, cost2):
+    """baoCudaLeftRightCheck_Buffered: returns the four planes after the check (oracle/golden_stages.cpp)."""
+    n1, c1, n2, c2 = _c(nnf, np.int16), _c(cost, np.float32), _c(nnf2, np.int16), _c(cost2, np.float32)
+    h, w = c1.shape
+    lib().golden_lr_check_buffered(n1.ctypes.data, c1.ctypes.data, n2.ctypes.data, c2.ctypes.data, w, h)
+    return n1, c1, n2, c2
+
+
+def flow_to_nnf(flow):
+    f = _c(flow, np.float32); h, w = f.shape[:2]
+    out = np.zeros((h, w, 2), np.int16)
+    lib().golden_flow_to_nnf(f.ctypes.data, out.ctypes.data, w, h)
+    return out
+
+
+def flow_cutoff(flow, m):
+    f = _c(flow, np.float32); h, w = f.shape[:2]
+    lib().golden_flow_cutoff(f.ctypes.data, w, h, m)
+    return f
+
+
+def eliminate_still(flow, rgba1, rgba2):
+    f, a, b = _c(flow, np.float32), _c(rgba1, np.uint8), _c(rgba2, np.uint8); h, w = f.shape[:2]
+    lib().golden_eliminate_still(f.ctypes.data, a.ctypes.data, b.ctypes.data, w, h)
+    return f
+
+
+def image_smoothing(rgba):
+    a = _c(rgba, np.uint8); h, w = a.shape[:2]
+    out = np.zeros((h, w, 3), np.uint8)
+    lib().golden_image_smoothing(a.ctypes.data, out.ctypes.data, w, h)
+    return out
+
+
+def flow_bilateral_upsample(out_init, rgba, small, ratio):
+    o, a, s = _c(out_init, np.float32), _c(rgba, np.uint8), _c(small, np.float32); h, w = o.shape[:2]
+    lib().golden_flow_bilateral_upsample(o.ctypes.data, a.ctypes.data, w, h, s.ctypes.data, s.shape[1], ratio)
+    return o
 
 
 def level_dims_for(h, w, level):

@@ -195,6 +195,29 @@ def test_oracle_subpixel_stage_against_reference_fixture(golden, path):
     assert np.array_equal(out[:y0], z["flow_in"][:y0]) and np.array_equal(out[y1:], z["flow_in"][y1:])
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "refstage_*.npz"))))
+def test_oracle_uncalled_stage_functions_against_reference_fixture(golden, path):
+    """oracle/golden_stages.cpp against outputs of the reference build (tools/gen_golden_stages.py) for the stage functions compute_flow
+    never calls.  Integer / pure-IEEE functions bit-exact; the three that weight by __expf (MUFU.EX2 on the GPU, exp2f here) within
+    the tolerances written below."""
+    z = np.load(path)
+    n1, c1, n2, c2 = golden.lr_check_buffered(z["lr_nnf1"], z["lr_cost1"], z["lr_nnf2"], z["lr_cost2"])
+    assert np.array_equal(n1, z["lr_out_nnf1"]) and np.array_equal(n2, z["lr_out_nnf2"])
+    assert np.array_equal(c1.view(np.uint32), z["lr_out_cost1"].view(np.uint32)) and np.array_equal(c2.view(np.uint32), z["lr_out_cost2"].view(np.uint32))
+    assert np.array_equal(golden.flow_to_nnf(z["f2n_flow"]), z["f2n_nnf"])                      # incl. saturation, NaN, unknown flow
+    assert np.array_equal(golden.flow_cutoff(z["f2n_flow"], 37.5).view(np.uint32), z["cutoff_out"].view(np.uint32))
+    h1, w1 = z["rgba1_L1"].shape[:2]
+    still = golden.eliminate_still(np.full((h1, w1, 2), 3.25, np.float32), z["rgba1_L1"], z["still_img2"])
+    assert ((still == 0).all(-1) == (z["still_out"] == 0).all(-1)).mean() >= 0.999            # threshold decisions, exp2f vs MUFU.EX2
+    sm = golden.image_smoothing(z["rgba1_L1"]).astype(np.int32)
+    d = np.abs(sm - z["smooth_out"].astype(np.int32))
+    assert d.max() <= 1 and (d == 0).mean() >= 0.99, (d.max(), (d == 0).mean())                # 8-bit levels
+    up = golden.flow_bilateral_upsample(np.full((h1, w1, 2), -7.0, np.float32), z["rgba1_L1"], z["up_small"], 2.0)
+    assert np.array_equal((up == -7.0).all(-1), (z["up_out"] == -7.0).all(-1))                  # the same pixels are left untouched
+    du = np.abs(up - z["up_out"])
+    assert du.mean() <= 1e-4 and du.max() <= 1e-2, (du.mean(), du.max())                        # px
+
+
 def test_oracle_stage_injection_is_deterministic(golden):
     """LR check / outlier removal / hole filling / NNF->flow given the reference's own PatchMatch output.  The backward field after
     the LR check is deterministic in the reference and must match bit for bit.  In the forward field, pixels that survive the

@@ -398,6 +398,43 @@ def test_subpixel_refine_against_committed_reference_fixture(mine, path):
     assert same_bits(fl.cpu().numpy(), z["flow_out"])
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "refstage_*.npz"))))
+def test_uncalled_stage_functions_against_committed_reference_fixture(mine, path):
+    """The stage functions compute_flow never calls against outputs of the reference build committed under tests/golden
+    (tools/gen_golden_stages.py): bit-exact, and runs without oracle/_ref."""
+    z = np.load(path)
+    S, I, V = C.c_size_t, C.c_int, C.c_void_p
+    mine.baoCudaLeftRightCheck_Buffered.argtypes = [V] * 6 + [I, I, S, S]
+    mine.baoCudaFlow2NNF.argtypes = [V, V, I, I, S, S]
+    mine.baoCudaFlowCutoff.argtypes = [V, I, I, S, C.c_float]
+    mine.baoEliminateStillRegionFlow.argtypes = [V, V, V, I, I, S]
+    mine.baoCudaImageSmoothing.argtypes = [V, V, I, I, S]
+    mine.baoCudaFlowBilteralUpsampling.argtypes = [V, V, I, I, S, V, I, I, C.c_float]
+    h1, w1 = z["rgba1_L1"].shape[:2]
+    h2, w2 = z["up_small"].shape[:2]
+    t = [dev(z["lr_nnf1"]), dev(z["lr_cost1"]), dev(z["lr_nnf2"]), dev(z["lr_cost2"])]
+    tn, tc = torch.zeros_like(t[0]), torch.zeros_like(t[1])
+    mine.baoCudaLeftRightCheck_Buffered(P(t[0]), P(t[1]), P(t[2]), P(t[3]), P(tn), P(tc), w1, h1, w1 * 4, w1 * 4)
+    torch.cuda.synchronize()
+    for got, key in zip(t, ("lr_out_nnf1", "lr_out_cost1", "lr_out_nnf2", "lr_out_cost2")):
+        assert same_bits(got.cpu().numpy(), z[key]), key
+    o = torch.zeros((h1, w1, 2), dtype=torch.int16, device="cuda"); d = dev(z["f2n_flow"])
+    mine.baoCudaFlow2NNF(P(o), P(d), w1, h1, w1 * 4, w1 * 8); torch.cuda.synchronize()
+    assert np.array_equal(o.cpu().numpy(), z["f2n_nnf"])
+    d = dev(z["f2n_flow"]); mine.baoCudaFlowCutoff(P(d), w1, h1, w1 * 8, 37.5); torch.cuda.synchronize()
+    assert same_bits(d.cpu().numpy(), z["cutoff_out"])
+    ia, pitch = refharness.pitched(z["rgba1_L1"]); ib, _ = refharness.pitched(z["still_img2"])
+    d = torch.full((h1, w1, 2), 3.25, dtype=torch.float32, device="cuda")
+    mine.baoEliminateStillRegionFlow(P(d), P(ia), P(ib), w1, h1, pitch); torch.cuda.synchronize()
+    assert same_bits(d.cpu().numpy(), z["still_out"])
+    o = torch.zeros_like(ia)
+    mine.baoCudaImageSmoothing(P(o), P(ia), w1, h1, pitch); torch.cuda.synchronize()
+    assert np.array_equal(o.cpu().numpy()[:, : w1 * 4].reshape(h1, w1, 4)[..., :3], z["smooth_out"])
+    o = torch.full((h1, w1, 2), -7.0, dtype=torch.float32, device="cuda"); d = dev(z["up_small"])
+    mine.baoCudaFlowBilteralUpsampling(P(o), P(ia), w1, h1, pitch, P(d), w2, h2, 2.0); torch.cuda.synchronize()
+    assert same_bits(o.cpu().numpy(), z["up_out"])
+
+
 @needs_ref
 def test_flow_smoothing_bit_exact_single_warp(ref, mine):
     """A 16x2 image is one warp of the reference's kernel: lock-step execution = all reads before all writes, so its in-place
