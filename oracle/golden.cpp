@@ -54,6 +54,7 @@ struct golden_ctx {
     int n_levels, num_iter;
     int num_guess = 6, search_range = 30, radius_min = 1, seg_len = 10;  // defs.h:36-38, bao_pmflow_kernel.cu:979
     int stride = 2;  // sample stride of the patch loops (bao_pmflow_kernel.cu:269,272)
+    int pf_cost = 0; // 1: the forward PatchMatch scores with the plane-fitting cost (baoCudaPatchMatch_PlaneFitting, bao_pmflow_kernel.cu:1897-1963)
     std::vector<Level> lv;
     std::vector<S2> nnf[2], rng_init, rng_search;
     std::vector<float> cost[2];
@@ -311,6 +312,11 @@ float patch_cost_pf(const golden_ctx* c, const Level& L, int x1, int y1, int x2,
     return best;
 }
 
+// cost of a PatchMatch candidate: the plain patch distance, or -- forward direction only -- the plane-fitting one
+inline float pm_cost(const golden_ctx* c, const Level& L, int A, int B, int x1, int y1, int x2, int y2) {
+    return (c->pf_cost && A == 0) ? patch_cost_pf(c, L, x1, y1, x2, y2) : patch_cost(c, L, A, B, x1, y1, x2, y2);
+}
+
 // ------------------------------------------------------------------------------------------------ PatchMatch
 // baoCudaPatchMatch (:1760-1826) for one direction.  Segment passes run in lock-step (step t of every segment before
 // step t+1), the order the reference gets from warp-synchronous execution (DESIGN.md "racy stages").
@@ -347,7 +353,7 @@ void pm_propagate(golden_ctx* c, int dir, int pass) {
                 if (pass == 2) p.x = (int16_t)(p.x - 1 > 0 ? p.x - 1 : 0);              // :1095
                 if (pass == 3) p.y = (int16_t)(p.y - 1 > 0 ? p.y - 1 : 0);              // :1155
                 const size_t id = idx(line, i);
-                const float cv = patch_cost(c, L, A, B, row ? i : line, row ? line : i, p.x, p.y);
+                const float cv = pm_cost(c, L, A, B, row ? i : line, row ? line : i, p.x, p.y);
                 if (cv < cost[id]) { nnf[id] = p; cost[id] = cv; } else { p = nnf[id]; }
             }
 }
@@ -370,7 +376,7 @@ void pm_search(golden_ctx* c, int dir, int it) {  // d_update_random_guess (:151
                 const int16_t ymin = (int16_t)(entry.y - mag > 0 ? entry.y - mag : 0), ymax = (int16_t)(entry.y + mag + 1 < L.h + 1 ? entry.y + mag + 1 : L.h + 1);
                 const int16_t gx = (int16_t)(xmin + r1 % (uint32_t)(xmax - xmin)), gy = (int16_t)(ymin + r2 % (uint32_t)(ymax - ymin));
                 if (mag / 2 >= c->radius_min) mag /= 2;
-                const float cv = patch_cost(c, L, A, B, x, y, gx, gy);
+                const float cv = pm_cost(c, L, A, B, x, y, gx, gy);
                 if (cv < best_cost) { best = S2{gx, gy}; best_cost = cv; }
             }
             c->nnf[dir][id] = best;
@@ -390,7 +396,7 @@ void patchmatch(golden_ctx* c, int n_steps) {
         for (int y = 0; y < L.h; y++)  // baoComputeCostField (:636-645)
             for (int x = 0; x < L.w; x++) {
                 const S2 t = c->nnf[dir][(size_t)y * L.w + x];
-                c->cost[dir][(size_t)y * L.w + x] = patch_cost(c, L, dir, dir ^ 1, x, y, t.x, t.y);
+                c->cost[dir][(size_t)y * L.w + x] = pm_cost(c, L, dir, dir ^ 1, x, y, t.x, t.y);
             }
         for (int it = 0; it < c->num_iter; it++) {
             bool stop = false;
@@ -620,6 +626,7 @@ golden_ctx* golden_create(int h, int w, int levels, int num_iter) {
 }
 void golden_destroy(golden_ctx* c) { delete c; }
 void golden_set_stride(golden_ctx* c, int stride) { c->stride = stride; }
+void golden_set_pf_cost(golden_ctx* c, int on) { c->pf_cost = on; }
 int golden_num_levels(const golden_ctx* c) { return c->n_levels; }
 void golden_level_dims(const golden_ctx* c, int level, int* h, int* w) { *h = c->lv[level].h; *w = c->lv[level].w; }
 

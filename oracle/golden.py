@@ -22,6 +22,7 @@ def lib():
         l.golden_create.restype = P; l.golden_create.argtypes = [I, I, I, I]
         l.golden_destroy.argtypes = [P]
         l.golden_set_stride.argtypes = [P, I]
+        l.golden_set_pf_cost.argtypes = [P, I]
         l.golden_num_levels.argtypes = [P]
         l.golden_level_dims.argtypes = [P, I, C.POINTER(I), C.POINTER(I)]
         l.golden_prepare.argtypes = [P, P, P]
@@ -143,8 +144,11 @@ class Golden:
         a = np.ascontiguousarray(img1, np.uint8); b = np.ascontiguousarray(img2, np.uint8)
         self.l.golden_prepare(self.ctx, a.ctypes.data, b.ctypes.data)
 
-    def patchmatch(self, n_steps=-1):
+    def patchmatch(self, n_steps=-1, plane_fitting=False):
+        """plane_fitting: the forward direction is scored with the four-model plane-fitting cost (baoCudaPatchMatch_PlaneFitting)."""
+        self.l.golden_set_pf_cost(self.ctx, 1 if plane_fitting else 0)
         self.l.golden_patchmatch(self.ctx, n_steps)
+        self.l.golden_set_pf_cost(self.ctx, 0)
 
     def consistency(self):
         self.l.golden_consistency(self.ctx)

@@ -216,6 +216,16 @@ def test_oracle_uncalled_stage_functions_against_reference_fixture(golden, path)
     assert np.array_equal((up == -7.0).all(-1), (z["up_out"] == -7.0).all(-1))                  # the same pixels are left untouched
     du = np.abs(up - z["up_out"])
     assert du.mean() <= 1e-4 and du.max() <= 1e-2, (du.mean(), du.max())                        # px
+    if "pf_nnf" in z:   # baoCudaPatchMatch_PlaneFitting: the whole forward PatchMatch with the four-model cost, coarsest level
+        h, w = int(z["h"]), int(z["w"])
+        a, b, _, _ = synth.make_pair(h, w, int(z["pair_idx"]), scale_to=float(z["scale_to"]))
+        g = golden.Golden(h, w)
+        g.prepare(a, b)
+        g.patchmatch(plane_fitting=True)
+        same = (g.plane("nnf_fwd") == z["pf_nnf"]).all(-1)
+        assert same.mean() >= 0.99, same.mean()                     # exp2f vs MUFU.EX2 may flip a near-tie, which then propagates
+        cg = g.plane("cost_fwd")
+        assert np.abs(cg[same] - z["pf_cost"][same]).max() <= 1e-5
 
 
 def test_oracle_stage_injection_is_deterministic(golden):

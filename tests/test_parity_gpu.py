@@ -433,6 +433,19 @@ def test_uncalled_stage_functions_against_committed_reference_fixture(mine, path
     o = torch.full((h1, w1, 2), -7.0, dtype=torch.float32, device="cuda"); d = dev(z["up_small"])
     mine.baoCudaFlowBilteralUpsampling(P(o), P(ia), w1, h1, pitch, P(d), w2, h2, 2.0); torch.cuda.synchronize()
     assert same_bits(o.cpu().numpy(), z["up_out"])
+    if "pf_nnf" in z:   # plane-fitting PatchMatch on the coarsest-level planes this library prepares from the same seeded pair
+        h, w = int(z["h"]), int(z["w"])
+        a, b, _, _ = synth.make_pair(h, w, int(z["pair_idx"]), scale_to=float(z["scale_to"]))
+        ctx = E.EppmContext(h, w, 1)
+        ctx.stage_prepare(dev(a[None]), dev(b[None]), 1)
+        hc, wc = ctx.level_dims(2)
+        planes = [refharness.pitched(ctx.read_plane(k, 2)) for k in (E.PLANE_RGBA1, E.PLANE_RGBA2, E.PLANE_CENSUS1, E.PLANE_CENSUS2)]
+        mine.baoCudaPatchMatch_PlaneFitting.argtypes = [V] * 6 + [I, I, S, S, S, S]
+        pn = torch.zeros((hc, wc, 2), dtype=torch.int16, device="cuda"); pc = torch.zeros((hc, wc), dtype=torch.float32, device="cuda")
+        mine.baoCudaPatchMatch_PlaneFitting(P(pn), P(pc), P(planes[0][0]), P(planes[1][0]), P(planes[2][0]), P(planes[3][0]), wc, hc, planes[0][1],
+                                            wc * 4, wc * 4, planes[2][1]); torch.cuda.synchronize()
+        assert np.array_equal(pn.cpu().numpy(), z["pf_nnf"]) and same_bits(pc.cpu().numpy(), z["pf_cost"])
+        ctx.close()
 
 
 @needs_ref

@@ -27,6 +27,7 @@ L.baoCudaFlowCutoff.argtypes = [V, I, I, S, F]
 L.baoEliminateStillRegionFlow.argtypes = [V, V, V, I, I, S]
 L.baoCudaImageSmoothing.argtypes = [V, V, I, I, S]
 L.baoCudaFlowBilteralUpsampling.argtypes = [V, V, I, I, S, V, I, I, F]
+L.baoCudaPatchMatch_PlaneFitting.argtypes = [V] * 6 + [I, I, S, S, S, S]
 dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 P = lambda t: t.data_ptr()
 
@@ -81,6 +82,13 @@ for name, h, w, idx, scale in [("s128x96", 96, 128, 7, 0.12)]:
     o = torch.full((h1, w1, 2), -7.0, dtype=torch.float32, device="cuda"); d = dev(small)
     L.baoCudaFlowBilteralUpsampling(P(o), P(ia[0]), w1, h1, ia[1], P(d), w2, h2, 2.0); torch.cuda.synchronize()
     out["up_out"] = o.cpu().numpy()
+    # the whole PatchMatch scored with the plane-fitting cost, forward direction, coarsest level (the oracle regenerates the planes
+    # from the seeded pair: they are pinned bit-exact by ref_*.npz)
+    out.update(pair_idx=idx, scale_to=scale)
+    j1, j2, k1, k2 = pitched(rg[0][2]), pitched(rg[1][2]), pitched(ce[0][2]), pitched(ce[1][2])
+    pn = torch.zeros((h2, w2, 2), dtype=torch.int16, device="cuda"); pc = torch.zeros((h2, w2), dtype=torch.float32, device="cuda")
+    L.baoCudaPatchMatch_PlaneFitting(P(pn), P(pc), P(j1[0]), P(j2[0]), P(k1[0]), P(k2[0]), w2, h2, j1[1], w2 * 4, w2 * 4, k1[1]); torch.cuda.synchronize()
+    out.update(pf_nnf=pn.cpu().numpy(), pf_cost=pc.cpu().numpy())
     np.savez_compressed(os.path.join(OUT, f"refstage_{name}.npz"), **out)
     print(name, "saved", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
     ref.destroy(rc)
