@@ -397,9 +397,8 @@ __global__ void k_flow_to_color(uchar4* __restrict__ rgb, const float2* __restri
 }  // namespace
 
 void bao_cuda_convert_flow_to_colorshow(uchar4* rgbflow, float2* flow_vec, int h, int w, float max_disp_x, float max_disp_y) {
-    static bool wheel_ready = false;
     cudaStreamSynchronize(0);
-    if (!wheel_ready) {
+    {   // 165 bytes of __constant__ per call: constant memory is per device, a process may use several
         unsigned char wh[55][3];
         const int RY = 15, YG = 6, GC = 4, CB = 11, BM = 13, MR = 6;     // :760-773
         int k = 0;
@@ -410,7 +409,6 @@ void bao_cuda_convert_flow_to_colorshow(uchar4* rgbflow, float2* flow_vec, int h
         for (int i = 0; i < BM; i++, k++) { wh[k][0] = 255 * i / BM; wh[k][1] = 0; wh[k][2] = 255; }
         for (int i = 0; i < MR; i++, k++) { wh[k][0] = 255; wh[k][1] = 0; wh[k][2] = 255 - 255 * i / MR; }
         cudaMemcpyToSymbol(c_wheel, wh, sizeof(wh));
-        wheel_ready = true;
     }
     const float max_rad = sqrt(max_disp_x * max_disp_x + max_disp_y * max_disp_y);   // :841
     k_flow_to_color<<<dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8)>>>(rgbflow, flow_vec, h, w, max_rad);
