@@ -7,6 +7,7 @@
 
 #include <map>
 #include <mutex>
+#include <tuple>
 #include <utility>
 
 #include "../../include/eppm_legacy_abi.h"
@@ -17,25 +18,27 @@ using namespace eppm;
 namespace {
 
 std::mutex g_mu;
-std::map<std::pair<int, int>, eppm_context*> g_single;   // single-level contexts keyed by (h, w)
-std::map<std::pair<int, int>, eppm_context*> g_pyramid;  // full-pyramid contexts keyed by (h, w) of level 0
+typedef std::map<std::tuple<int, int, int>, eppm_context*> CtxCache;   // keyed by (device, h, w)
+CtxCache g_single;    // single-level contexts
+CtxCache g_pyramid;   // full-pyramid contexts, (h, w) of level 0
 
 void complain(const char* where) { fprintf(stderr, "EPPM(b200) %s: %s\n", where, eppm_last_error()); }
 
-eppm_context* get_ctx(std::map<std::pair<int, int>, eppm_context*>& cache, int h, int w, int levels) {
+eppm_context* get_ctx(CtxCache& cache, int h, int w, int levels) {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = cache.find({h, w});
+    int dev = 0;
+    cudaGetDevice(&dev);   // the caller's current device, like the reference's implicit context
+    const std::tuple<int, int, int> key(dev, h, w);
+    auto it = cache.find(key);
     if (it != cache.end() && it->second->n_levels == levels) return it->second;
     if (it != cache.end()) { eppm_destroy(it->second); cache.erase(it); }
     eppm_params p;
     eppm_default_params(&p);
     p.pyr_levels = levels;
     eppm_context* c = nullptr;
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (eppm_create(&c, dev, h, w, 1, &p) != EPPM_OK) { complain("context"); return nullptr; }
     c->n_cur = 1;
-    cache[{h, w}] = c;
+    cache[key] = c;
     return c;
 }
 
