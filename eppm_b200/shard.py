@@ -14,6 +14,18 @@ def shard_range(n_total, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def stream_shard(n_frames, rank, world):
+    """Video stream (BASELINE config 5): frames [f_lo, f_hi) for `rank` such that its consecutive pairs (t, t+1) are the contiguous
+    pair shard [p_lo, p_hi) of the n_frames - 1 pairs -- neighbouring ranks share exactly one frame.
+    Returns (f_lo, f_hi, p_lo, p_hi); a rank without pairs gets an empty range."""
+    if n_frames < 1:
+        raise ValueError("a stream needs at least one frame")
+    p_lo, p_hi = shard_range(n_frames - 1, rank, world)
+    if p_hi == p_lo:
+        return p_lo, p_lo, p_lo, p_hi
+    return p_lo, p_hi + 1, p_lo, p_hi
+
+
 def max_over_ranks(value, world, device=None):
     """MAX all-reduce of a python float over the default process group (gloo on CPU, nccl on GPU); identity when world == 1."""
     if world == 1:

@@ -318,6 +318,20 @@ def test_shard_ranges():
         assert max(sizes) - min(sizes) <= 1
 
 
+def test_stream_shards_overlap_by_one_frame():
+    """Config 5 across GPUs: contiguous frame ranges, one shared frame between neighbours, every pair computed exactly once."""
+    for n_frames, world in ((300, 1), (300, 8), (17, 4), (3, 8), (1, 2)):
+        spans = [shard.stream_shard(n_frames, r, world) for r in range(world)]
+        pairs = []
+        for f_lo, f_hi, p_lo, p_hi in spans:
+            assert f_hi - f_lo == (p_hi - p_lo + 1 if p_hi > p_lo else 0)
+            pairs += list(range(p_lo, p_hi))
+            assert all(f_lo <= t and t + 1 < f_hi for t in range(p_lo, p_hi))       # both frames of every pair are local
+        assert pairs == list(range(n_frames - 1))
+        busy = [s for s in spans if s[3] > s[2]]
+        assert all(busy[i][1] - 1 == busy[i + 1][0] for i in range(len(busy) - 1))    # exactly one frame shared
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
