@@ -175,7 +175,8 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         c->occl_count = A.take<int>(64);
         {
             const int sl = p.prop_seg_length;
-            const size_t thr_row = (size_t)gc.h * ((gc.w + sl - 1) / sl), thr_col = (size_t)gc.w * ((gc.h + sl - 1) / sl);
+            // chains of a pass: scan lines (rounded up to whole warps) x segments per line
+            const size_t thr_row = (size_t)((gc.h + 31) & ~31) * ((gc.w + sl - 1) / sl), thr_col = (size_t)((gc.w + 31) & ~31) * ((gc.h + sl - 1) / sl);
             const size_t thr = 2 * B * (thr_row > thr_col ? thr_row : thr_col);
             c->prop_prev = A.take<short2>(thr);
             c->prop_queue = A.take<int4>(thr);

@@ -130,12 +130,14 @@ struct PixPk {  // a packed-plane pixel viewed as two FP32 pairs: (r,g) and (b, 
 };
 __device__ __forceinline__ PixPk pack_pix(const float4& p) { return PixPk{pk2(p.x, p.y), pk2(p.z, p.w)}; }
 
-// max(|a.x-b.x|, |a.y-b.y|, |a.z-b.z|) with the three subtractions issued as two packed ones (the .w half is ignored)
+// max(|a.x-b.x|, |a.y-b.y|, |a.z-b.z|): x and y as one packed subtraction, z as a scalar one (a packed instruction holds the FMA
+// pipe for two cycles, and the .w half of a second packed subtraction would be thrown away)
 __device__ __forceinline__ float max3abs_diff(const PixPk& a, const PixPk& b) {
-    float dx, dy, dz, dw;
+    float dx, dy, az, aw, bz, bw;
     upk2(sub2(a.xy, b.xy), dx, dy);
-    upk2(sub2(a.zw, b.zw), dz, dw);
-    return fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
+    upk2(a.zw, az, aw);
+    upk2(b.zw, bz, bw);
+    return fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(__fsub_rn(az, bz)));
 }
 
 // One sample of the bilateral-weighted AD+census patch cost (bao_pmflow_kernel.cu:274-296):
@@ -174,6 +176,65 @@ __device__ __forceinline__ float ex2_tiny(float t) {
     const float r = ex2_mufu(__fmul_rn(t, 0.5f));
     return __fmul_rn(r, r);
 }
+
+// TWO samples (a, b) side by side: everything behind the two max|.| reductions of a sample -- the squares, both constant divisions,
+// the log2e multiplies, 1 - e, + census -- runs in the halves of packed FP32x2 instructions, one issue slot for the two samples (the
+// scalar form above pairs the AD chain with the weight chain of ONE sample and leaves squares, 1 - e, + census, e*gg and the
+// accumulation scalar: 29.5 issued instructions per sample in the refine kernel against ~23 here).  Every half is rounded like the
+// scalar instruction, so each sample's (cost, t2) is the bit pattern sample_eval returns.
+//   p1a/p1b: image-1 pixel of sample a / b (the same pixel when a and b are two models of one candidate), p2a/p2b: image-2 pixels,
+//   c2a/c2b: candidate centres in image 2, d1: (d1_a, d1_b) range distances on the image-1 side.
+// Returns ct = (cost_a, cost_b) and t2 = (log2e-scaled exponent of the range weight of a, of b).
+template <class LutRef>
+__device__ __forceinline__ void sample_eval2(const float4& p1a, const PixPk& p1ka, const float4& p1b, const PixPk& p1kb, const float4& p2a, const float4& p2b,
+                                             const PixPk& c2a, const PixPk& c2b, f32x2 d1, LutRef lut_base, f32x2& ct, f32x2& t2) {
+    const PixPk p2ka = pack_pix(p2a), p2kb = pack_pix(p2b);
+    const f32x2 c = pk2(max3abs_diff(p1ka, p2ka), max3abs_diff(p1kb, p2kb));
+    const f32x2 d2 = pk2(max3abs_diff(c2a, p2ka), max3abs_diff(c2b, p2kb));
+    const f32x2 xc = mul2(c, c);                          // c^2                          (bao_pmflow_kernel.cu:282)
+    const f32x2 xw = fma2(d1, d1, mul2(d2, d2));          // fma(d1, d1, d2*d2)           (:288 as contracted)
+    const f32x2 R = pk2(-99.99999237060546875f, -99.99999237060546875f), D = pk2(0.010000000707805156708f, 0.010000000707805156708f);
+    const f32x2 Z = pk2(0.f, 0.f), L2E = pk2(1.4426950216293334961f, 1.4426950216293334961f);
+    const f32x2 qc0 = fma2(xc, R, Z), qw0 = fma2(xw, R, Z);                        // div_neg_0p01 on both pairs
+    const f32x2 qc = fma2(R, fma2(qc0, D, xc), qc0), qw = fma2(R, fma2(qw0, D, xw), qw0);
+    float t1a, t1b;
+    upk2(mul2(qc, L2E), t1a, t1b);
+    t2 = mul2(qw, L2E);
+    const f32x2 e = pk2(ex2_mufu(t1a), ex2_mufu(t1b));
+    const f32x2 lut = pk2(census_lut_ref(lut_base, p1a, p2a), census_lut_ref(lut_base, p1b, p2b));
+    ct = add2(sub2(pk2(1.0f, 1.0f), e), lut);             // (1 - e) + census, two roundings like the scalar form
+}
+// range weights of FOUR samples (two pairs): w = __expf-equivalent(t2) * gg per value.  The `t2 < -126` fix-up of __expf (~1 % of the
+// samples) is ONE test and one rarely taken block for the four; the values are formed as scalars so that the rare path patches them
+// in place (patching a packed value costs two register copies on the common path).
+__device__ __forceinline__ void sample_weight4(f32x2 t2a, f32x2 t2b, float g0, float g1, float g2, float g3, f32x2& wa, f32x2& wb) {
+    float t[4], w[4];
+    const float g[4] = {g0, g1, g2, g3};
+    upk2(t2a, t[0], t[1]);
+    upk2(t2b, t[2], t[3]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) w[k] = __fmul_rn(ex2_mufu(t[k]), g[k]);
+    if (fminf(fminf(t[0], t[1]), fminf(t[2], t[3])) < -126.0f) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (t[k] < -126.0f) w[k] = __fmul_rn(ex2_tiny(t[k]), g[k]);
+    }
+    wa = pk2(w[0], w[1]);
+    wb = pk2(w[2], w[3]);
+}
+__device__ __forceinline__ void sample_weight4(f32x2 t2a, f32x2 t2b, float gg, f32x2& wa, f32x2& wb) { sample_weight4(t2a, t2b, gg, gg, gg, gg, wa, wb); }
+// the same for one pair
+__device__ __forceinline__ f32x2 sample_weight2(f32x2 t2, float g0, float g1) {
+    float ta, tb;
+    upk2(t2, ta, tb);
+    float wa = __fmul_rn(ex2_mufu(ta), g0), wb = __fmul_rn(ex2_mufu(tb), g1);
+    if (fminf(ta, tb) < -126.0f) {
+        if (ta < -126.0f) wa = __fmul_rn(ex2_tiny(ta), g0);
+        if (tb < -126.0f) wb = __fmul_rn(ex2_tiny(tb), g1);
+    }
+    return pk2(wa, wb);
+}
+__device__ __forceinline__ float min2(f32x2 v) { float a, b; upk2(v, a, b); return fminf(a, b); }
 
 // sample_eval + the per-sample fix-up + accumulation: the plain form of one sample
 __device__ __forceinline__ void sample_term(const float4& p1, const PixPk& p1k, const float4& p2, const PixPk& c2k, float d1, float gg,

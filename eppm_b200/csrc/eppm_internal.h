@@ -25,6 +25,9 @@ enum {
     EPPM_VAR_SEARCH_TEX3 = 512,    // random search: the three wide-window guesses gather their target side through the texture unit
     EPPM_VAR_SEARCH_NOTEX = 1024,  //   ... none (default: the two widest)
     EPPM_VAR_SEARCH_SPLIT3 = 65536,  //   ... three passes of two (64 registers, 8 CTAs)
+    EPPM_VAR_REFINE_SCALAR = 2048,     // table refine with the four models of a candidate as scalar chains (round-1 default) instead of packed pairs
+    EPPM_VAR_REFINE_PK_BRANCH = 4096,  // packed-pair refine that branches around candidate rows outside the image instead of scoring them at a clamped centre
+    EPPM_VAR_PROP_QUEUE = 8192,        // propagation: the global work queue, two launches per lock-step (round-1 default), instead of barrier-free segment chains
     EPPM_VAR_PROP_NOSKIP = 8,      // propagation: evaluate candidates that equal the current target (the reference does)
 };
 

@@ -395,6 +395,217 @@ static void launch_propagate_queue(eppm_context* c, const PmArgs& a, int n, int 
     EPPM_LAUNCH_COUNT(2 * sl);
 }
 
+// ---- propagation as independent segment chains with warp-shared evaluations (default) ----
+// What the lock-step really orders.  A segment touches only its own pixels; the cost of a candidate reads the (immutable) images
+// and the pixel's own cost.  Across segments of a scan line exactly three things are ordered by the reference's warp-synchronous
+// execution (and by the barrier / launch boundary per step of the kernels above):
+//   (1) every segment reads the pixel in front of it -- the last pixel of the neighbouring segment -- before anything is written;
+//   (2) forward passes: segments 0 and 1 both update pixel seg_len (:1055-1058); segment 1 does it in its FIRST step, segment 0 in
+//       its LAST one, which therefore sees segment 1's result;
+//   (3) nothing else: reverse segments are disjoint.
+// So a pass is: k_prop_snapshot (the start targets of all chains, ordering (1) by a launch boundary), ONE kernel in which every
+// chain runs its steps back to back with no barrier at all, and for forward passes a tail launch with the last step of segment 0
+// (ordering (2)).  3 launches per pass instead of 20, and no grid-wide wait per step.
+//
+// Inside the chain kernel a warp owns 32 chains (adjacent scan lines, same segment).  Per step the lanes shift their targets and
+// decide (a candidate equal to the pixel's current target is never better, see k_pm_propagate); the evaluations that are needed are
+// then done BY THE WHOLE WARP, one after the other: lane l scores samples l, l+32, l+64, l+96 of the patch (both sides of every
+// sample are short row segments of a 19x19 window: coalesced, and shared through L1 with the neighbouring lines' evaluations; the
+// thread-per-evaluation kernels gather 32 unrelated windows per load, L1 hit rate 12 %), writes (cost, weight) per sample to shared
+// memory, and the owning lane adds the samples up IN SAMPLE ORDER -- the reference's accumulation order, hence its bits.  The four
+// rounds of a lane are two packed pairs (sample_eval2).
+struct ChainGeom {
+    int n_line, line0, nlp;   // scan lines of the band, the first one, n_line rounded up to a multiple of 32 (a warp never straddles segments)
+    int n_seg, seg0;          // segments per line handled by this context (band) and the first one
+    int seg_count;            // segments enumerated by this launch: n_seg (main) or 1 (tail: segment 0 only)
+    int len;                  // pixels along a line
+    int t0, t1;               // steps [t0, t1] of every chain run in this launch
+    int defer;                // 1: segment 0 stops one step early (its last step runs in the tail launch)
+    int n_z;                  // pairs x directions
+};
+
+template <int DIR>
+__device__ __forceinline__ void chain_span(int seg, int seg_len, int len, int& start, int& steps) {
+    if (DIR < 2) {
+        start = seg == 0 ? 0 : seg * seg_len - 1;   // :1055-1058
+        steps = min(len - 1, start + seg_len) - start;
+    } else {
+        start = (seg + 1) * seg_len;                // :1085-1088
+        if (start >= len) start = len - 1;
+        steps = start - seg * seg_len;
+    }
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(256) k_prop_snapshot(PmArgs a, ChainGeom g, int seg_len, short2* __restrict__ st_prev) {
+    constexpr bool ROW = (DIR == 0 || DIR == 2);
+    const int cid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cid >= g.n_z * g.n_seg * g.nlp) return;
+    const int ll = cid % g.nlp, r = cid / g.nlp;
+    const int seg = g.seg0 + r % g.n_seg, z = r / g.n_seg;
+    if (ll >= g.n_line) return;
+    const int line = g.line0 + ll;
+    int start, steps;
+    chain_span<DIR>(seg, seg_len, g.len, start, steps);
+    if (steps <= 0) return;
+    const int dir = a.n_dirs == 2 ? (z & 1) : 0, b = a.n_dirs == 2 ? (z >> 1) : z;
+    const short2* nnf = (dir ? a.nnf[1] : a.nnf[0]) + (size_t)b * a.w * a.h;
+    st_prev[cid] = nnf[ROW ? line * a.w + start : start * a.w + line];
+}
+
+template <int STRIDE>
+struct ChainCfg {
+    static constexpr int NJ = (2 * PATCH_R) / STRIDE + 1;
+    static constexpr int NS = NJ * NJ;                 // samples per evaluation
+    static constexpr int NSP = NS | 1;                 // odd pitch of a slot in shared memory: the owners' 8-byte reads fall in distinct banks
+    static constexpr int R = (NS + 31) / 32;           // rounds of 32 samples
+    static constexpr int RP = (R + 1) / 2;             // rounds in packed pairs
+    static constexpr int SLOTS = STRIDE == 1 ? 2 : 8;  // evaluations buffered per warp before their owners add them up
+    static constexpr int WARPS = 4;
+};
+
+template <int DIR, int STRIDE>
+__global__ void __launch_bounds__(ChainCfg<STRIDE>::WARPS * 32) k_prop_chain(PmArgs a, ChainGeom g, int seg_len, short2* __restrict__ st_prev,
+                                                                            const __grid_constant__ CostLut lut) {
+    typedef ChainCfg<STRIDE> C;
+    constexpr bool ROW = (DIR == 0 || DIR == 2), FWD = (DIR < 2);
+    __shared__ float s_census[CENSUS_LUT_N];
+    __shared__ float2 s_val[C::WARPS][C::SLOTS][C::NSP];
+    load_census_lut(s_census, lut);
+    const unsigned lut_base = census_lut_base(s_census);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wi = blockIdx.x * C::WARPS + warp;
+    const int groups = g.nlp >> 5;
+    if (wi >= g.n_z * g.seg_count * groups) return;   // whole warps only; nothing below synchronises across warps
+    const int llg = wi % groups, r = wi / groups;
+    const int sidx = r % g.seg_count, z = r / g.seg_count;
+    const int seg = g.seg0 + sidx;
+    const int ll = llg * 32 + lane, line = g.line0 + ll;
+    const int cid = (z * g.n_seg + sidx) * g.nlp + ll;
+    const float4 *A, *B; short2* nnf; float* cost;
+    pm_select<false>(a, z, A, B, nnf, cost);
+    int start, steps;
+    chain_span<DIR>(seg, seg_len, g.len, start, steps);
+    if (ll >= g.n_line) steps = 0;
+    int t_hi = min(steps, g.t1);
+    if (g.defer && seg == 0) t_hi = min(t_hi, seg_len - 1);
+    short2 prev = make_short2(0, 0);
+    if (steps > 0) prev = st_prev[cid];
+    // per-lane sample sites of the rounds: sample s = lane + 32 r at (i, j) = (-9 + STRIDE * (s / NJ), -9 + STRIDE * (s % NJ))
+    int soff[2 * C::RP];
+    float sgg[2 * C::RP];
+#pragma unroll
+    for (int q = 0; q < 2 * C::RP; q++) {
+        int s = lane + 32 * q;
+        if (s >= C::NS) s = C::NS - 1;   // lanes past the last sample score a valid site and do not store
+        const int i = -PATCH_R + STRIDE * (s / C::NJ), j = -PATCH_R + STRIDE * (s % C::NJ);
+        soff[q] = i * a.pw + j;
+        sgg[q] = lut.gg[i < 0 ? -i : i][j < 0 ? -j : j];
+    }
+    const int t_max = __reduce_max_sync(0xffffffffu, t_hi);
+    for (int t = g.t0; t <= t_max; t++) {
+        bool need = false;
+        int id = 0, pos = 0;
+        short2 cur = make_short2(0, 0);
+        if (t <= t_hi) {
+            const int i = FWD ? start + t : start - t;
+            const int x1 = ROW ? i : line, y1 = ROW ? line : i;
+            id = y1 * a.w + x1;
+            pos = x1 | (y1 << 16);
+            if (DIR == 0) prev.x = min(prev.x + 1, a.w - 1);   // :1065/:1095/:1125/:1155
+            if (DIR == 1) prev.y = min(prev.y + 1, a.h - 1);
+            if (DIR == 2) prev.x = max(prev.x - 1, 0);
+            if (DIR == 3) prev.y = max(prev.y - 1, 0);
+            cur = nnf[id];
+            // a candidate equal to the current target would be scored by the evaluation that produced cost[id]: never '<'
+            need = !(prev.x == cur.x && prev.y == cur.y);
+        }
+        const int cand = (int)(unsigned short)prev.x | ((int)prev.y << 16);
+        unsigned todo = __ballot_sync(0xffffffffu, need);
+        while (todo) {
+            int my_slot = -1;
+#pragma unroll 1
+            for (int k = 0; k < C::SLOTS && todo; k++) {
+                const int e = __ffs(todo) - 1;
+                todo &= todo - 1;
+                if (lane == e) my_slot = k;
+                const int epos = __shfl_sync(0xffffffffu, pos, e), ecand = __shfl_sync(0xffffffffu, cand, e);
+                const unsigned oa = (unsigned)((epos & 0xffff) + PAD) + (unsigned)((epos >> 16) + PAD) * (unsigned)a.pw;
+                const unsigned ob = (unsigned)((short)(ecand & 0xffff) + PAD) + (unsigned)((ecand >> 16) + PAD) * (unsigned)a.pw;
+                const PixPk c1k = pack_pix(ldpix(A + oa)), c2k = pack_pix(ldpix(B + ob));
+                float2* slot = s_val[warp][k];
+#pragma unroll
+                for (int q = 0; q < C::RP; q++) {
+                    const float4 p1a = ldpix(A + (oa + (unsigned)soff[2 * q])), p1b = ldpix(A + (oa + (unsigned)soff[2 * q + 1]));
+                    const float4 p2a = ldpix(B + (ob + (unsigned)soff[2 * q])), p2b = ldpix(B + (ob + (unsigned)soff[2 * q + 1]));
+                    const PixPk p1ka = pack_pix(p1a), p1kb = pack_pix(p1b);
+                    f32x2 ct, t2;
+                    sample_eval2(p1a, p1ka, p1b, p1kb, p2a, p2b, c2k, c2k, pk2(max3abs_diff(c1k, p1ka), max3abs_diff(c1k, p1kb)), lut_base, ct, t2);
+                    float ca, cb, wa, wb;
+                    upk2(ct, ca, cb);
+                    upk2(sample_weight2(t2, sgg[2 * q], sgg[2 * q + 1]), wa, wb);
+                    if (lane + 64 * q < C::NS) slot[lane + 64 * q] = make_float2(ca, wa);
+                    if (lane + 64 * q + 32 < C::NS) slot[lane + 64 * q + 32] = make_float2(cb, wb);
+                }
+            }
+            __syncwarp();
+            if (my_slot >= 0) {
+                // the owner adds the samples of its evaluation in the reference's order (i outer, j inner; :274-296) and applies the strict '<'
+                const float2* slot = s_val[warp][my_slot];
+                float cs = 0.f, ws = 0.f;
+#pragma unroll 4
+                for (int s = 0; s < C::NS; s++) {
+                    const float2 v = slot[s];
+                    cs = __fmaf_rn(v.x, v.y, cs);
+                    ws = __fadd_rn(ws, v.y);
+                }
+                const float cv = __fdiv_rn(cs, ws);
+                if (cv < cost[id]) {
+                    nnf[id] = prev;
+                    cost[id] = cv;
+                } else {
+                    prev = cur;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (g.defer && seg == 0 && steps > 0) st_prev[cid] = prev;   // handed to the tail launch
+}
+
+template <int DIR, int STRIDE>
+static void launch_propagate_chain(eppm_context* c, const PmArgs& a, int n) {
+    typedef ChainCfg<STRIDE> C;
+    const bool row = (DIR == 0 || DIR == 2), fwd = DIR < 2;
+    const int sl = c->prm.prop_seg_length;
+    ChainGeom g;
+    g.n_line = row ? a.y1 - a.y0 : a.w;
+    g.line0 = row ? a.y0 : 0;
+    g.nlp = (g.n_line + 31) & ~31;
+    g.n_seg = row ? (a.w + sl - 1) / sl : (a.y1 + sl - 1) / sl - a.y0 / sl;
+    g.seg0 = row ? 0 : a.y0 / sl;
+    g.len = row ? a.w : a.h;
+    g.n_z = a.n_dirs * n;
+    g.seg_count = g.n_seg;
+    g.t0 = 1; g.t1 = sl;
+    // segment 0's last step follows segment 1's first one (both update pixel seg_len): it runs in a second launch
+    g.defer = fwd && g.seg0 == 0 && (g.len + sl - 1) / sl >= 2;
+    const int chains = g.n_z * g.n_seg * g.nlp;
+    k_prop_snapshot<DIR><<<(chains + 255) / 256, 256, 0, c->stream>>>(a, g, sl, c->prop_prev);
+    const int warps = chains / 32;
+    k_prop_chain<DIR, STRIDE><<<(warps + C::WARPS - 1) / C::WARPS, C::WARPS * 32, 0, c->stream>>>(a, g, sl, c->prop_prev, c->cost_lut);
+    EPPM_LAUNCH_COUNT(2);
+    if (g.defer) {
+        ChainGeom gt = g;
+        gt.seg_count = 1;
+        gt.t0 = gt.t1 = sl;
+        gt.defer = 0;
+        const int twarps = g.n_z * (g.nlp / 32);
+        k_prop_chain<DIR, STRIDE><<<(twarps + C::WARPS - 1) / C::WARPS, C::WARPS * 32, 0, c->stream>>>(a, gt, sl, c->prop_prev, c->cost_lut);
+        EPPM_LAUNCH_COUNT(1);
+    }
+}
+
 // Random search (d_update_random_guess): num_guess candidates drawn in windows of radius 30,15,7,3,1,1 around the
 // ENTRY best target, evaluated in order with strict '<'.
 template <int STRIDE>
@@ -478,9 +689,11 @@ __global__ void __launch_bounds__(128, MINB) k_pm_search_joint(PmArgs a, const s
             ob[k] = (unsigned)(gx[k] + PAD) + (unsigned)(gy[k] + PAD) * (unsigned)a.pw;
             c2k[k] = pack_pix(ldpix(B + ob[k]));
         }
-        float cs[GS], ws[GS];
+        // the guesses of a group are scored in packed pairs (sample_eval2): guess 2h in the low halves, 2h+1 in the high halves
+        static_assert(GS % 2 == 0, "guesses are scored in pairs");
+        f32x2 cs[GS / 2], ws[GS / 2];
 #pragma unroll
-        for (int k = 0; k < GS; k++) cs[k] = ws[k] = 0.f;
+        for (int h = 0; h < GS / 2; h++) cs[h] = ws[h] = pk2(0.f, 0.f);
 #pragma unroll 1
         for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
             const int ai = i < 0 ? -i : i;
@@ -490,36 +703,45 @@ __global__ void __launch_bounds__(128, MINB) k_pm_search_joint(PmArgs a, const s
                 const unsigned off = irow + (unsigned)j;
                 const float4 p1 = ldpix(A + (oa + off));
                 const PixPk p1k = pack_pix(p1);
-                const float d1 = max3abs_diff(c1k, p1k);
+                const float d1s = max3abs_diff(c1k, p1k);
+                const f32x2 d1 = pk2(d1s, d1s);
                 const float gg = lut.gg[ai][j < 0 ? -j : j];
-                float ct[GS], t2[GS], w[GS];
-                float tmin = 0.f;
+                f32x2 ct[GS / 2], t2[GS / 2], w[GS / 2];
 #pragma unroll
-                for (int k = 0; k < GS; k++) {
-                    const float4 p2 = g * GS + k < NTEX ? texpix(texB, tb + ob[k] + off) : ldpix(B + (ob[k] + off));
-                    sample_eval(p1, p1k, p2, c2k[k], d1, lut_base, ct[k], t2[k]);
-                    w[k] = __fmul_rn(ex2_mufu(t2[k]), gg);
-                    tmin = fminf(tmin, t2[k]);
+                for (int h = 0; h < GS / 2; h++) {
+                    const int k0 = 2 * h, k1 = 2 * h + 1;
+                    const float4 p2a = g * GS + k0 < NTEX ? texpix(texB, tb + ob[k0] + off) : ldpix(B + (ob[k0] + off));
+                    const float4 p2b = g * GS + k1 < NTEX ? texpix(texB, tb + ob[k1] + off) : ldpix(B + (ob[k1] + off));
+                    sample_eval2(p1, p1k, p1, p1k, p2a, p2b, c2k[k0], c2k[k1], d1, lut_base, ct[h], t2[h]);
                 }
-                if (tmin < -126.0f) {   // rare: the __expf fix-up (see exp_ref), one test per GS samples
+                if (GS == 6) {   // one fix-up test per four + one per two samples
+                    sample_weight4(t2[0], t2[1], gg, w[0], w[1]);
+                    w[2] = sample_weight2(t2[2], gg, gg);
+                } else {
 #pragma unroll
-                    for (int k = 0; k < GS; k++)
-                        if (t2[k] < -126.0f) w[k] = __fmul_rn(ex2_tiny(t2[k]), gg);
+                    for (int h = 0; h < GS / 2; h++) w[h] = sample_weight2(t2[h], gg, gg);
                 }
 #pragma unroll
-                for (int k = 0; k < GS; k++) {
-                    cs[k] = __fmaf_rn(ct[k], w[k], cs[k]);
-                    ws[k] = __fadd_rn(ws[k], w[k]);
+                for (int h = 0; h < GS / 2; h++) {
+                    cs[h] = fma2(ct[h], w[h], cs[h]);
+                    ws[h] = add2(ws[h], w[h]);
                 }
             }
         }
         // guesses are compared in their order with strict '<' (:1577); groups are visited in that order too
 #pragma unroll
-        for (int k = 0; k < GS; k++) {
-            const float cv = __fdiv_rn(cs[k], ws[k]);
-            if (cv < best_cost) {
-                best = make_short2(gx[k], gy[k]);
-                best_cost = cv;
+        for (int h = 0; h < GS / 2; h++) {
+            float c0, c1, w0, w1;
+            upk2(cs[h], c0, c1);
+            upk2(ws[h], w0, w1);
+            const float cv0 = __fdiv_rn(c0, w0), cv1 = __fdiv_rn(c1, w1);
+            if (cv0 < best_cost) {
+                best = make_short2(gx[2 * h], gy[2 * h]);
+                best_cost = cv0;
+            }
+            if (cv1 < best_cost) {
+                best = make_short2(gx[2 * h + 1], gy[2 * h + 1]);
+                best_cost = cv1;
             }
         }
     }
@@ -763,6 +985,11 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
             if (run()) launch_propagate<1, STRIDE>(c, a, n);
             if (run()) launch_propagate<2, STRIDE>(c, a, n);
             if (run()) launch_propagate<3, STRIDE>(c, a, n);
+        } else if (!(c->variant & EPPM_VAR_PROP_QUEUE)) {
+            if (run()) launch_propagate_chain<0, STRIDE>(c, a, n);
+            if (run()) launch_propagate_chain<1, STRIDE>(c, a, n);
+            if (run()) launch_propagate_chain<2, STRIDE>(c, a, n);
+            if (run()) launch_propagate_chain<3, STRIDE>(c, a, n);
         } else {
             if (run()) launch_propagate_queue<0, STRIDE>(c, a, n, it * 4 + 0);
             if (run()) launch_propagate_queue<1, STRIDE>(c, a, n, it * 4 + 1);

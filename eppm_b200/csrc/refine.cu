@@ -61,6 +61,8 @@ struct RefineArgs {
     float2* flow;         // [B][h][w] out
     int upsample;         // 1: coarse is the next-coarser level (x2 upsample fused); 0: coarse is already at this level
     int y0;               // first row of the band this launch owns (grid.y = rows in the band)
+    int px_bytes;         // sizeof(float4) as a run-time value: the product off * px_bytes is then formed once per site and shared by the three
+                          // candidate rows (a literal 16 is strength-reduced per load into a shift, a high-part multiply and a 64-bit add)
 };
 
 // CTA = 3 warps x 32 pixels: warp m evaluates candidate column m of 32 consecutive pixels of one row (coalesced plane
@@ -201,6 +203,13 @@ __device__ __forceinline__ const float4* pix_at(const float4* base, int off) {
     return r;
 }
 
+// base + off pixels with the multiplier (16) taken from kernel parameter space, where ptxas cannot fold it (see RefineArgs::px_bytes)
+__device__ __forceinline__ const float4* pix_at_b(const float4* base, int off, int px_bytes) {
+    const float4* r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(off), "r"(px_bytes), "l"(base));
+    return r;
+}
+
 // NCT = candidate rows per thread.  3: CTA = 3 warps, warp m owns candidate column m (96 registers, 18 warps per SM).
 // 1: CTA = 9 warps, warp (m, n) owns ONE candidate and its four models (72 registers, 27 warps per SM): the image-1 side of a
 // sample is shared by 4 instead of 12 accumulator pairs (33.4 instead of 30.7 instructions per sample).  Measured equal (8.70 vs 8.74 ms
@@ -324,6 +333,147 @@ EPPM_PRAGMA(unroll RF_JUNROLL)
     for (int n = 0; n < NCT; n++) s_best[m * 3 + n0 + n][pl] = valid[n] ? cost[n] : __int_as_float(0x7f800000);
     __syncthreads();
     if (in && wq == 0) {
+        float2 out;
+        if (unknown) out = make_float2(0.f, 0.f);
+        else {
+            // arg-min in the reference's order: m outer, n inner, strict '<' against 999999 (:2024,:2031)
+            float bcost = 999999.f;
+            int bk = -1;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const float oc = s_best[k][pl];
+                if (oc < bcost) { bcost = oc; bk = k; }
+            }
+            short bx = cxc, by = cyc;   // :2020-2022 default = centre candidate
+            if (bk >= 0) { bx = (short)(cxc + (bk / 3 - 1)); by = (short)(cyc + (bk % 3 - 1)); }
+            out = make_float2((float)(bx - x), (float)(by - y));  // :2038-2039
+        }
+        a.flow[(size_t)b * a.w * a.h + (size_t)y * a.w + x] = out;
+    }
+}
+
+// ---- table-driven refine, models in packed pairs (default) ----
+// Same decomposition as k_c2f_refine_tab with NCT = 3 (warp m owns candidate column m, a thread its three candidate rows x four
+// models), but the four models of a candidate are evaluated as TWO PAIRS in the halves of packed FP32x2 instructions
+// (sample_eval2): squares, both constant divisions, log2e, 1 - e, + census, e * gg and the two accumulations cost one issue slot per
+// pair instead of one per model.  Accumulators are pairs too: cs[n][0] = (model 0, model 1), cs[n][1] = (model 2, model 3).  Each
+// (candidate, model) still adds its samples in the reference's order with per-half IEEE rounding: the same bits.
+// ALLROWS: candidate rows that are not valid (outside the image, :2029) are scored at a clamped centre and discarded instead of
+// being branched around -- only warps at the image border contain such rows, and the branch costs three issue slots per candidate
+// and sample everywhere else.
+#ifndef RF_PK_MINBLOCKS
+#define RF_PK_MINBLOCKS 7
+#endif
+#ifndef RF_PK_LUT
+#define RF_PK_LUT lut_base
+#endif
+#ifdef RF_PK_MAXNREG
+#define RF_PK_BOUNDS __maxnreg__(RF_PK_MAXNREG)
+#else
+#define RF_PK_BOUNDS __launch_bounds__(RF_PIX * 3, MINB)
+#endif
+template <int MINB, int STRIDE, bool ALLROWS>
+__global__ void RF_PK_BOUNDS
+    k_c2f_refine_pk(RefineArgs a, const __grid_constant__ CostLut lut, const __grid_constant__ AffineTab tab) {
+    __shared__ float s_best[9][RF_PIX];
+    __shared__ float s_census[CENSUS_LUT_N];
+    load_census_lut(s_census, lut);
+    const unsigned lut_base = census_lut_base(s_census);
+    const int m = threadIdx.x >> 5, pl = threadIdx.x & 31;
+    const int x = blockIdx.x * RF_PIX + pl, y = a.y0 + blockIdx.y;
+    const bool in = x < a.w;
+    const int b = blockIdx.z;
+    const float4* I1 = a.pix1 + (size_t)b * a.plane;
+    const float4* I2 = a.pix2 + (size_t)b * a.plane;
+    float2 fl = make_float2(0.f, 0.f);
+    if (in) fl = a.upsample ? upsample2(a.coarse + (size_t)b * a.ws * a.hs, a.ws, a.hs, x, y) : a.coarse[(size_t)b * a.w * a.h + (size_t)y * a.w + x];
+    const bool unknown = fl.x > EPPM_UNKNOWN_FLOW_THRESH || fl.y > EPPM_UNKNOWN_FLOW_THRESH;  // :2011
+    const short cxc = (short)((short)(int)fl.x + x), cyc = (short)((short)(int)fl.y + y);     // :2014-2019
+    const short cx = (short)(cxc + (m - 1));
+    float cost[3];
+    bool valid[3];
+    bool any = false;
+#pragma unroll
+    for (int n = 0; n < 3; n++) {
+        const short cy = (short)(cyc + (n - 1));
+        cost[n] = FLT_MAX;
+        valid[n] = in && !unknown && !(cx < 0 || cy < 0 || cx >= a.w || cy >= a.h);  // :2029
+        any = any || valid[n];
+    }
+    if (any) {
+        f32x2 cs[3][2], ws[3][2];
+#pragma unroll
+        for (int n = 0; n < 3; n++)
+#pragma unroll
+            for (int q = 0; q < 2; q++) cs[n][q] = ws[n][q] = pk2(0.f, 0.f);
+        const float4* a0 = I1 + (unsigned)((y + PAD) * a.pw + x + PAD);
+        const PixPk c1k = pack_pix(ldpix(a0));
+        PixPk c2k[3];
+        const float4* P[3];
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+            const int cy = max(0, min(a.h - 1, (int)cyc + n - 1));   // rows that are not valid are scored at a clamped centre and never used
+            const int cxs = max(0, min(a.w - 1, (int)cx));
+            P[n] = I2 + (unsigned)((cy + PAD) * a.pw + cxs + PAD);
+            c2k[n] = pack_pix(ldpix(P[n]));
+            asm volatile("" : "+l"(P[n]));
+        }
+        int s = 0;
+#pragma unroll 1
+        for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
+            const int ai = i < 0 ? -i : i;
+            const int irow = i * a.pw;
+EPPM_PRAGMA(unroll RF_JUNROLL)
+            for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE, s++) {
+                const float4 p1 = ldpix(a0 + irow + j);
+                const PixPk p1k = pack_pix(p1);
+                const float d1s = max3abs_diff(c1k, p1k);
+                const f32x2 d1 = pk2(d1s, d1s);
+                const float ggs = lut.gg[ai][j < 0 ? -j : j];
+                int off[4];
+                off[0] = irow + j;  // identity model: the exact integer site (cx + j, cy + i)
+#pragma unroll
+                for (int q = 0; q < 3; q++) off[q + 1] = tab.off[q][s];
+                if (STRIDE == 1 && s == tab.exc_s) {   // the one site of stride 1 whose x offset depends on the coordinate itself (see AffineTab)
+                    const int X = (int)cx + j;
+                    const int dx = __float2int_rd(__fmaf_rn((float)i, tab.exc_ci, __fmaf_rn((float)j, tab.exc_cj, (float)X))) - X;
+#pragma unroll
+                    for (int q = 0; q < 3; q++)
+                        if (q == tab.exc_q) off[q + 1] += dx;
+                }
+#pragma unroll
+                for (int n = 0; n < 3; n++) {
+                    if (!ALLROWS && !valid[n]) continue;
+                    const int pxb = a.px_bytes;
+                    f32x2 ct[2], t2[2], w[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                        sample_eval2(p1, p1k, p1, p1k, ldpix(pix_at_b(P[n], off[2 * h], pxb)), ldpix(pix_at_b(P[n], off[2 * h + 1], pxb)), c2k[n], c2k[n], d1,
+                                     RF_PK_LUT, ct[h], t2[h]);
+                    sample_weight4(t2[0], t2[1], ggs, w[0], w[1]);
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        cs[n][h] = fma2(ct[h], w[h], cs[n][h]);
+                        ws[n][h] = add2(ws[n][h], w[h]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+            if (!valid[n]) continue;
+            float c0, c1, c2, c3, w0, w1, w2, w3;
+            upk2(cs[n][0], c0, c1); upk2(cs[n][1], c2, c3);
+            upk2(ws[n][0], w0, w1); upk2(ws[n][1], w2, w3);
+            const float k1 = __fdiv_rn(c0, w0), k2 = __fdiv_rn(c1, w1), k3 = __fdiv_rn(c2, w2), k4 = __fdiv_rn(c3, w3);
+            cost[n] = min_ref(k1, min_ref(k2, min_ref(k3, k4)));  // :512
+        }
+    }
+    // candidates that are not valid never win: the reference skips them (:2029), here they carry +inf against the strict '<' below
+#pragma unroll
+    for (int n = 0; n < 3; n++) s_best[m * 3 + n][pl] = valid[n] ? cost[n] : __int_as_float(0x7f800000);
+    __syncthreads();
+    if (in && m == 0) {
         float2 out;
         if (unknown) out = make_float2(0.f, 0.f);
         else {
@@ -709,6 +859,7 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
     a.flow = out;
     a.upsample = upsample;
     a.y0 = y0;
+    a.px_bytes = (int)sizeof(float4);
     dim3 blk(RF_PIX * 3), grd((g.w + RF_PIX - 1) / RF_PIX, y1 - y0, n);
     if (!(c->variant & EPPM_VAR_REFINE_GENERIC)) {
         // table-driven kernel: the site table of this pitch and stride was built and verified at eppm_create
@@ -724,7 +875,9 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
             default:
                 if (v & EPPM_VAR_REFINE_NOGROUP) k_c2f_refine_tab<false, 3, RF_MINBLOCKS, 2><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else if (v & EPPM_VAR_REFINE_9WARP3) k_c2f_refine_tab<true, 1, 3, 2><<<grd, blk9, 0, c->stream>>>(a, c->cost_lut, *tabp);
-                else k_c2f_refine_tab<true, 3, RF_TAB2_MINBLOCKS, 2><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+                else if (v & EPPM_VAR_REFINE_SCALAR) k_c2f_refine_tab<true, 3, RF_TAB2_MINBLOCKS, 2><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+                else if (v & EPPM_VAR_REFINE_PK_BRANCH) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, false><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+                else k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, true><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
             }
             EPPM_LAUNCH_COUNT(1);
             return;
