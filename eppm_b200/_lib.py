@@ -15,7 +15,7 @@ class EppmParams(C.Structure):
         ("lambda_ad", C.c_float), ("lambda_census", C.c_float), ("pm_sig_r", C.c_float),
         ("stat_radius", C.c_int), ("stat_sim_thresh", C.c_int), ("wmf_radius", C.c_int), ("wmf_sig_r", C.c_float),
         ("wmf_iters", C.c_int), ("blf_sig_s", C.c_int), ("blf_sig_r", C.c_float), ("rng_mode", C.c_int),
-        ("seed", C.c_ulonglong), ("reserved", C.c_int * 8),
+        ("seed", C.c_ulonglong), ("inplace_filters", C.c_int), ("reserved", C.c_int * 7),
     ]
 
 
@@ -31,6 +31,7 @@ EPPM_SYMBOLS = {
     "eppm_compute_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "eppm_compute_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "eppm_compute_stream_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "eppm_compute_stream_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "eppm_synchronize": (C.c_int, [C.c_void_p]),
     "eppm_stream": (C.c_void_p, [C.c_void_p]),
     "eppm_stage_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

@@ -5,6 +5,7 @@
 (bao_flow_patchmatch_multiscale_cuda.h:33-45: init, set_data, compute_flow) for callers who think in those terms.
 Everything executes in libeppm_b200.so on the GPU; nothing here computes."""
 import ctypes as C
+import sys
 
 import numpy as np
 
@@ -35,8 +36,40 @@ def _ptr(a):
     return a.data_ptr()
 
 
+def _check_array(a, shape, dtype, what, device=None):
+    """Raw pointers cross the C ABI: refuse anything that is not the exact dtype / shape / C-contiguous layout the library reads.
+    `device`: None = host memory expected, an int = a tensor on that CUDA device (raw int addresses are the caller's responsibility)."""
+    if isinstance(a, int):
+        return
+    np_dt = np.dtype(dtype)
+    if isinstance(a, np.ndarray):
+        if device is not None:
+            raise EppmError(f"{what}: a numpy array is host memory, a device tensor is required")
+        if a.dtype != np_dt or tuple(a.shape) != tuple(shape) or not a.flags["C_CONTIGUOUS"]:
+            raise EppmError(f"{what}: need C-contiguous {np_dt.name} {tuple(shape)}, got {a.dtype.name} {tuple(a.shape)}"
+                            f"{'' if a.flags['C_CONTIGUOUS'] else ' (not contiguous)'}")
+        return
+    if hasattr(a, "data_ptr"):   # torch tensor
+        name = str(a.dtype).replace("torch.", "")
+        if name != np_dt.name or tuple(a.shape) != tuple(shape) or not a.is_contiguous():
+            raise EppmError(f"{what}: need contiguous {np_dt.name} {tuple(shape)}, got {name} {tuple(a.shape)}"
+                            f"{'' if a.is_contiguous() else ' (not contiguous)'}")
+        if device is None and a.is_cuda:
+            raise EppmError(f"{what}: host memory required, got a CUDA tensor")
+        if device is not None and (not a.is_cuda or a.device.index != device):
+            raise EppmError(f"{what}: a tensor on cuda:{device} is required, got {a.device}")
+        return
+    raise EppmError(f"{what}: unsupported buffer type {type(a).__name__}")
+
+
 class EppmContext:
-    """One context per (device, h, w, params): owns all device memory (eppm_create)."""
+    """One context per (device, h, w, params): owns all device memory (eppm_create).
+
+    Stream contract: the library enqueues on the context's own non-blocking stream (eppm_stream).  The device-tensor methods of this
+    wrapper order that stream AFTER the caller's current torch stream on entry and make the current torch stream wait for it on exit, so
+    tensors produced by torch just before a call are complete when the library reads them and the outputs are complete for any torch
+    work queued afterwards on the same stream -- no explicit synchronize() needed.  C callers do the same with eppm_stream() and events
+    (INTEGRATION.md)."""
 
     def __init__(self, h, w, max_batch=1, device=0, params=None):
         self.lib = _lib.load()
@@ -61,6 +94,38 @@ class EppmContext:
         if rc != 0:
             raise EppmError(f"{what} failed ({rc}): {self.lib.eppm_last_error().decode()}")
 
+    class _Ordered:
+        """with ctx._ordered(): the context stream waits for the current torch stream, and the current torch stream for the context stream."""
+
+        def __init__(self, ctx):
+            self.pair = None
+            torch = sys.modules.get("torch")
+            if torch is None or not torch.cuda.is_available():
+                return
+            cur = torch.cuda.current_stream(ctx.device)
+            own = ctx.lib.eppm_stream(ctx._ctx)
+            if own is None or cur.cuda_stream == own:
+                return
+            self.torch = torch
+            self.pair = (cur, torch.cuda.ExternalStream(own, device=ctx.device))
+
+        def __enter__(self):
+            if self.pair:
+                ev = self.torch.cuda.Event()
+                ev.record(self.pair[0])
+                self.pair[1].wait_event(ev)
+            return self
+
+        def __exit__(self, *exc):
+            if self.pair:
+                ev = self.torch.cuda.Event()
+                ev.record(self.pair[1])
+                self.pair[0].wait_event(ev)
+            return False
+
+    def _ordered(self):
+        return EppmContext._Ordered(self)
+
     # --- geometry ---------------------------------------------------------------------------------
     @property
     def num_levels(self):
@@ -78,23 +143,57 @@ class EppmContext:
         n = int(img1.shape[0])
         if out is None:
             out = np.empty((n, self.h, self.w, 2), np.float32)
+        _check_array(img1, (n, self.h, self.w, 3), np.uint8, "img1")
+        _check_array(img2, (n, self.h, self.w, 3), np.uint8, "img2")
+        _check_array(out, (n, self.h, self.w, 2), np.float32, "out")
         self._check(self.lib.eppm_compute_batch_host(self._ctx, _ptr(img1), _ptr(img2), n, _ptr(out)), "eppm_compute_batch_host")
         return out
 
     def compute_batch_device(self, d_img1, d_img2, n, d_flow):
-        """Device-resident tensors / raw device addresses; stream-ordered, returns without synchronising."""
-        self._check(self.lib.eppm_compute_batch_device(self._ctx, _ptr(d_img1), _ptr(d_img2), n, _ptr(d_flow)), "eppm_compute_batch_device")
+        """Device-resident tensors / raw device addresses; stream-ordered, returns without synchronising.  Tensors may hold more than n
+        pairs (a slice of a larger batch is the usual case): the first n are used."""
+        for t, c, dt, what in ((d_img1, 3, np.uint8, "d_img1"), (d_img2, 3, np.uint8, "d_img2"), (d_flow, 2, np.float32, "d_flow")):
+            if not isinstance(t, int):
+                if t.shape[0] < n:
+                    raise EppmError(f"{what}: holds {t.shape[0]} pairs, {n} requested")
+                _check_array(t, (t.shape[0], self.h, self.w, c), dt, what, device=self.device)
+        with self._ordered():
+            self._check(self.lib.eppm_compute_batch_device(self._ctx, _ptr(d_img1), _ptr(d_img2), n, _ptr(d_flow)), "eppm_compute_batch_device")
 
     def compute_stream_device(self, d_frames, n_pairs, d_flow):
         """Consecutive pairs of a frame list [n_pairs+1,h,w,3] (device); each frame is prepared once."""
-        self._check(self.lib.eppm_compute_stream_device(self._ctx, _ptr(d_frames), n_pairs, _ptr(d_flow)), "eppm_compute_stream_device")
+        if not isinstance(d_frames, int):
+            if d_frames.shape[0] < n_pairs + 1:
+                raise EppmError(f"d_frames: holds {d_frames.shape[0]} frames, {n_pairs + 1} needed")
+            _check_array(d_frames, (d_frames.shape[0], self.h, self.w, 3), np.uint8, "d_frames", device=self.device)
+        if not isinstance(d_flow, int):
+            if d_flow.shape[0] < n_pairs:
+                raise EppmError(f"d_flow: holds {d_flow.shape[0]} pairs, {n_pairs} needed")
+            _check_array(d_flow, (d_flow.shape[0], self.h, self.w, 2), np.float32, "d_flow", device=self.device)
+        with self._ordered():
+            self._check(self.lib.eppm_compute_stream_device(self._ctx, _ptr(d_frames), n_pairs, _ptr(d_flow)), "eppm_compute_stream_device")
+
+    def compute_stream_host(self, frames, out=None):
+        """frames: uint8 [n_frames,h,w,3] host array (numpy or pinned torch); returns float32 [n_frames-1,h,w,2]: the flow of every
+        consecutive pair.  n_frames may exceed max_batch (chunked, copies overlapped with compute inside the library)."""
+        n = int(frames.shape[0])
+        if out is None:
+            out = np.empty((n - 1, self.h, self.w, 2), np.float32)
+        _check_array(frames, (n, self.h, self.w, 3), np.uint8, "frames")
+        _check_array(out, (n - 1, self.h, self.w, 2), np.float32, "out")
+        self._check(self.lib.eppm_compute_stream_host(self._ctx, _ptr(frames), n, _ptr(out)), "eppm_compute_stream_host")
+        return out
 
     def synchronize(self):
         self._check(self.lib.eppm_synchronize(self._ctx), "eppm_synchronize")
 
     # --- staged ---------------------------------------------------------------------------------------
     def stage_prepare(self, d_img1, d_img2, n):
-        self._check(self.lib.eppm_stage_prepare(self._ctx, _ptr(d_img1), _ptr(d_img2), n), "eppm_stage_prepare")
+        for t, what in ((d_img1, "d_img1"), (d_img2, "d_img2")):
+            if not isinstance(t, int):
+                _check_array(t, (t.shape[0], self.h, self.w, 3), np.uint8, what, device=self.device)
+        with self._ordered():
+            self._check(self.lib.eppm_stage_prepare(self._ctx, _ptr(d_img1), _ptr(d_img2), n), "eppm_stage_prepare")
 
     def stage_patchmatch(self):
         self._check(self.lib.eppm_stage_patchmatch(self._ctx), "eppm_stage_patchmatch")
@@ -103,7 +202,13 @@ class EppmContext:
         self._check(self.lib.eppm_stage_patchmatch_partial(self._ctx, n_steps), "eppm_stage_patchmatch_partial")
 
     def write_plane(self, which, arr, level=0, pair=0):
+        h, w = self.level_dims(level if which in (PLANE_FLOW, PLANE_FLOW_TMP) else self.num_levels - 1)
+        shape, dt = {PLANE_NNF_FWD: ((h, w, 2), np.int16), PLANE_NNF_BWD: ((h, w, 2), np.int16), PLANE_COST_FWD: ((h, w), np.float32),
+                     PLANE_COST_BWD: ((h, w), np.float32), PLANE_FLOW: ((h, w, 2), np.float32)}.get(which, (None, None))
+        if shape is None:
+            raise EppmError(f"write_plane: plane {which} is read-only")
         arr = np.ascontiguousarray(arr)
+        _check_array(arr, shape, dt, "write_plane")
         n = self.lib.eppm_write_plane(self._ctx, which, level, pair, arr.ctypes.data)
         if n != arr.nbytes:
             raise EppmError(f"eppm_write_plane returned {n} for {arr.nbytes} bytes: {self.lib.eppm_last_error().decode()}")
@@ -112,7 +217,10 @@ class EppmContext:
         self._check(self.lib.eppm_stage_consistency(self._ctx), "eppm_stage_consistency")
 
     def stage_c2f(self, d_flow=None):
-        self._check(self.lib.eppm_stage_c2f(self._ctx, _ptr(d_flow)), "eppm_stage_c2f")
+        if d_flow is not None and not isinstance(d_flow, int):
+            _check_array(d_flow, (d_flow.shape[0], self.h, self.w, 2), np.float32, "d_flow", device=self.device)
+        with self._ordered():
+            self._check(self.lib.eppm_stage_c2f(self._ctx, _ptr(d_flow)), "eppm_stage_c2f")
 
     def read_plane(self, which, level=0, pair=0):
         h, w = self.level_dims(level)

@@ -300,9 +300,14 @@ void run_consistency(eppm_context* c) {
     op_lr_check(s, c->nnf[1], c->cost[1], c->nnf[0], g.w, g.h, n);
     short2* cur = c->nnf[0];
     short2* other = c->nnf_tmp;
-    op_outlier_removal(s, cur, other, c->cost[0], g.w, g.h, n, c->prm.stat_radius, c->prm.stat_sim_thresh);
-    { short2* t = cur; cur = other; other = t; }
-    wmf_sweeps(c, cur, other, c->pix[0][L], g.plane, g.pw, g.w, g.h, n, c->prm.wmf_iters, true);
+    if (c->inplace) {   // the reference's own update order: both filters rewrite the field they are reading
+        op_outlier_inplace(c, cur, c->cost[0], g.w, g.h, n);
+        op_wmf_inplace(c, cur, c->pix[0][L], g.plane, g.pw, g.w, g.h, n, c->prm.wmf_iters, true);
+    } else {
+        op_outlier_removal(s, cur, other, c->cost[0], g.w, g.h, n, c->prm.stat_radius, c->prm.stat_sim_thresh);
+        { short2* t = cur; cur = other; other = t; }
+        wmf_sweeps(c, cur, other, c->pix[0][L], g.plane, g.pw, g.w, g.h, n, c->prm.wmf_iters, true);
+    }
     op_fill_holes(s, cur, other, c->pix[0][L], g.plane, g.pw, g.w, g.h, n);
     { short2* t = cur; cur = other; other = t; }
     // keep the forward field where callers expect it

@@ -6,13 +6,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "eppm_internal.h"
 
 namespace eppm {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 static thread_local std::string g_err;
 void set_error(const std::string& s) { g_err = s; }
 bool cuda_ok(cudaError_t e, const char* what) {
@@ -43,6 +44,20 @@ static void host_luts(eppm_context* c) {
     volatile int bs = p.blf_sig_s;
     for (int i = 0; i < 21; i++) c->smooth_lut.g[i] = i <= 2 * p.blf_sig_s ? expf(-float(i * i) / float(bs * bs)) : 0.f;  // refine:812
 }
+
+// Every entry point runs on the context's device and puts the caller's current device back afterwards (a process that drives several
+// GPUs from one thread, or Python's garbage collector calling eppm_destroy at an arbitrary moment, must not find its device changed).
+struct DeviceScope {
+    int prev = -1;
+    explicit DeviceScope(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 
 }  // namespace eppm
 
@@ -78,9 +93,7 @@ void eppm_default_params(eppm_params* p) {
 }
 
 unsigned long long eppm_launch_count(int reset) {
-    unsigned long long v = g_launches;
-    if (reset) g_launches = 0;
-    return v;
+    return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, const eppm_params* params) {
@@ -93,7 +106,8 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         if (g_err.empty()) set_error("eppm_create: no such CUDA device (this library has no CPU path)");
         return EPPM_ERR_CUDA;
     }
-    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return EPPM_ERR_CUDA;
+    DeviceScope dev_scope(device);
+    if (!cuda_ok(cudaGetLastError(), "cudaSetDevice")) return EPPM_ERR_CUDA;
     eppm_context* c = new eppm_context;
     c->device = device;
     c->h = h; c->w = w; c->max_batch = max_batch;
@@ -103,6 +117,16 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         p.num_rand_guess < 0 || p.num_rand_guess > 16 || p.prop_seg_length < 1 || p.blf_sig_s < 1 || p.blf_sig_s > 10 || p.stat_radius < 0 ||
         p.stat_radius > 16 || (p.rng_mode != EPPM_RNG_XORWOW && p.rng_mode != EPPM_RNG_PHILOX) || p.lambda_ad != 0.1f || p.pm_sig_r != 0.1f) {
         set_error("eppm_create: parameter combination not supported by this build");
+        delete c;
+        return EPPM_ERR_ARG;
+    }
+    // ranges the kernels rely on: the search window arithmetic is done in 16-bit (bao_pmflow_kernel.cu:1557-1563), a window must hold at
+    // least one pixel, and every sigma / lambda divides
+    if (p.search_range < 1 || p.search_range > 32767 || p.search_radius_min < 0 || p.search_radius_min > p.search_range || !(p.lambda_census > 0.f) ||
+        !(p.wmf_sig_r > 0.f) || !(p.blf_sig_r > 0.f) || p.wmf_iters < 0 || p.wmf_iters > 1000 || p.stat_sim_thresh < 0 || p.num_iter > 1000 ||
+        p.prop_seg_length > 4096 || !(p.lambda_census < 1e6f) || !(p.wmf_sig_r < 1e6f) || !(p.blf_sig_r < 1e6f)) {
+        set_error("eppm_create: parameter out of range (search_range 1..32767, 0 <= search_radius_min <= search_range, positive finite lambda_census / "
+                  "wmf_sig_r / blf_sig_r, 0 <= wmf_iters, num_iter <= 1000, stat_sim_thresh >= 0)");
         delete c;
         return EPPM_ERR_ARG;
     }
@@ -124,6 +148,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
     }
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->n_sm = v; }
     c->variant = getenv("EPPM_VARIANT") ? atoi(getenv("EPPM_VARIANT")) : 0;
+    c->inplace = p.inplace_filters != 0 || (getenv("EPPM_INPLACE_LEGACY") && atoi(getenv("EPPM_INPLACE_LEGACY")) != 0);
     c->profile = getenv("EPPM_PROFILE") && atoi(getenv("EPPM_PROFILE")) != 0;
     {
         // EPPM_STREAM_PRIORITY (measurement knob): CUDA stream priority of this context's compute stream (lower = more urgent), so that
@@ -166,6 +191,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         for (int i = 0; i < c->n_levels; i++) c->gauss[i].d_w = A.take<float>(7 * 7 + 1);
         const size_t nc = (size_t)gc.w * gc.h;
         for (int img = 0; img < 2; img++) c->pixT[img] = A.take<float4>(B * gc.plane);
+        for (int img = 0; img < 2; img++) c->pixQ[img] = A.take<float4>(B * (size_t)make_qgeom(gc.pw, gc.ph).plane);
         for (int d = 0; d < 2; d++) {
             c->nnf[d] = A.take<short2>(B * nc);
             c->cost[d] = A.take<float>(B * nc);
@@ -180,6 +206,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
             const size_t thr = 2 * B * (thr_row > thr_col ? thr_row : thr_col);
             c->prop_prev = A.take<short2>(thr);
             c->prop_queue = A.take<int4>(thr);
+            c->prop_memo = A.take<int4>(2 * B * nc);
             c->prop_count = A.take<int>((size_t)(p.num_iter > 0 ? p.num_iter : 1) * 4 * sl);
         }
         c->rng_init = A.take<short2>(nc);
@@ -246,7 +273,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
 
 void eppm_destroy(eppm_context* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int img = 0; img < 2; img++)
         if (c->tex_pm[img]) cudaDestroyTextureObject(c->tex_pm[img]);
@@ -278,7 +305,7 @@ int eppm_level_dims(const eppm_context* c, int level, int* h, int* w) {
 void* eppm_stream(eppm_context* c) { return c ? (void*)c->stream : nullptr; }
 int eppm_synchronize(eppm_context* c) {
     if (!c) return EPPM_ERR_ARG;
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     return cuda_ok(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize") ? EPPM_OK : EPPM_ERR_CUDA;
 }
 
@@ -287,38 +314,38 @@ static int check_batch(eppm_context* c, const void* a, const void* b, int n) {
         set_error("bad argument (null pointer or batch size out of range)");
         return EPPM_ERR_ARG;
     }
-    cudaSetDevice(c->device);
     return EPPM_OK;
 }
 
 int eppm_stage_prepare(eppm_context* c, const uint8_t* d_img1, const uint8_t* d_img2, int n) {
     int rc = check_batch(c, d_img1, d_img2, n);
     if (rc) return rc;
+    DeviceScope dev_scope(c->device);
     c->n_cur = n;
     run_prepare(c, d_img1, d_img2, n);
     return cuda_ok(cudaGetLastError(), "prepare") ? EPPM_OK : EPPM_ERR_CUDA;
 }
 int eppm_stage_patchmatch(eppm_context* c) {
     if (!c || c->n_cur < 1) { set_error("patchmatch before prepare"); return EPPM_ERR_STATE; }
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     run_patchmatch(c);
     return cuda_ok(cudaGetLastError(), "patchmatch") ? EPPM_OK : EPPM_ERR_CUDA;
 }
 int eppm_stage_patchmatch_partial(eppm_context* c, int n_steps) {
     if (!c || c->n_cur < 1) { set_error("patchmatch before prepare"); return EPPM_ERR_STATE; }
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     run_patchmatch_dirs(c, 2, n_steps);
     return cuda_ok(cudaGetLastError(), "patchmatch") ? EPPM_OK : EPPM_ERR_CUDA;
 }
 int eppm_stage_consistency(eppm_context* c) {
     if (!c || c->n_cur < 1) { set_error("consistency before prepare"); return EPPM_ERR_STATE; }
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     run_consistency(c);
     return cuda_ok(cudaGetLastError(), "consistency") ? EPPM_OK : EPPM_ERR_CUDA;
 }
 int eppm_stage_c2f(eppm_context* c, float* d_flow) {
     if (!c || c->n_cur < 1) { set_error("c2f before prepare"); return EPPM_ERR_STATE; }
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     run_c2f(c, d_flow);
     return cuda_ok(cudaGetLastError(), "c2f") ? EPPM_OK : EPPM_ERR_CUDA;
 }
@@ -327,6 +354,7 @@ int eppm_compute_batch_device(eppm_context* c, const uint8_t* d_img1, const uint
     int rc = check_batch(c, d_img1, d_img2, n);
     if (rc) return rc;
     if (!d_flow) { set_error("null output"); return EPPM_ERR_ARG; }
+    DeviceScope dev_scope(c->device);
     c->n_cur = n;
     cudaStream_t s = c->stream;
     if (c->profile) cudaEventRecord(c->ev[0], s);
@@ -348,28 +376,31 @@ int eppm_compute_stream_device(eppm_context* c, const uint8_t* d_frames, int n_p
         set_error("bad argument (null pointer, or n_pairs + 1 frames exceed max_batch)");
         return EPPM_ERR_ARG;
     }
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     run_prepare_frames(c, d_frames, n_pairs + 1);
     // image 2 of pair f is frame f+1: alias the image-2 plane bases one plane behind the image-1 bases for this call
     float4* keep_pix[MAX_LEVELS];
     float4* keep_pixT = c->pixT[1];
+    float4* keep_pixQ = c->pixQ[1];
     for (int l = 0; l < c->n_levels; l++) {
         keep_pix[l] = c->pix[1][l];
         c->pix[1][l] = c->pix[0][l] + c->lv[l].plane;
     }
     c->pixT[1] = c->pixT[0] + c->lv[c->n_levels - 1].plane;
+    c->pixQ[1] = c->pixQ[0] + make_qgeom(c->lv[c->n_levels - 1].pw, c->lv[c->n_levels - 1].ph).plane;
     c->n_cur = n_pairs;
     run_patchmatch(c);
     run_consistency(c);
     run_c2f(c, d_flow);
     for (int l = 0; l < c->n_levels; l++) c->pix[1][l] = keep_pix[l];
     c->pixT[1] = keep_pixT;
+    c->pixQ[1] = keep_pixQ;
     return cuda_ok(cudaGetLastError(), "compute_stream") ? EPPM_OK : EPPM_ERR_CUDA;
 }
 
 int eppm_last_stage_ms(eppm_context* c, float out[5]) {
     if (!c || !c->profile) return EPPM_ERR_STATE;
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     if (!cuda_ok(cudaEventSynchronize(c->ev[4]), "event sync")) return EPPM_ERR_CUDA;
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&out[i], c->ev[i], c->ev[i + 1]);
     cudaEventElapsedTime(&out[4], c->ev[0], c->ev[4]);
@@ -378,7 +409,7 @@ int eppm_last_stage_ms(eppm_context* c, float out[5]) {
 
 int eppm_last_kernel_ms(eppm_context* c, int which, float* ms) {
     if (!c || !c->profile || !ms || which < 0 || which > 1) return EPPM_ERR_STATE;
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     if (!cuda_ok(cudaEventSynchronize(c->ev_k[2 * which + 1]), "event sync")) return EPPM_ERR_CUDA;
     return cuda_ok(cudaEventElapsedTime(ms, c->ev_k[2 * which], c->ev_k[2 * which + 1]), "event elapsed") ? EPPM_OK : EPPM_ERR_CUDA;
 }
@@ -389,7 +420,7 @@ int eppm_last_kernel_ms(eppm_context* c, int which, float* ms) {
 int eppm_compute_batch_host(eppm_context* c, const uint8_t* img1, const uint8_t* img2, int n, float* flow) {
     if (!c || !img1 || !img2 || n < 1) { set_error("bad argument (null pointer or empty batch)"); return EPPM_ERR_ARG; }
     if (!flow) { set_error("null output"); return EPPM_ERR_ARG; }
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     const size_t px = (size_t)c->h * c->w;
     cudaStream_t s = c->stream, cs = c->copy_stream;
     uint8_t* in[2][2] = {{c->d_rgb[0], c->d_rgb[1]}, {c->d_rgb_alt[0], c->d_rgb_alt[1]}};
@@ -408,7 +439,13 @@ int eppm_compute_batch_host(eppm_context* c, const uint8_t* img1, const uint8_t*
         cudaStreamWaitEvent(s, c->ev_h2d[slot], 0);
         if (k >= 2) cudaStreamWaitEvent(s, c->ev_d2h[slot], 0);  // the previous result in this slot has left the device
         int rc = eppm_compute_batch_device(c, in[slot][0], in[slot][1], m, out[slot]);
-        if (rc) return rc;
+        if (rc) {   // copies of earlier chunks into the caller's memory may still be in flight: drain both streams before giving up
+            const std::string keep = g_err;
+            cudaStreamSynchronize(cs);
+            cudaStreamSynchronize(s);
+            set_error(keep);
+            return rc;
+        }
         cudaEventRecord(c->ev_done[slot], s);
         if (k + 1 < n_chunks) upload(k + 1);
         cudaStreamWaitEvent(cs, c->ev_done[slot], 0);
@@ -419,9 +456,51 @@ int eppm_compute_batch_host(eppm_context* c, const uint8_t* img1, const uint8_t*
     return cuda_ok(cudaStreamSynchronize(s), "compute_batch_host") ? EPPM_OK : EPPM_ERR_CUDA;
 }
 
+// Video stream with HOST buffers: frames [n_frames][h][w][3] u8, flow [n_frames - 1][h][w][2] f32.  The stream is cut into
+// chunks of max_batch - 1 pairs (max_batch frames; neighbouring chunks share one frame, uploaded with both); while chunk k computes,
+// chunk k+1 uploads and chunk k-1's flow downloads on the copy stream.  Each frame's pyramid / census / packed planes are built once per
+// chunk.  Replaces a loop of set_data + compute_flow over consecutive pairs (main.cpp:59-65 in a video loop).
+int eppm_compute_stream_host(eppm_context* c, const uint8_t* frames, int n_frames, float* flow) {
+    if (!c || !frames || !flow || n_frames < 2) { set_error("bad argument (null pointer or fewer than two frames)"); return EPPM_ERR_ARG; }
+    if (c->max_batch < 2) { set_error("eppm_compute_stream_host needs a context with max_batch >= 2"); return EPPM_ERR_ARG; }
+    DeviceScope dev_scope(c->device);
+    const size_t px = (size_t)c->h * c->w;
+    cudaStream_t s = c->stream, cs = c->copy_stream;
+    uint8_t* in[2] = {c->d_rgb[0], c->d_rgb_alt[0]};
+    float* out[2] = {c->d_flow_out, c->d_flow_out_alt};
+    const int P = c->max_batch - 1, n_pairs = n_frames - 1, n_chunks = (n_pairs + P - 1) / P;
+    auto upload = [&](int k) {
+        const int f0 = k * P, m = n_pairs - f0 < P ? n_pairs - f0 : P, slot = k & 1;
+        if (k >= 2) cudaStreamWaitEvent(cs, c->ev_done[slot], 0);
+        cudaMemcpyAsync(in[slot], frames + (size_t)f0 * px * 3, (size_t)(m + 1) * px * 3, cudaMemcpyHostToDevice, cs);
+        cudaEventRecord(c->ev_h2d[slot], cs);
+    };
+    upload(0);
+    for (int k = 0; k < n_chunks; k++) {
+        const int f0 = k * P, m = n_pairs - f0 < P ? n_pairs - f0 : P, slot = k & 1;
+        cudaStreamWaitEvent(s, c->ev_h2d[slot], 0);
+        if (k >= 2) cudaStreamWaitEvent(s, c->ev_d2h[slot], 0);
+        int rc = eppm_compute_stream_device(c, in[slot], m, out[slot]);
+        if (rc) {
+            const std::string keep = g_err;
+            cudaStreamSynchronize(cs);
+            cudaStreamSynchronize(s);
+            set_error(keep);
+            return rc;
+        }
+        cudaEventRecord(c->ev_done[slot], s);
+        if (k + 1 < n_chunks) upload(k + 1);
+        cudaStreamWaitEvent(cs, c->ev_done[slot], 0);
+        cudaMemcpyAsync(flow + (size_t)f0 * px * 2, out[slot], (size_t)m * px * 2 * sizeof(float), cudaMemcpyDeviceToHost, cs);
+        cudaEventRecord(c->ev_d2h[slot], cs);
+    }
+    if (!cuda_ok(cudaStreamSynchronize(cs), "compute_stream_host (copy stream)")) return EPPM_ERR_CUDA;
+    return cuda_ok(cudaStreamSynchronize(s), "compute_stream_host") ? EPPM_OK : EPPM_ERR_CUDA;
+}
+
 long eppm_read_plane(eppm_context* c, int which, int level, int pair, void* host_out) {
     if (!c || !host_out || level < 0 || level >= c->n_levels || pair < 0 || pair >= c->max_batch) return EPPM_ERR_ARG;
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     if (!cuda_ok(cudaStreamSynchronize(c->stream), "read_plane sync")) return EPPM_ERR_CUDA;
     const LevelGeom& g = c->lv[level];
     const LevelGeom& gc = c->lv[c->n_levels - 1];
@@ -486,7 +565,7 @@ int eppm_band_rows(eppm_context* c, int level, int* y0, int* y1) {
 }
 int eppm_tiled_pm_steps(eppm_context* c, int first_step, int end_step) {
     if (!c || c->n_cur < 1) { set_error("patchmatch before prepare"); return EPPM_ERR_STATE; }
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     run_patchmatch_dirs(c, 2, end_step, first_step);
     return cuda_ok(cudaGetLastError(), "tiled patchmatch") ? EPPM_OK : EPPM_ERR_CUDA;
 }
@@ -495,7 +574,7 @@ int eppm_tiled_c2f_step(eppm_context* c, int level, int kind) {
         set_error("eppm_tiled_c2f_step: bad argument");
         return EPPM_ERR_ARG;
     }
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     run_c2f_step(c, level, kind, nullptr);
     return cuda_ok(cudaGetLastError(), "tiled c2f") ? EPPM_OK : EPPM_ERR_CUDA;
 }
@@ -538,7 +617,7 @@ int eppm_smooth_uses_tma(eppm_context* c) { return c ? c->tmap_ok[0] : EPPM_ERR_
 
 long eppm_write_plane(eppm_context* c, int which, int level, int pair, const void* host_in) {
     if (!c || !host_in || level < 0 || level >= c->n_levels || pair < 0 || pair >= c->max_batch) return EPPM_ERR_ARG;
-    cudaSetDevice(c->device);
+    DeviceScope dev_scope(c->device);
     if (!cuda_ok(cudaStreamSynchronize(c->stream), "write_plane sync")) return EPPM_ERR_CUDA;
     const LevelGeom& g = c->lv[level];
     const LevelGeom& gc = c->lv[c->n_levels - 1];
@@ -561,6 +640,8 @@ long eppm_write_plane(eppm_context* c, int which, int level, int pair, const voi
     default:
         return EPPM_ERR_ARG;
     }
+    // a caller-written field voids what the propagation remembers about candidates it has already scored
+    if (which != EPPM_PLANE_FLOW) cudaMemset(c->prop_memo, 0xff, (size_t)2 * c->max_batch * nc * sizeof(int4));
     return cuda_ok(e, "write_plane copy") ? bytes : EPPM_ERR_CUDA;
 }
 

@@ -328,4 +328,73 @@ __device__ __forceinline__ float patch_cost(const float4* __restrict__ A, const 
     return __fdiv_rn(cost_sum, weight_sum);
 }
 
+
+// ---- parity-split ("Q") planes of the PatchMatch level --------------------------------------------------------------------------
+// The patch samples every SECOND pixel in x and y (bao_pmflow_kernel.cu:269,272), so the 10 samples of a patch row are 32 bytes apart
+// in a packed plane: one 16-byte request per sample and lane, half of every line fetched for nothing.  The Q plane stores the padded
+// plane as four sub-planes by the parity of (x, y); the 100 samples of a patch then form a dense 10 x 10 block of ONE sub-plane and a
+// lane reads two neighbouring samples with one 256-bit load (LDG.E.256, new on sm_100): half the L1 requests of the kernels that are
+// bound by them.  A 256-bit load must be 32-byte aligned and a patch row starts at an arbitrary sample, so every sub-plane is stored
+// twice, the second copy shifted by one sample (16 bytes): rows that start at an odd sample index read the shifted copy.
+struct QGeom {
+    int qp;          // row pitch of a sub-plane in pixels (even)
+    int qh;          // rows of a sub-plane
+    unsigned c1;     // element offset of the shifted copy (odd)
+    unsigned plane;  // elements per image (both copies)
+};
+__host__ __device__ inline QGeom make_qgeom(int pw, int ph) {
+    QGeom q;
+    q.qp = ((pw + 1) / 2 + 2 + 1) & ~1;
+    q.qh = (ph + 1) / 2 + 1;
+    q.c1 = 4u * q.qh * q.qp + 3u;
+    q.plane = (2u * 4u * q.qh * q.qp + 8u) & ~1u;
+    return q;
+}
+// element index of padded pixel (X, Y) in copy 0
+__device__ __forceinline__ unsigned q_index(const QGeom& q, int X, int Y) {
+    return (unsigned)((((Y & 1) * 2 + (X & 1)) * q.qh + (Y >> 1)) * q.qp + (X >> 1));
+}
+struct Pix2 {
+    float4 a, b;
+};
+__device__ __forceinline__ Pix2 ldpix2(const float4* p) {   // p 32-byte aligned
+    Pix2 r;
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+        : "l"(p));
+    return r;
+}
+// element index (even) of the top-left sample of the patch centred at logical pixel (x, y): padded (x + PAD - 9, y + PAD - 9)
+__device__ __forceinline__ unsigned q_patch_origin(const QGeom& q, int x, int y) {
+    const int X = x + PAD - PATCH_R, Y = y + PAD - PATCH_R;
+    const unsigned e = q_index(q, X, Y);
+    return (e & 1u) ? e + q.c1 : e;
+}
+
+// patch_cost at sample stride 2 on Q planes: QA / QB = Q planes of the source / target image (pair base), A / B the packed planes (centre
+// pixels only).  Sample order, arithmetic and accumulation are patch_cost's: rows outer, samples inner.
+__device__ __forceinline__ float patch_cost_q(const float4* __restrict__ A, const float4* __restrict__ B, const float4* __restrict__ QA,
+                                              const float4* __restrict__ QB, const QGeom& q, int pw, int x1, int y1, int x2, int y2,
+                                              const CostLut& lut, const float* s_census) {
+    const PixPk c1k = pack_pix(ldpix(A + ((unsigned)(x1 + PAD) + (unsigned)(y1 + PAD) * (unsigned)pw)));
+    const PixPk c2k = pack_pix(ldpix(B + ((unsigned)(x2 + PAD) + (unsigned)(y2 + PAD) * (unsigned)pw)));
+    unsigned ea = q_patch_origin(q, x1, y1), eb = q_patch_origin(q, x2, y2);
+    float cost_sum = 0.f, weight_sum = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < 10; i++) {
+        const int ai = i < 5 ? 9 - 2 * i : 2 * i - 9;
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+            const Pix2 u = ldpix2(QA + (ea + 2u * m)), v = ldpix2(QB + (eb + 2u * m));
+            const float4 p1[2] = {u.a, u.b}, p2[2] = {v.a, v.b};
+            const int j0 = 2 * m < 5 ? 9 - 4 * m : 4 * m - 9, j1 = 2 * m + 1 < 5 ? 7 - 4 * m : 4 * m - 7;   // |-9 + 2 (2m)|, |-9 + 2 (2m + 1)|
+            const float gg[2] = {lut.gg[ai][j0], lut.gg[ai][j1]};
+            sample_group<2>(p1, p2, c1k, c2k, gg, s_census, cost_sum, weight_sum);
+        }
+        ea += q.qp;
+        eb += q.qp;
+    }
+    return __fdiv_rn(cost_sum, weight_sum);
+}
+
 }  // namespace eppm

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -25,9 +26,14 @@ enum {
     EPPM_VAR_SEARCH_TEX3 = 512,    // random search: the three wide-window guesses gather their target side through the texture unit
     EPPM_VAR_SEARCH_NOTEX = 1024,  //   ... none (default: the two widest)
     EPPM_VAR_SEARCH_SPLIT3 = 65536,  //   ... three passes of two (64 registers, 8 CTAs)
-    EPPM_VAR_REFINE_SCALAR = 2048,     // table refine with the four models of a candidate as scalar chains (round-1 default) instead of packed pairs
+    EPPM_VAR_REFINE_PK = 2048,         // table refine with the four models of a candidate in packed pairs (measured slower: 8.82 vs 8.29 ms per 1080p pair at level 0; packed FP32x2 holds the FMA pipe two cycles)
     EPPM_VAR_REFINE_PK_BRANCH = 4096,  // packed-pair refine that branches around candidate rows outside the image instead of scoring them at a clamped centre
-    EPPM_VAR_PROP_QUEUE = 8192,        // propagation: the global work queue, two launches per lock-step (round-1 default), instead of barrier-free segment chains
+    EPPM_VAR_PROP_THREAD = 8192,       // propagation queue scored by one THREAD per evaluation (round-1 default) instead of one warp per evaluation
+    EPPM_VAR_PROP_CHAIN = 16384,       // propagation as barrier-free segment chains, 32 chains per warp (measured slower than the queue: 5.70 vs 5.26 ms per pair)
+    EPPM_VAR_SEARCH_WARP = 32768,      // random search with one WARP per evaluation (measured slower: neighbouring pixels' narrow guesses already coalesce in the thread-per-pixel kernel)
+    EPPM_VAR_PROP_NOMEMO = 262144,     // propagation: score candidates the pixel has scored before (the reference does; the memo skips them, same outcome)
+    EPPM_VAR_PM_NOQ = 524288,          // PatchMatch kernels read the packed planes sample by sample (16-byte loads) instead of the parity-split planes pair by pair
+    EPPM_VAR_PROP_WARP_FULL = 131072,  // propagation queue scored by one warp per evaluation with ALL samples staged in shared memory (13 KB per warp starves the L1)
     EPPM_VAR_PROP_NOSKIP = 8,      // propagation: evaluate candidates that equal the current target (the reference does)
 };
 
@@ -101,6 +107,7 @@ struct eppm_context {
     uchar4* blur_tmp[2] = {nullptr, nullptr};    // scratch for pyramid levels beyond the 2-octave fast path
     float4* pix[2][eppm::MAX_LEVELS] = {};       // [B][ph_l][pw_l] packed float rgb + census
     float4* pixT[2] = {nullptr, nullptr};        // column-major copies of the coarsest level ([B][pw][ph]) for row propagation
+    float4* pixQ[2] = {nullptr, nullptr};        // parity-split copies of the coarsest level (QGeom, eppm_device.cuh): 256-bit sample-pair loads
     cudaTextureObject_t tex_pm[2] = {0, 0};      // linear uint4 textures over pix[img][coarsest]: scattered gathers of the random search
     const float4* tex_pm_base[2] = {nullptr, nullptr};
     size_t tex_pm_texels = 0;
@@ -113,6 +120,7 @@ struct eppm_context {
     int* occl_count = nullptr;                   // [2] device counters
     short2* prop_prev = nullptr;                 // propagation work queue: running target per (pair, direction, line, segment)
     int4* prop_queue = nullptr;                  //   evaluations of the current lock-step
+    int4* prop_memo = nullptr;                   //   last candidate scored per (pair, direction, pixel) and pass direction: [2*B][h_c][w_c]
     int* prop_count = nullptr;                   //   queue length per (pass, step): [num_iter * 4 * seg_len]
     int n_sm = 148;
     short2* rng_init = nullptr;                  // [h_c][w_c] initial targets (same for every pair/direction)
@@ -131,13 +139,14 @@ struct eppm_context {
     int aff_ok[eppm::MAX_LEVELS] = {};
     int variant = 0;                             // EPPM_VARIANT bit mask (A/B switches for measurements, see EPPM_VAR_*)
     int smooth_fast_div = 0;                     // set at create time when the constant-division fast path was verified exact
+    int inplace = 0;                             // eppm_params::inplace_filters or EPPM_INPLACE_LEGACY=1: the three racy filters of the reference run in place (legacy_inplace.cu)
     int rng_ready = 0;                           // rng_init / rng_search expanded (lazily, before the first PatchMatch)
 };
 
 namespace eppm {
 void set_error(const std::string& s);
 bool cuda_ok(cudaError_t e, const char* what);
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
 #define EPPM_LAUNCH_COUNT(n) (eppm::g_launches += (n))
 
 // stage drivers (each enqueues on ctx->stream)
@@ -168,12 +177,17 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                float2* out, int n, int y0 = 0, int y1 = -1);
 long long selftest_const_div(float d, unsigned lo_bits, unsigned hi_bits);
 void op_smooth(eppm_context* c, const float2* src, float2* dst, const float4* pix1, const LevelGeom& g, int n, int y0 = 0, int y1 = -1);
+// in-place forms of the reference's racy filters (legacy_inplace.cu; opt-in)
+void op_outlier_inplace(eppm_context* c, short2* nnf, float* cost, int w, int h, int n);
+void op_wmf_inplace(eppm_context* c, short2* nnf, const float4* pix, size_t plane, int pw, int w, int h, int n, int iters, bool only_occlusion);
+void op_smooth_inplace(eppm_context* c, float2* flow, const float4* pix1, const LevelGeom& g, int n);
 void op_preblur_rgba(eppm_context* c, const uchar4* src1, const uchar4* src2, size_t pitch_bytes);
 void op_pyramid_and_pack(eppm_context* c, int n, int two = 2);
 void run_prepare_frames(eppm_context* c, const uint8_t* d_frames, int n_frames);
 void op_pack_foreign(cudaStream_t s, const uchar4* rgba, size_t rgba_pitch_bytes, const unsigned char* census, size_t census_pitch_bytes, float4* pix,
                      const LevelGeom& g);
 void op_transpose_plane(cudaStream_t s, const float4* src, float4* dst, const LevelGeom& g, int n_img);
+void op_split_plane(cudaStream_t s, const float4* src, float4* dst, const LevelGeom& g, int n_img);
 void op_extract_census(cudaStream_t s, const float4* pix, const LevelGeom& g, unsigned char* out, size_t out_pitch_bytes);
 void k_pack_planes(cudaStream_t s, const uchar4* rgba, size_t rgba_pitch_bytes, size_t rgba_img_stride_bytes, float4* pix,
                    const LevelGeom& g, int n_img);

@@ -173,6 +173,7 @@ void baoCudaPatchMatch(short2* d_disp_vec, float* d_cost, uchar4* d_img1, uchar4
     op_pack_foreign(c->stream, d_img1, img_pitch, d_census1, census_pitch, c->pix[0][0], g);
     op_pack_foreign(c->stream, d_img2, img_pitch, d_census2, census_pitch, c->pix[1][0], g);
     for (int img = 0; img < 2; img++) op_transpose_plane(c->stream, c->pix[img][0], c->pixT[img], g, 1);
+    for (int img = 0; img < 2; img++) op_split_plane(c->stream, c->pix[img][0], c->pixQ[img], g, 1);
     run_patchmatch_dirs(c, 1);
     copy_out(c, d_disp_vec, disp_pitch, c->nnf[0], w, h);
     copy_out(c, d_cost, cost_pitch, c->cost[0], w, h);
@@ -225,8 +226,13 @@ void baoCudaOutlierRemoval(short2* d_disp_vec, float* d_cost, int w, int h, size
     Scope sc(c, "baoCudaOutlierRemoval");
     copy_in(c, c->nnf[0], d_disp_vec, disp_pitch, w, h);
     copy_in(c, c->cost[0], d_cost, cost_pitch, w, h);
-    op_outlier_removal(c->stream, c->nnf[0], c->nnf_tmp, c->cost[0], w, h, 1, c->prm.stat_radius, c->prm.stat_sim_thresh);
-    copy_out(c, d_disp_vec, disp_pitch, c->nnf_tmp, w, h);
+    if (c->inplace) {
+        op_outlier_inplace(c, c->nnf[0], c->cost[0], w, h, 1);
+        copy_out(c, d_disp_vec, disp_pitch, c->nnf[0], w, h);
+    } else {
+        op_outlier_removal(c->stream, c->nnf[0], c->nnf_tmp, c->cost[0], w, h, 1, c->prm.stat_radius, c->prm.stat_sim_thresh);
+        copy_out(c, d_disp_vec, disp_pitch, c->nnf_tmp, w, h);
+    }
     copy_out(c, d_cost, cost_pitch, c->cost[0], w, h);
 }
 
@@ -241,7 +247,8 @@ void baoCudaWeightedMedianFilter(short2* d_disp_vec, float* d_cost, uchar4* d_im
     copy_in(c, c->nnf[0], d_disp_vec, disp_pitch, w, h);
     short2* cur = c->nnf[0];
     short2* other = c->nnf_tmp;
-    wmf_sweeps(c, cur, other, c->pix[0][0], g.plane, g.pw, w, h, 1, num_iter, is_only_occlusion);
+    if (c->inplace) op_wmf_inplace(c, cur, c->pix[0][0], g.plane, g.pw, w, h, 1, num_iter, is_only_occlusion);
+    else wmf_sweeps(c, cur, other, c->pix[0][0], g.plane, g.pw, w, h, 1, num_iter, is_only_occlusion);
     copy_out(c, d_disp_vec, disp_pitch, cur, w, h);
 }
 
@@ -318,8 +325,13 @@ void baoCudaFlowSmoothing(float2* d_flow, uchar4* d_img, int w, int h, size_t im
     const LevelGeom& g = c->lv[0];
     op_pack_foreign(c->stream, d_img, img_pitch, nullptr, 0, c->pix[0][0], g);
     copy_in(c, c->flow[0], d_flow, flow_pitch, w, h);
-    op_smooth(c, c->flow[0], c->flow_tmp, c->pix[0][0], g, 1);
-    copy_out(c, d_flow, flow_pitch, c->flow_tmp, w, h);
+    if (c->inplace) {
+        op_smooth_inplace(c, c->flow[0], c->pix[0][0], g, 1);
+        copy_out(c, d_flow, flow_pitch, c->flow[0], w, h);
+    } else {
+        op_smooth(c, c->flow[0], c->flow_tmp, c->pix[0][0], g, 1);
+        copy_out(c, d_flow, flow_pitch, c->flow_tmp, w, h);
+    }
 }
 
 void baoCudaLeftRightCheck_Buffered(short2* d_disp_vec, float* d_cost, short2* d_disp_vec2, float* d_cost2, short2* d_disp_vec_temp,

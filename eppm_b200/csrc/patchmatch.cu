@@ -96,6 +96,8 @@ struct PmArgs {
     int y0, y1;             // row band [y0, y1) this launch owns (whole level unless the frame is tiled across GPUs); segment aligned
     // optional texture path for scattered target-side gathers: linear uint4 textures over the packed planes of this level;
     // texB[dir] is the one that holds direction dir's TARGET image, texB_off[dir] the texel index of pair 0's padded origin in it
+    const float4* q[2];     // parity-split (Q) planes of image 1 / image 2, pair 0 (null: not built)
+    QGeom qg;
     cudaTextureObject_t tex[2];      // per image: linear texture that holds its packed planes (0 = none)
     unsigned tex_off[2];             // texel index of pair 0's padded origin of pix[image] inside that texture
 };
@@ -117,6 +119,13 @@ __device__ __forceinline__ void pm_select(const PmArgs& a, int z, const float4*&
     asm volatile("" : "+l"(A), "+l"(B));  // keep the plane bases in registers: every load is then base + u32 offset
 }
 
+__device__ __forceinline__ void pm_select_q(const PmArgs& a, int z, const float4*& QA, const float4*& QB) {
+    const int dir = a.n_dirs == 2 ? (z & 1) : 0, b = a.n_dirs == 2 ? (z >> 1) : z;
+    QA = (dir ? a.q[1] : a.q[0]) + (size_t)b * a.qg.plane;
+    QB = (dir ? a.q[0] : a.q[1]) + (size_t)b * a.qg.plane;
+    asm volatile("" : "+l"(QA), "+l"(QB));
+}
+
 // Random field + initial cost (d_gen_rand_field + d_compute_cost_field).
 template <int STRIDE>
 __global__ void __launch_bounds__(128) k_pm_init(PmArgs a, const short2* __restrict__ rng_init, const __grid_constant__ CostLut lut) {
@@ -128,7 +137,13 @@ __global__ void __launch_bounds__(128) k_pm_init(PmArgs a, const short2* __restr
     pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
     const short2 t = rng_init[y * a.w + x];
     nnf[y * a.w + x] = t;
-    cost[y * a.w + x] = patch_cost<STRIDE, false>(A, B, a.pw, x, y, t.x, t.y, lut, s_census);
+    if (STRIDE == 2 && a.q[0]) {
+        const float4 *QA, *QB;
+        pm_select_q(a, blockIdx.z, QA, QB);
+        cost[y * a.w + x] = patch_cost_q(A, B, QA, QB, a.qg, a.pw, x, y, t.x, t.y, lut, s_census);
+    } else {
+        cost[y * a.w + x] = patch_cost<STRIDE, false>(A, B, a.pw, x, y, t.x, t.y, lut, s_census);
+    }
 }
 
 // Segment propagation, the four passes of baoSegPropagate.  DIR: 0 row forward, 1 column forward, 2 row reverse,
@@ -301,7 +316,7 @@ struct PropGeom {
 
 template <int DIR>
 __global__ void __launch_bounds__(256) k_prop_decide(PmArgs a, PropGeom g, int seg_len, int t, short2* __restrict__ st_prev, int4* __restrict__ queue,
-                                                     int* __restrict__ counter) {
+                                                     int* __restrict__ counter, int4* __restrict__ memo) {
     constexpr bool ROW = (DIR == 0 || DIR == 2), FWD = (DIR < 2);
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     bool need = false;
@@ -333,7 +348,23 @@ __global__ void __launch_bounds__(256) k_prop_decide(PmArgs a, PropGeom g, int s
             st_prev[gid] = prev;   // a skipped candidate equals the current target; an evaluated one is settled by k_prop_eval
             // a candidate equal to the current target would be scored by the evaluation that produced cost[id]: never '<'
             need = !(prev.x == cur.x && prev.y == cur.y);
-            item = make_int4(z, x1 | (y1 << 16), (int)(unsigned short)prev.x | ((int)prev.y << 16), gid);
+            const int cand = (int)(unsigned short)prev.x | ((int)prev.y << 16);
+            if (need && memo) {
+                // A candidate this pixel has ALREADY scored can never win again: the cost of a (pixel, target) pair is a pure function of the
+                // images, and the pixel's own cost only ever decreases, so `cv < cost` was false or made cost == cv then and is false now.
+                // The memo keeps the last candidate scored at this pixel per pass direction (the same neighbour keeps proposing the same
+                // target once the field has settled); a hit is the reference's outcome -- rejected, chain continues with the pixel's own
+                // target -- without the 100 samples.
+                int4* mp = memo + ((size_t)z * a.w * a.h + (size_t)y1 * a.w + x1);
+                const int4 m = *mp;
+                if (m.x == cand || m.y == cand || m.z == cand || m.w == cand) {
+                    need = false;
+                    st_prev[gid] = cur;
+                } else {
+                    reinterpret_cast<int*>(mp)[DIR] = cand;
+                }
+            }
+            item = make_int4(z, x1 | (y1 << 16), cand, gid);
         }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, need);
@@ -346,7 +377,7 @@ __global__ void __launch_bounds__(256) k_prop_decide(PmArgs a, PropGeom g, int s
     }
 }
 
-template <int DIR, int STRIDE>
+template <int DIR, int STRIDE, bool USEQ>
 __global__ void __launch_bounds__(128) k_prop_eval(PmArgs a, const int4* __restrict__ queue, const int* __restrict__ counter, short2* __restrict__ st_prev,
                                                    const __grid_constant__ CostLut lut) {
     constexpr bool ROW = (DIR == 0 || DIR == 2);
@@ -360,7 +391,15 @@ __global__ void __launch_bounds__(128) k_prop_eval(PmArgs a, const int4* __restr
         pm_select<ROW>(a, it.x, A, B, nnf, cost);
         const int x1 = it.y & 0xffff, y1 = it.y >> 16;
         const short2 cand = make_short2((short)(it.z & 0xffff), (short)(it.z >> 16));
-        const float cv = patch_cost<STRIDE, ROW>(A, B, pitch, x1, y1, cand.x, cand.y, lut, s_census);
+        float cv;
+        if (STRIDE == 2 && USEQ) {
+            const float4 *A0, *B0, *QA, *QB; short2* n0; float* c0;
+            pm_select<false>(a, it.x, A0, B0, n0, c0);
+            pm_select_q(a, it.x, QA, QB);
+            cv = patch_cost_q(A0, B0, QA, QB, a.qg, a.pw, x1, y1, cand.x, cand.y, lut, s_census);
+        } else {
+            cv = patch_cost<STRIDE, ROW>(A, B, pitch, x1, y1, cand.x, cand.y, lut, s_census);
+        }
         const int id = y1 * a.w + x1;
         if (cv < cost[id]) {
             nnf[id] = cand;
@@ -368,6 +407,331 @@ __global__ void __launch_bounds__(128) k_prop_eval(PmArgs a, const int4* __restr
         } else {
             st_prev[it.w] = nnf[id];
         }
+    }
+}
+
+// ---- warp-cooperative evaluation (default of the queue's scoring kernel and of the random search) ----
+// A thread-per-evaluation kernel gathers 32 unrelated 19x19 windows per load: every lane hits a different cache line on both image
+// sides (k_prop_eval: L1 hit rate 12 %, 53 % of the LSU wavefront peak at 27 % resident warps; the search spends one L1 wavefront per
+// lane per sample).  Here the WARP scores one evaluation at a time: lane l takes samples l, l+32, l+64, ... of the patch, so a load
+// covers ~3 sample rows of ONE window (10 samples of a row lie within 304 bytes: 3 lines instead of 10) and neighbouring evaluations
+// share lines through L1.  Every sample's (cost, weight) goes to shared memory; after BATCH evaluations lane k adds up evaluation k
+// IN SAMPLE ORDER (i outer, j inner, cs = fma(cost, w, cs), ws += w: bao_pmflow_kernel.cu:274-296), which is the reference's
+// accumulation order and therefore its bits.  The serial sum costs 3 instructions per sample for BATCH evaluations at once.
+template <int STRIDE>
+struct Coop {
+    static constexpr int NJ = (2 * PATCH_R) / STRIDE + 1;
+    static constexpr int NS = NJ * NJ;            // samples per evaluation (100 at stride 2)
+    static constexpr int NSP = NS | 1;            // odd pitch (in float2) of an evaluation in shared memory: the 8-byte reads of the serial sums fall in distinct banks
+    static constexpr int R = (NS + 31) / 32;      // rounds of 32 samples
+};
+
+// per-lane sample sites: sample s = lane + 32 r lies at (i, j) = (-9 + STRIDE * (s / NJ), -9 + STRIDE * (s % NJ))
+template <int STRIDE>
+__device__ __forceinline__ void coop_sites(int lane, int pw, const CostLut& lut, int (&soff)[Coop<STRIDE>::R], float (&sgg)[Coop<STRIDE>::R]) {
+    typedef Coop<STRIDE> C;
+#pragma unroll
+    for (int r = 0; r < C::R; r++) {
+        int s = lane + 32 * r;
+        if (s >= C::NS) s = C::NS - 1;   // lanes past the last sample score a valid site and do not store
+        const int i = -PATCH_R + STRIDE * (s / C::NJ), j = -PATCH_R + STRIDE * (s % C::NJ);
+        soff[r] = i * pw + j;
+        sgg[r] = lut.gg[i < 0 ? -i : i][j < 0 ? -j : j];
+    }
+}
+
+// image-1 side of an evaluation, per lane: the R samples of the source patch and their range distances to its centre
+template <int STRIDE>
+struct CoopSrc {
+    float4 p1[Coop<STRIDE>::R];
+    float d1[Coop<STRIDE>::R];
+};
+template <int STRIDE>
+__device__ __forceinline__ void coop_load_src(CoopSrc<STRIDE>& S, const float4* __restrict__ A, unsigned oa, const int (&soff)[Coop<STRIDE>::R]) {
+    const PixPk c1k = pack_pix(ldpix(A + oa));
+#pragma unroll
+    for (int r = 0; r < Coop<STRIDE>::R; r++) S.p1[r] = ldpix(A + (oa + (unsigned)soff[r]));
+#pragma unroll
+    for (int r = 0; r < Coop<STRIDE>::R; r++) S.d1[r] = max3abs_diff(c1k, pack_pix(S.p1[r]));
+}
+// the lane's samples of ONE evaluation against target offset ob, written to `slot`
+template <int STRIDE>
+__device__ __forceinline__ void coop_score(const CoopSrc<STRIDE>& S, const float4* __restrict__ B, unsigned ob, const int (&soff)[Coop<STRIDE>::R],
+                                           const float (&sgg)[Coop<STRIDE>::R], unsigned lut_base, int lane, float2* __restrict__ slot) {
+    typedef Coop<STRIDE> C;
+    const PixPk c2k = pack_pix(ldpix(B + ob));
+    float4 p2[C::R];
+#pragma unroll
+    for (int r = 0; r < C::R; r++) p2[r] = ldpix(B + (ob + (unsigned)soff[r]));
+    float ct[C::R], t2[C::R], w[C::R];
+    float tmin = 0.f;
+#pragma unroll
+    for (int r = 0; r < C::R; r++) {
+        sample_eval(S.p1[r], pack_pix(S.p1[r]), p2[r], c2k, S.d1[r], lut_base, ct[r], t2[r]);
+        w[r] = __fmul_rn(ex2_mufu(t2[r]), sgg[r]);
+        tmin = fminf(tmin, t2[r]);
+    }
+    if (tmin < -126.0f) {   // the rare __expf fix-up, one test for the lane's samples (see sample_group)
+#pragma unroll
+        for (int r = 0; r < C::R; r++)
+            if (t2[r] < -126.0f) w[r] = __fmul_rn(ex2_tiny(t2[r]), sgg[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < C::R; r++)
+        if ((r + 1) * 32 <= C::NS || lane + 32 * r < C::NS) slot[lane + 32 * r] = make_float2(ct[r], w[r]);
+}
+// the serial sum of one evaluation (the owner lane): the reference's accumulation order
+template <int STRIDE>
+__device__ __forceinline__ float coop_sum(const float2* __restrict__ slot) {
+    float cs = 0.f, ws = 0.f;
+#pragma unroll 10
+    for (int s = 0; s < Coop<STRIDE>::NS; s++) {
+        const float2 v = slot[s];
+        cs = __fmaf_rn(v.x, v.y, cs);
+        ws = __fadd_rn(ws, v.y);
+    }
+    return __fdiv_rn(cs, ws);
+}
+
+// k_prop_eval with warp-cooperative scoring: a warp takes BATCH consecutive queue items
+template <int STRIDE, int BATCH, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_prop_eval_w(PmArgs a, const int4* __restrict__ queue, const int* __restrict__ counter, short2* __restrict__ st_prev,
+                                                           const __grid_constant__ CostLut lut) {
+    typedef Coop<STRIDE> C;
+    __shared__ float s_census[CENSUS_LUT_N];
+    extern __shared__ float2 s_val_dyn[];   // [WARPS][BATCH][NSP]
+    load_census_lut(s_census, lut);
+    const unsigned lut_base = census_lut_base(s_census);
+    const int n = *counter;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* s_val = s_val_dyn + (size_t)warp * BATCH * C::NSP;
+    int soff[C::R];
+    float sgg[C::R];
+    coop_sites<STRIDE>(lane, a.pw, lut, soff, sgg);
+    for (int base = (blockIdx.x * WARPS + warp) * BATCH; base < n; base += gridDim.x * WARPS * BATCH) {
+        const int cnt = min(BATCH, n - base);
+        int4 it = make_int4(0, 0, 0, 0);
+        if (lane < cnt) it = queue[base + lane];
+        for (int k = 0; k < cnt; k++) {
+            const int z = __shfl_sync(0xffffffffu, it.x, k), pos = __shfl_sync(0xffffffffu, it.y, k), cand = __shfl_sync(0xffffffffu, it.z, k);
+            const float4 *A, *B; short2* nnf; float* cost;
+            pm_select<false>(a, z, A, B, nnf, cost);
+            const unsigned oa = (unsigned)((pos & 0xffff) + PAD) + (unsigned)((pos >> 16) + PAD) * (unsigned)a.pw;
+            const unsigned ob = (unsigned)((short)(cand & 0xffff) + PAD) + (unsigned)((cand >> 16) + PAD) * (unsigned)a.pw;
+            CoopSrc<STRIDE> S;
+            coop_load_src<STRIDE>(S, A, oa, soff);
+            coop_score<STRIDE>(S, B, ob, soff, sgg, lut_base, lane, s_val + k * C::NSP);
+        }
+        __syncwarp();
+        if (lane < cnt) {
+            const float cv = coop_sum<STRIDE>(s_val + lane * C::NSP);
+            const float4 *A, *B; short2* nnf; float* cost;
+            pm_select<false>(a, it.x, A, B, nnf, cost);
+            const int id = (it.y >> 16) * a.w + (it.y & 0xffff);
+            if (cv < cost[id]) {
+                nnf[id] = make_short2((short)(it.z & 0xffff), (short)(it.z >> 16));
+                cost[id] = cv;
+            } else {
+                st_prev[it.w] = nnf[id];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Round-major form of k_prop_eval_w (default).  Staging all samples of BATCH evaluations takes 13 KB of shared memory per warp; at
+// four warps per CTA the occupancy limit fills the whole 228 KB carve-out, leaves the L1 cache ~30 KB and the kernel waits on L2
+// (measured slower than the thread-per-evaluation kernel).  Here a warp walks its BATCH items once per ROUND of 32 samples: stage
+// (cost, weight) of that round only (BATCH x 33 float2 = 4 KB per warp), the owner lanes fold the 32 samples into their running
+// (cost_sum, weight_sum) registers -- still sample order -- and the next round reuses the buffer.  The loads of U items are issued
+// together (4 x U 16-byte loads in flight per lane).  The samples past the last full round (4 of 100 at stride 2) are scored for
+// 32 / 4 items at once, lane l = (item l / 4, sample l % 4), instead of a round with 28 idle lanes per item.
+template <int STRIDE, int BATCH, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_prop_eval_r(PmArgs a, const int4* __restrict__ queue, const int* __restrict__ counter, short2* __restrict__ st_prev,
+                                                           const __grid_constant__ CostLut lut) {
+    typedef Coop<STRIDE> C;
+    constexpr int RF = C::NS / 32;             // full rounds
+    constexpr int TS = C::NS - 32 * RF;        // samples of the tail
+    constexpr int IPP = TS > 0 ? 32 / TS : 1;  // items per tail pass
+    constexpr int U = 4;
+    constexpr int PITCH = 33;
+    __shared__ float s_census[CENSUS_LUT_N];
+    __shared__ float2 s_stage[WARPS][BATCH][PITCH];
+    load_census_lut(s_census, lut);
+    const unsigned lut_base = census_lut_base(s_census);
+    const int n = *counter;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2 (*stage)[PITCH] = s_stage[warp];
+    int soff[C::R];
+    float sgg[C::R];
+    coop_sites<STRIDE>(lane, a.pw, lut, soff, sgg);
+    // tail site of this lane: sample 32 RF + lane % TS
+    int toff = 0;
+    float tgg = 0.f;
+    if (TS > 0) {
+        const int s = 32 * RF + lane % (TS > 0 ? TS : 1);
+        const int i = -PATCH_R + STRIDE * (s / C::NJ), j = -PATCH_R + STRIDE * (s % C::NJ);
+        toff = i * a.pw + j;
+        tgg = lut.gg[i < 0 ? -i : i][j < 0 ? -j : j];
+    }
+    for (int base = (blockIdx.x * WARPS + warp) * BATCH; base < n; base += gridDim.x * WARPS * BATCH) {
+        const int cnt = min(BATCH, n - base);
+        int4 it = make_int4(0, 0, 0, 0);
+        if (lane < cnt) it = queue[base + lane];
+        float cs = 0.f, ws = 0.f;
+#pragma unroll
+        for (int r = 0; r < RF; r++) {
+            for (int k0 = 0; k0 < cnt; k0 += U) {
+                float4 c1[U], c2[U], p1[U], p2[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int k = min(k0 + u, cnt - 1);   // past the end: the last item again (same values to the same slot)
+                    const int z = __shfl_sync(0xffffffffu, it.x, k), pos = __shfl_sync(0xffffffffu, it.y, k), cand = __shfl_sync(0xffffffffu, it.z, k);
+                    const float4 *A, *B; short2* nnf; float* cost;
+                    pm_select<false>(a, z, A, B, nnf, cost);
+                    const unsigned oa = (unsigned)((pos & 0xffff) + PAD) + (unsigned)((pos >> 16) + PAD) * (unsigned)a.pw;
+                    const unsigned ob = (unsigned)((short)(cand & 0xffff) + PAD) + (unsigned)((cand >> 16) + PAD) * (unsigned)a.pw;
+                    c1[u] = ldpix(A + oa);
+                    c2[u] = ldpix(B + ob);
+                    p1[u] = ldpix(A + (oa + (unsigned)soff[r]));
+                    p2[u] = ldpix(B + (ob + (unsigned)soff[r]));
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int k = min(k0 + u, cnt - 1);
+                    const PixPk p1k = pack_pix(p1[u]);
+                    float ct, t2;
+                    sample_eval(p1[u], p1k, p2[u], pack_pix(c2[u]), max3abs_diff(pack_pix(c1[u]), p1k), lut_base, ct, t2);
+                    float w = __fmul_rn(ex2_mufu(t2), sgg[r]);
+                    if (t2 < -126.0f) w = __fmul_rn(ex2_tiny(t2), sgg[r]);
+                    stage[k][lane] = make_float2(ct, w);
+                }
+            }
+            __syncwarp();
+            if (lane < cnt) {
+#pragma unroll 8
+                for (int s = 0; s < 32; s++) {
+                    const float2 v = stage[lane][s];
+                    cs = __fmaf_rn(v.x, v.y, cs);
+                    ws = __fadd_rn(ws, v.y);
+                }
+            }
+            __syncwarp();
+        }
+        if (TS > 0) {
+            for (int g0 = 0; g0 < cnt; g0 += IPP) {
+                const int ki = g0 + lane / TS;
+                const bool valid = lane < IPP * TS && ki < cnt;
+                const int src = min(ki, cnt - 1);
+                const int z = __shfl_sync(0xffffffffu, it.x, src), pos = __shfl_sync(0xffffffffu, it.y, src), cand = __shfl_sync(0xffffffffu, it.z, src);
+                const float4 *A, *B; short2* nnf; float* cost;
+                pm_select<false>(a, z, A, B, nnf, cost);
+                const unsigned oa = (unsigned)((pos & 0xffff) + PAD) + (unsigned)((pos >> 16) + PAD) * (unsigned)a.pw;
+                const unsigned ob = (unsigned)((short)(cand & 0xffff) + PAD) + (unsigned)((cand >> 16) + PAD) * (unsigned)a.pw;
+                const float4 c1 = ldpix(A + oa), c2 = ldpix(B + ob), p1 = ldpix(A + (oa + (unsigned)toff)), p2 = ldpix(B + (ob + (unsigned)toff));
+                const PixPk p1k = pack_pix(p1);
+                float ct, t2;
+                sample_eval(p1, p1k, p2, pack_pix(c2), max3abs_diff(pack_pix(c1), p1k), lut_base, ct, t2);
+                float w = __fmul_rn(ex2_mufu(t2), tgg);
+                if (t2 < -126.0f) w = __fmul_rn(ex2_tiny(t2), tgg);
+                if (valid) stage[ki][lane % TS] = make_float2(ct, w);
+            }
+            __syncwarp();
+            if (lane < cnt) {
+#pragma unroll
+                for (int s = 0; s < TS; s++) {
+                    const float2 v = stage[lane][s];
+                    cs = __fmaf_rn(v.x, v.y, cs);
+                    ws = __fadd_rn(ws, v.y);
+                }
+            }
+        }
+        if (lane < cnt) {
+            const float cv = __fdiv_rn(cs, ws);
+            const float4 *A, *B; short2* nnf; float* cost;
+            pm_select<false>(a, it.x, A, B, nnf, cost);
+            const int id = (it.y >> 16) * a.w + (it.y & 0xffff);
+            if (cv < cost[id]) {
+                nnf[id] = make_short2((short)(it.z & 0xffff), (short)(it.z >> 16));
+                cost[id] = cv;
+            } else {
+                st_prev[it.w] = nnf[id];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Random search, warp-cooperative: a warp owns PIX consecutive pixels of a row and scores their PIX * NG guesses one after the
+// other (the image-1 side of a pixel's samples is loaded once for its NG guesses); lane q = (pixel q / NG, guess q % NG) then adds
+// up evaluation q in sample order, and the guesses of a pixel are compared in their order with strict '<' (:1577).
+template <int STRIDE, int NG, int PIX, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_pm_search_w(PmArgs a, const short2* __restrict__ rng, int search_range, int radius_min,
+                                                           const __grid_constant__ CostLut lut) {
+    typedef Coop<STRIDE> C;
+    static_assert(PIX * NG <= 32, "one lane per (pixel, guess)");
+    __shared__ float s_census[CENSUS_LUT_N];
+    extern __shared__ float2 s_val_dyn[];   // [WARPS][PIX * NG][NSP]
+    load_census_lut(s_census, lut);
+    const unsigned lut_base = census_lut_base(s_census);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* s_val = s_val_dyn + (size_t)warp * (PIX * NG) * C::NSP;
+    const int x0 = (blockIdx.x * WARPS + warp) * PIX, y = a.y0 + blockIdx.y;
+    if (x0 >= a.w) return;   // whole warps only; nothing below synchronises across warps
+    const float4 *A, *B; short2* nnf; float* cost;
+    pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
+    int soff[C::R];
+    float sgg[C::R];
+    coop_sites<STRIDE>(lane, a.pw, lut, soff, sgg);
+    // lane q: its pixel, its guess
+    const int qp = lane / NG, qk = lane - qp * NG;
+    const int x = x0 + qp;
+    const bool mine = lane < PIX * NG && x < a.w;
+    const int id = y * a.w + min(x, a.w - 1);
+    const short2 entry = nnf[id];
+    int cand = 0;
+    {
+        int mag = search_range;
+        for (int k = 0; k < qk; k++)
+            if (mag / 2 >= radius_min) mag /= 2;
+        const short2 rr = rng[(size_t)qk * a.w * a.h + id];
+        const unsigned r1 = (unsigned)(int)rr.x, r2 = (unsigned)(int)rr.y;   // :1557-1563
+        const short xmin = (short)max(entry.x - mag, 0), xmax = (short)min(entry.x + mag + 1, a.w + 1);
+        const short ymin = (short)max(entry.y - mag, 0), ymax = (short)min(entry.y + mag + 1, a.h + 1);
+        const short gx = (short)(xmin + r1 % (unsigned)(xmax - xmin));
+        const short gy = (short)(ymin + r2 % (unsigned)(ymax - ymin));
+        cand = (int)(unsigned short)gx | ((int)gy << 16);
+    }
+    const int npix = min(PIX, a.w - x0);
+    CoopSrc<STRIDE> S;
+    for (int q = 0; q < npix * NG; q++) {
+        if (q % NG == 0) {
+            const unsigned oa = (unsigned)(x0 + q / NG + PAD) + (unsigned)(y + PAD) * (unsigned)a.pw;
+            coop_load_src<STRIDE>(S, A, oa, soff);
+        }
+        const int ec = __shfl_sync(0xffffffffu, cand, q);
+        const unsigned ob = (unsigned)((short)(ec & 0xffff) + PAD) + (unsigned)((ec >> 16) + PAD) * (unsigned)a.pw;
+        coop_score<STRIDE>(S, B, ob, soff, sgg, lut_base, lane, s_val + q * C::NSP);
+    }
+    __syncwarp();
+    float cv = 0.f;
+    if (mine) cv = coop_sum<STRIDE>(s_val + lane * C::NSP);
+    // the guesses of a pixel in their order (every lane of the pixel follows the scan; the lane of guess 0 stores)
+    int best = (int)(unsigned short)entry.x | ((int)entry.y << 16);
+    float best_cost = cost[id];
+#pragma unroll
+    for (int k = 0; k < NG; k++) {
+        const int src = min(qp * NG + k, 31);
+        const float cvk = __shfl_sync(0xffffffffu, cv, src);
+        const int ck = __shfl_sync(0xffffffffu, cand, src);
+        if (cvk < best_cost) {
+            best = ck;
+            best_cost = cvk;
+        }
+    }
+    if (mine && qk == 0) {
+        nnf[id] = make_short2((short)(best & 0xffff), (short)(best >> 16));
+        cost[id] = best_cost;
     }
 }
 
@@ -388,9 +752,27 @@ static void launch_propagate_queue(eppm_context* c, const PmArgs& a, int n, int 
     // they drain, which balances better than a capped grid striding over the queue: 5.06 -> 5.01 ms per 1080p pair); EPPM_PROP_EVAL_CAP = CTAs per SM
     static const int cap = getenv("EPPM_PROP_EVAL_CAP") ? atoi(getenv("EPPM_PROP_EVAL_CAP")) : 0;
     const int eval_blocks = cap > 0 ? min((g.total + 127) / 128, c->n_sm * cap) : (g.total + 127) / 128;
+    // warp-cooperative scoring: round-major (default) or whole evaluations staged (EPPM_VAR_PROP_WARP_FULL)
+    constexpr int WB = STRIDE == 1 ? 4 : 16, WW = 4;
+    constexpr int RB = 16, RW = 4;
+    const size_t wsmem = (size_t)WW * WB * Coop<STRIDE>::NSP * sizeof(float2);
+    static bool attr_w[64] = {};
+    const int mode = (c->variant & EPPM_VAR_PROP_THREAD) ? 0 : (c->variant & EPPM_VAR_PROP_WARP_FULL) ? 1 : 2;
+    if (mode && (c->device < 0 || c->device >= 64 || !attr_w[c->device])) {
+        cudaFuncSetAttribute(k_prop_eval_w<STRIDE, WB, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+        // leave the larger part of the unified L1 / shared memory to the cache: the patch windows of neighbouring queue items overlap
+        static const int carve = getenv("EPPM_PROP_CARVEOUT") ? atoi(getenv("EPPM_PROP_CARVEOUT")) : 40;
+        cudaFuncSetAttribute(k_prop_eval_r<STRIDE, RB, RW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (c->device >= 0 && c->device < 64) attr_w[c->device] = true;
+    }
+    const int wblocks = (g.total + WB * WW - 1) / (WB * WW), rblocks = (g.total + RB * RW - 1) / (RB * RW);
     for (int t = 1; t <= sl; t++) {
-        k_prop_decide<DIR><<<(g.total + 255) / 256, 256, 0, c->stream>>>(a, g, sl, t, c->prop_prev, c->prop_queue, counters + t - 1);
-        k_prop_eval<DIR, STRIDE><<<eval_blocks, 128, 0, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
+        k_prop_decide<DIR><<<(g.total + 255) / 256, 256, 0, c->stream>>>(a, g, sl, t, c->prop_prev, c->prop_queue, counters + t - 1,
+                                                                         (c->variant & EPPM_VAR_PROP_NOMEMO) ? nullptr : c->prop_memo);
+        if (mode == 2) k_prop_eval_r<STRIDE, RB, RW><<<rblocks, RW * 32, 0, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
+        else if (mode == 1) k_prop_eval_w<STRIDE, WB, WW><<<wblocks, WW * 32, wsmem, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
+        else if (STRIDE == 2 && a.q[0]) k_prop_eval<DIR, STRIDE, true><<<eval_blocks, 128, 0, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
+        else k_prop_eval<DIR, STRIDE, false><<<eval_blocks, 128, 0, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
     }
     EPPM_LAUNCH_COUNT(2 * sl);
 }
@@ -749,6 +1131,114 @@ __global__ void __launch_bounds__(128, MINB) k_pm_search_joint(PmArgs a, const s
     cost[id] = best_cost;
 }
 
+// k_pm_search_joint at sample stride 2 on the parity-split (Q) planes: the image-1 side and the LSU-path guesses read TWO neighbouring
+// samples of a patch row per 256-bit load (half the L1 requests of a kernel that is bound by them: 84 % of the L1 throughput, 46 % of the
+// issue slots with 16-byte loads).  Everything else -- guesses, sample order, packed guess pairs, fix-up grouping, strict '<' -- is
+// k_pm_search_joint's.
+template <int NTEX, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_pm_search_q(PmArgs a, const short2* __restrict__ rng, int search_range, int radius_min,
+                                                          const __grid_constant__ CostLut lut) {
+    constexpr int NG = 6;
+    __shared__ float s_census[CENSUS_LUT_N];
+    load_census_lut(s_census, lut);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y;
+    if (x >= a.w) return;
+    const float4 *A, *B; short2* nnf; float* cost;
+    pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
+    const float4 *QA, *QB;
+    pm_select_q(a, blockIdx.z, QA, QB);
+    const unsigned lut_base = census_lut_base(s_census);
+    const int zdir = a.n_dirs == 2 ? (blockIdx.z & 1) : 0, zb = a.n_dirs == 2 ? (blockIdx.z >> 1) : blockIdx.z;
+    const cudaTextureObject_t texB = zdir ? a.tex[0] : a.tex[1];
+    const unsigned tb = (zdir ? a.tex_off[0] : a.tex_off[1]) + (unsigned)zb * a.plane;
+    const int id = y * a.w + x;
+    const short2 entry = nnf[id];
+    const PixPk c1k = pack_pix(ldpix(A + ((unsigned)(x + PAD) + (unsigned)(y + PAD) * (unsigned)a.pw)));
+    unsigned ea = q_patch_origin(a.qg, x, y);
+    short2 best = entry;
+    float best_cost = cost[id];
+    int mag = search_range;
+    short gx[NG], gy[NG];
+    unsigned eb[NG];      // Q origin of the guess's patch (LSU path) or, for the texture-path guesses, the packed-plane offset of its top-left sample
+    PixPk c2k[NG];
+#pragma unroll
+    for (int k = 0; k < NG; k++) {
+        const short2 rr = rng[(size_t)k * a.w * a.h + id];
+        const unsigned r1 = (unsigned)(int)rr.x, r2 = (unsigned)(int)rr.y;   // :1557-1563
+        const short xmin = (short)max(entry.x - mag, 0), xmax = (short)min(entry.x + mag + 1, a.w + 1);
+        const short ymin = (short)max(entry.y - mag, 0), ymax = (short)min(entry.y + mag + 1, a.h + 1);
+        gx[k] = (short)(xmin + r1 % (unsigned)(xmax - xmin));
+        gy[k] = (short)(ymin + r2 % (unsigned)(ymax - ymin));
+        if (mag / 2 >= radius_min) mag /= 2;
+        const unsigned ob = (unsigned)(gx[k] + PAD) + (unsigned)(gy[k] + PAD) * (unsigned)a.pw;
+        c2k[k] = pack_pix(ldpix(B + ob));
+        eb[k] = k < NTEX ? tb + ob - (unsigned)(PATCH_R * a.pw + PATCH_R) : q_patch_origin(a.qg, gx[k], gy[k]);
+    }
+    f32x2 cs[NG / 2], ws[NG / 2];
+#pragma unroll
+    for (int h = 0; h < NG / 2; h++) cs[h] = ws[h] = pk2(0.f, 0.f);
+#pragma unroll 1
+    for (int i = 0; i < 10; i++) {
+        const int ai = i < 5 ? 9 - 2 * i : 2 * i - 9;
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+            const Pix2 P1 = ldpix2(QA + (ea + 2u * m));
+            Pix2 P2[NG];
+#pragma unroll
+            for (int k = 0; k < NG; k++) {
+                if (k < NTEX) {
+                    P2[k].a = texpix(texB, eb[k] + 4u * m);
+                    P2[k].b = texpix(texB, eb[k] + 4u * m + 2u);
+                } else {
+                    P2[k] = ldpix2(QB + (eb[k] + 2u * m));
+                }
+            }
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const float4 p1 = half ? P1.b : P1.a;
+                const PixPk p1k = pack_pix(p1);
+                const float d1s = max3abs_diff(c1k, p1k);
+                const f32x2 d1 = pk2(d1s, d1s);
+                const int aj = half ? (2 * m + 1 < 5 ? 7 - 4 * m : 4 * m - 7) : (2 * m < 5 ? 9 - 4 * m : 4 * m - 9);
+                const float gg = lut.gg[ai][aj];
+                f32x2 ct[NG / 2], t2[NG / 2], w[NG / 2];
+#pragma unroll
+                for (int h = 0; h < NG / 2; h++) {
+                    const float4 p2a = half ? P2[2 * h].b : P2[2 * h].a, p2b = half ? P2[2 * h + 1].b : P2[2 * h + 1].a;
+                    sample_eval2(p1, p1k, p1, p1k, p2a, p2b, c2k[2 * h], c2k[2 * h + 1], d1, lut_base, ct[h], t2[h]);
+                }
+                sample_weight4(t2[0], t2[1], gg, w[0], w[1]);
+                w[2] = sample_weight2(t2[2], gg, gg);
+#pragma unroll
+                for (int h = 0; h < NG / 2; h++) {
+                    cs[h] = fma2(ct[h], w[h], cs[h]);
+                    ws[h] = add2(ws[h], w[h]);
+                }
+            }
+        }
+        ea += a.qg.qp;
+#pragma unroll
+        for (int k = 0; k < NG; k++) eb[k] += k < NTEX ? 2u * (unsigned)a.pw : (unsigned)a.qg.qp;
+    }
+#pragma unroll
+    for (int h = 0; h < NG / 2; h++) {   // guesses in their order with strict '<' (:1577)
+        float c0, c1, w0, w1;
+        upk2(cs[h], c0, c1);
+        upk2(ws[h], w0, w1);
+        const float cv0 = __fdiv_rn(c0, w0), cv1 = __fdiv_rn(c1, w1);
+        if (cv0 < best_cost) {
+            best = make_short2(gx[2 * h], gy[2 * h]);
+            best_cost = cv0;
+        }
+        if (cv1 < best_cost) {
+            best = make_short2(gx[2 * h + 1], gy[2 * h + 1]);
+            best_cost = cv1;
+        }
+    }
+    nnf[id] = best;
+    cost[id] = best_cost;
+}
+
 template <int DIR, int STRIDE>
 static void launch_propagate(eppm_context* c, const PmArgs& a, int n) {
     const bool row = (DIR == 0 || DIR == 2);
@@ -953,6 +1443,10 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
     a.pix[1] = c->pix[1][L];
     a.pixT[0] = c->pixT[0];
     a.pixT[1] = c->pixT[1];
+    const bool use_q = STRIDE == 2 && !(c->variant & EPPM_VAR_PM_NOQ);
+    a.q[0] = use_q ? c->pixQ[0] : nullptr;
+    a.q[1] = use_q ? c->pixQ[1] : nullptr;
+    a.qg = make_qgeom(g.pw, g.ph);
     a.plane = (unsigned)g.plane;
     a.pw = g.pw; a.ph = g.ph;
     a.nnf[0] = c->nnf[0]; a.nnf[1] = c->nnf[1];
@@ -978,6 +1472,8 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
     if (run()) {
         k_pm_init<STRIDE><<<grd, blk, 0, c->stream>>>(a, c->rng_init, c->cost_lut);
         EPPM_LAUNCH_COUNT(1);
+        // the evaluated-candidate memo of the propagation starts empty (-1 is no target: targets lie in [0, w] x [0, h])
+        cudaMemsetAsync(c->prop_memo, 0xff, (size_t)2 * n * g.w * g.h * sizeof(int4), c->stream);
     }
     for (int it = 0; it < c->prm.num_iter && step < n_steps; it++) {
         if (c->variant & (EPPM_VAR_PROP_NOSKIP | EPPM_VAR_PROP_NOCOMPACT | EPPM_VAR_PROP_CTA)) {
@@ -985,7 +1481,7 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
             if (run()) launch_propagate<1, STRIDE>(c, a, n);
             if (run()) launch_propagate<2, STRIDE>(c, a, n);
             if (run()) launch_propagate<3, STRIDE>(c, a, n);
-        } else if (!(c->variant & EPPM_VAR_PROP_QUEUE)) {
+        } else if (c->variant & EPPM_VAR_PROP_CHAIN) {
             if (run()) launch_propagate_chain<0, STRIDE>(c, a, n);
             if (run()) launch_propagate_chain<1, STRIDE>(c, a, n);
             if (run()) launch_propagate_chain<2, STRIDE>(c, a, n);
@@ -1001,6 +1497,29 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
         const bool tex_ok = a.tex[0] && a.tex[1];
         const int v = c->variant;
         const bool joint = c->prm.num_rand_guess == 6 && !(v & EPPM_VAR_SEARCH_SERIAL);
+        if (joint && (v & EPPM_VAR_SEARCH_WARP)) {
+            // warp-cooperative search (measured slower than one thread per pixel: 8.98 vs 5.26 ms per pair of PatchMatch): 4 pixels x 6 guesses per warp at strides 2 and 3, 1 pixel at stride 1 (361 samples per evaluation)
+            constexpr int SP = STRIDE == 1 ? 1 : 4, SW = 2;
+            const size_t ssmem = (size_t)SW * SP * 6 * Coop<STRIDE>::NSP * sizeof(float2);
+            static bool attr_s[64] = {};
+            if (c->device < 0 || c->device >= 64 || !attr_s[c->device]) {
+                cudaFuncSetAttribute(k_pm_search_w<STRIDE, 6, SP, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+                if (c->device >= 0 && c->device < 64) attr_s[c->device] = true;
+            }
+            dim3 sgrd((g.w + SP * SW - 1) / (SP * SW), a.y1 - a.y0, n_dirs * n);
+            k_pm_search_w<STRIDE, 6, SP, SW><<<sgrd, SW * 32, ssmem, c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut);
+            EPPM_LAUNCH_COUNT(1);
+            continue;
+        }
+        if (joint && STRIDE == 2 && a.q[0]) {
+            static const int qtex = getenv("EPPM_SEARCH_QTEX") ? atoi(getenv("EPPM_SEARCH_QTEX")) : 0;   // tuning knob: guesses on the texture path
+            const int nt = tex_ok ? qtex : 0;
+            if (nt >= 2) k_pm_search_q<2, 4><<<grd, blk, 0, c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut);
+            else if (nt == 1) k_pm_search_q<1, 4><<<grd, blk, 0, c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut);
+            else k_pm_search_q<0, 4><<<grd, blk, 0, c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut);
+            EPPM_LAUNCH_COUNT(1);
+            continue;
+        }
 #define EPPM_SEARCH(NT, NS, MB) k_pm_search_joint<STRIDE, 6, NT, NS, MB><<<grd, blk, 0, c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut)
         if (joint && ((v & EPPM_VAR_SEARCH_NOTEX) || !tex_ok)) EPPM_SEARCH(0, 1, 4);
         else if (joint && (v & EPPM_VAR_SEARCH_TEX3)) EPPM_SEARCH(3, 1, 4);

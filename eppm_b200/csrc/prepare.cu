@@ -270,6 +270,23 @@ __global__ void __launch_bounds__(256) k_transpose_plane(const float4* __restric
     if (x < pw && y < ph) dst[off + (size_t)x * ph + y] = tile[threadIdx.x][threadIdx.y];
 }
 
+// Q planes (eppm_device.cuh): every padded pixel goes to its parity sub-plane, in both copies
+__global__ void __launch_bounds__(256) k_split_plane(const float4* __restrict__ src, float4* __restrict__ dst, int pw, int ph, QGeom q) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= pw || y >= ph) return;
+    const float4 v = src[(size_t)blockIdx.z * pw * ph + (size_t)y * pw + x];
+    float4* d = dst + (size_t)blockIdx.z * q.plane;
+    const unsigned e = q_index(q, x, y);
+    d[e] = v;
+    d[e + q.c1] = v;
+}
+
+void op_split_plane(cudaStream_t s, const float4* src, float4* dst, const LevelGeom& g, int n_img) {
+    dim3 blk(32, 8), grd((g.pw + 31) / 32, (g.ph + 7) / 8, n_img);
+    k_split_plane<<<grd, blk, 0, s>>>(src, dst, g.pw, g.ph, make_qgeom(g.pw, g.ph));
+    EPPM_LAUNCH_COUNT(1);
+}
+
 void op_transpose_plane(cudaStream_t s, const float4* src, float4* dst, const LevelGeom& g, int n_img) {
     dim3 blk(16, 16), grd((g.pw + 15) / 16, (g.ph + 15) / 16, n_img);
     k_transpose_plane<<<grd, blk, 0, s>>>(src, dst, g.pw, g.ph);
@@ -337,6 +354,7 @@ void op_pyramid_and_pack(eppm_context* c, int n, int two) {
     }
     const int L = c->n_levels - 1;
     for (int img = 0; img < two; img++) op_transpose_plane(s, c->pix[img][L], c->pixT[img], c->lv[L], n);
+    for (int img = 0; img < two; img++) op_split_plane(s, c->pix[img][L], c->pixQ[img], c->lv[L], n);
 }
 
 }  // namespace eppm

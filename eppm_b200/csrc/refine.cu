@@ -875,9 +875,9 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
             default:
                 if (v & EPPM_VAR_REFINE_NOGROUP) k_c2f_refine_tab<false, 3, RF_MINBLOCKS, 2><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else if (v & EPPM_VAR_REFINE_9WARP3) k_c2f_refine_tab<true, 1, 3, 2><<<grd, blk9, 0, c->stream>>>(a, c->cost_lut, *tabp);
-                else if (v & EPPM_VAR_REFINE_SCALAR) k_c2f_refine_tab<true, 3, RF_TAB2_MINBLOCKS, 2><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else if (v & EPPM_VAR_REFINE_PK_BRANCH) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, false><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
-                else k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, true><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+                else if (v & EPPM_VAR_REFINE_PK) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, true><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+                else k_c2f_refine_tab<true, 3, RF_TAB2_MINBLOCKS, 2><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
             }
             EPPM_LAUNCH_COUNT(1);
             return;
@@ -1084,6 +1084,13 @@ void run_c2f_step(eppm_context* c, int level, int kind, float2* out) {
         if (c->profile && level == 0) cudaEventRecord(c->ev_k[0], c->stream);
         op_refine(c, c->pix[0][level], c->pix[1][level], g, c->flow[level + 1], gs.w, gs.h, 1, c->flow_tmp, n, y0, y1);
         if (c->profile && level == 0) cudaEventRecord(c->ev_k[1], c->stream);
+    } else if (c->inplace) {
+        // reference order: the smoothing rewrites the plane it reads (whole level; not combined with spatial tiling)
+        const size_t bytes = (size_t)n * g.w * g.h * sizeof(float2);
+        float2* dst = kind == 1 ? c->flow[level] : (out ? out : c->flow_tmp);
+        const float2* src = kind == 1 ? c->flow_tmp : c->flow[0];
+        cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream);
+        op_smooth_inplace(c, dst, c->pix[0][level], g, n);
     } else if (kind == 1) {
         op_smooth(c, c->flow_tmp, c->flow[level], c->pix[0][level], g, n, y0, y1);
     } else {

@@ -57,7 +57,13 @@ typedef struct eppm_params {
     float blf_sig_r;         /* POSTPROC_BLF_SIG_R 0.02 */
     int rng_mode;            /* EPPM_RNG_XORWOW */
     unsigned long long seed; /* 1234 (bao_pmflow_kernel.cu:68) */
-    int reserved[8];
+    int inplace_filters;     /* 0 (default): outlier removal, weighted median and flow smoothing read a snapshot and write a second
+                                buffer (deterministic).  1: they update IN PLACE with the reference's 16x16 launch geometry and
+                                per-thread raster walk (bao_pmflow_refine_kernel.cu:149-193, 206-286, 764-826), reproducing the
+                                reference's read-while-write race as far as the hardware schedules it the same way; slower, and
+                                like the reference not guaranteed reproducible across GPUs.  EPPM_INPLACE_LEGACY=1 in the
+                                environment forces 1 for every context. */
+    int reserved[7];
 } eppm_params;
 
 typedef struct eppm_context eppm_context; /* opaque; one per (device, h, w, params) */
@@ -92,6 +98,10 @@ int eppm_compute_batch_device(eppm_context* ctx, const uint8_t* d_img1, const ui
  * (frame f -> frame f+1).  Each frame's pyramid, census and packed planes are built once and used by both pairs it belongs to
  * (the reference rebuilds them per pair, bao_flow_patchmatch_multiscale_cuda.cpp:159-168).  n_pairs + 1 <= max_batch. */
 int eppm_compute_stream_device(eppm_context* ctx, const uint8_t* d_frames, int n_pairs, float* d_flow);
+/* The same with HOST buffers: frames [n_frames][h][w][3] u8, flow [n_frames - 1][h][w][2] f32; n_frames may exceed max_batch (the stream
+ * is processed in chunks of max_batch - 1 pairs, uploads / downloads of neighbouring chunks overlapped with compute; pinned host memory
+ * recommended).  max_batch >= 2.  Replaces a video loop of set_data + compute_flow (main.cpp:59-65). */
+int eppm_compute_stream_host(eppm_context* ctx, const uint8_t* frames, int n_frames, float* flow);
 int eppm_synchronize(eppm_context* ctx);
 void* eppm_stream(eppm_context* ctx); /* cudaStream_t */
 

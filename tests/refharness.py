@@ -58,6 +58,14 @@ class Ref:
             getattr(lib, name).restype = None
         self.lib = lib
 
+    def shim_stats(self):
+        """(texture binds issued, texture objects created) by the texture-reference shim since the library was loaded."""
+        if not hasattr(self.lib, "ref_shim_stats"):
+            return None
+        b, c = C.c_ulonglong(), C.c_ulonglong()
+        self.lib.ref_shim_stats(C.byref(b), C.byref(c))
+        return int(b.value), int(c.value)
+
     def create(self, h, w):
         return self.lib.ref_create(h, w)
 
