@@ -19,6 +19,11 @@ class EppmParams(C.Structure):
     ]
 
 
+class EppmFlowError(C.Structure):
+    """struct eppm_flow_error (include/eppm.h)."""
+    _fields_ = [("epe", C.c_double), ("aae_deg", C.c_double), ("outlier_frac", C.c_double), ("n_valid", C.c_longlong), ("n_known", C.c_longlong)]
+
+
 # every symbol include/eppm.h declares: name -> (restype, argtypes)
 EPPM_SYMBOLS = {
     "eppm_default_params": (None, [C.POINTER(EppmParams)]),
@@ -52,6 +57,9 @@ EPPM_SYMBOLS = {
     "eppm_selftest_affine_sites": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "eppm_selftest_affine_sites_stride": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "eppm_refine_uses_site_table": (C.c_int, [C.c_void_p, C.c_int]),
+    "eppm_eval_flow": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.POINTER(EppmFlowError)]),
+    "eppm_write_flo": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
+    "eppm_read_flo": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_size_t]),
     "eppm_launch_count": (C.c_ulonglong, [C.c_int]),
     "eppm_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 5)]),
     "eppm_last_kernel_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),

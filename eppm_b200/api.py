@@ -243,6 +243,18 @@ class EppmContext:
         """One coarse-to-fine step on the context's band: 0 = upsample + refine (-> FLOW_TMP), 1 = smoothing, 2 = final smoothing."""
         self._check(self.lib.eppm_tiled_c2f_step(self._ctx, level, kind), "eppm_tiled_c2f_step")
 
+    def eval_flow(self, d_flow, d_gt, n, border=0, outlier_thresh=3.0):
+        """Device-side EPE / AAE / outlier share of n flows against ground truth (bao_calc_flow_error semantics); list of dicts."""
+        for t, what in ((d_flow, "d_flow"), (d_gt, "d_gt")):
+            if not isinstance(t, int):
+                if t.shape[0] < n:
+                    raise EppmError(f"{what}: holds {t.shape[0]} pairs, {n} requested")
+                _check_array(t, (t.shape[0], self.h, self.w, 2), np.float32, what, device=self.device)
+        out = (_lib.EppmFlowError * n)()
+        with self._ordered():
+            self._check(self.lib.eppm_eval_flow(self._ctx, _ptr(d_flow), _ptr(d_gt), n, border, outlier_thresh, out), "eppm_eval_flow")
+        return [dict(epe=o.epe, aae_deg=o.aae_deg, outlier_frac=o.outlier_frac, n_valid=o.n_valid, n_known=o.n_known) for o in out]
+
     def last_stage_ms(self):
         buf = (C.c_float * 5)()
         self._check(self.lib.eppm_last_stage_ms(self._ctx, C.byref(buf)), "eppm_last_stage_ms")
@@ -255,6 +267,29 @@ class EppmContext:
 
     def launch_count(self, reset=False):
         return int(self.lib.eppm_launch_count(1 if reset else 0))
+
+
+def write_flo(path, flow):
+    """eppm_write_flo: float32 [h,w,2] -> Middlebury .flo."""
+    flow = np.ascontiguousarray(flow, np.float32)
+    lib = _lib.load()
+    rc = lib.eppm_write_flo(str(path).encode(), flow.ctypes.data, flow.shape[0], flow.shape[1])
+    if rc != 0:
+        raise EppmError(f"eppm_write_flo failed ({rc}): {lib.eppm_last_error().decode()}")
+
+
+def read_flo(path):
+    """eppm_read_flo: Middlebury .flo -> float32 [h,w,2]."""
+    lib = _lib.load()
+    h, w = C.c_int(), C.c_int()
+    rc = lib.eppm_read_flo(str(path).encode(), None, C.byref(h), C.byref(w), 0)
+    if rc != 0:
+        raise EppmError(f"eppm_read_flo failed ({rc}): {lib.eppm_last_error().decode()}")
+    out = np.empty((h.value, w.value, 2), np.float32)
+    rc = lib.eppm_read_flo(str(path).encode(), out.ctypes.data, C.byref(h), C.byref(w), out.size)
+    if rc != 0:
+        raise EppmError(f"eppm_read_flo failed ({rc}): {lib.eppm_last_error().decode()}")
+    return out
 
 
 class BaoFlowPatchmatchMultiscaleCuda:

@@ -32,7 +32,9 @@ enum {
     EPPM_VAR_PROP_CHAIN = 16384,       // propagation as barrier-free segment chains, 32 chains per warp (measured slower than the queue: 5.70 vs 5.26 ms per pair)
     EPPM_VAR_SEARCH_WARP = 32768,      // random search with one WARP per evaluation (measured slower: neighbouring pixels' narrow guesses already coalesce in the thread-per-pixel kernel)
     EPPM_VAR_PROP_NOMEMO = 262144,     // propagation: score candidates the pixel has scored before (the reference does; the memo skips them, same outcome)
-    EPPM_VAR_PM_NOQ = 524288,          // PatchMatch kernels read the packed planes sample by sample (16-byte loads) instead of the parity-split planes pair by pair
+    EPPM_VAR_PM_Q = 524288,            // PatchMatch kernels read parity-split (Q) planes with 256-bit loads, two samples per request (measured slower: 4.79-4.88 vs 4.67 ms per pair;
+                                       //   a 256-bit request costs the L1 as many wavefronts as two 128-bit ones)
+    EPPM_VAR_REFINE_BRANCH = 1048576,  // table refine that branches around candidate rows outside the image (round-1 default) instead of scoring them at a clamped centre
     EPPM_VAR_PROP_WARP_FULL = 131072,  // propagation queue scored by one warp per evaluation with ALL samples staged in shared memory (13 KB per warp starves the L1)
     EPPM_VAR_PROP_NOSKIP = 8,      // propagation: evaluate candidates that equal the current target (the reference does)
 };

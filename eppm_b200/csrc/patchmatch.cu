@@ -1443,7 +1443,7 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
     a.pix[1] = c->pix[1][L];
     a.pixT[0] = c->pixT[0];
     a.pixT[1] = c->pixT[1];
-    const bool use_q = STRIDE == 2 && !(c->variant & EPPM_VAR_PM_NOQ);
+    const bool use_q = STRIDE == 2 && (c->variant & EPPM_VAR_PM_Q);
     a.q[0] = use_q ? c->pixQ[0] : nullptr;
     a.q[1] = use_q ? c->pixQ[1] : nullptr;
     a.qg = make_qgeom(g.pw, g.ph);

@@ -223,7 +223,7 @@ __device__ __forceinline__ const float4* pix_at_b(const float4* base, int off, i
 #endif
 #define EPPM_PRAGMA_(x) _Pragma(#x)
 #define EPPM_PRAGMA(x) EPPM_PRAGMA_(x)
-template <bool GROUP_TINY, int NCT, int MINB, int STRIDE>
+template <bool GROUP_TINY, int NCT, int MINB, int STRIDE, bool ALLROWS = false, bool WIDE = false>
 __global__ void __launch_bounds__(RF_PIX * 9 / NCT, MINB)
     k_c2f_refine_tab(RefineArgs a, const __grid_constant__ CostLut lut, const __grid_constant__ AffineTab tab) {
     __shared__ float s_best[9][RF_PIX];
@@ -295,12 +295,16 @@ EPPM_PRAGMA(unroll RF_JUNROLL)
 #pragma unroll
                 for (int n = 0; n < NCT; n++) {
 #ifndef RF_NOVALID
-                    if (NCT > 1 && !valid[n]) continue;
+                    // ALLROWS: candidate rows outside the image (:2029) are scored at a clamped centre and discarded instead of being branched
+                    // around: only warps at the image border contain such rows, the divergent branch costs BSSY + BSYNC + BRA per candidate row
+                    // and sample everywhere else
+                    if (NCT > 1 && !ALLROWS && !valid[n]) continue;
 #endif
                     if (GROUP_TINY) {
                         float ct[4], t2[4], w[4];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) sample_eval(p1, p1k, ldpix(pix_at(P[n], off[q])), c2k[n], d1, lut_base, ct[q], t2[q]);
+                        for (int q = 0; q < 4; q++)
+                            sample_eval(p1, p1k, ldpix(WIDE ? pix_at_b(P[n], off[q], a.px_bytes) : pix_at(P[n], off[q])), c2k[n], d1, lut_base, ct[q], t2[q]);
 #pragma unroll
                         for (int q = 0; q < 4; q++) w[q] = __fmul_rn(ex2_mufu(t2[q]), gg);
                         if (fminf(fminf(t2[0], t2[1]), fminf(t2[2], t2[3])) < -126.0f) {
@@ -877,7 +881,23 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                 else if (v & EPPM_VAR_REFINE_9WARP3) k_c2f_refine_tab<true, 1, 3, 2><<<grd, blk9, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else if (v & EPPM_VAR_REFINE_PK_BRANCH) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, false><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else if (v & EPPM_VAR_REFINE_PK) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, true><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
-                else k_c2f_refine_tab<true, 3, RF_TAB2_MINBLOCKS, 2><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
+                else {
+                    // tuning knob EPPM_REFINE_MODE = allrows + 2 * wide + 4 * (6 CTAs per SM instead of 7)
+                    static const int mode = getenv("EPPM_REFINE_MODE") ? atoi(getenv("EPPM_REFINE_MODE")) : 0;
+                    const int md = (v & EPPM_VAR_REFINE_BRANCH) ? 0 : mode;
+#define EPPM_RT(MB, AR, WD) k_c2f_refine_tab<true, 3, MB, 2, AR, WD><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp)
+                    switch (md) {
+                    case 1: EPPM_RT(RF_TAB2_MINBLOCKS, true, false); break;
+                    case 2: EPPM_RT(RF_TAB2_MINBLOCKS, false, true); break;
+                    case 3: EPPM_RT(RF_TAB2_MINBLOCKS, true, true); break;
+                    case 4: EPPM_RT(6, false, false); break;
+                    case 5: EPPM_RT(6, true, false); break;
+                    case 6: EPPM_RT(6, false, true); break;
+                    case 7: EPPM_RT(6, true, true); break;
+                    default: EPPM_RT(RF_TAB2_MINBLOCKS, false, false); break;
+                    }
+#undef EPPM_RT
+                }
             }
             EPPM_LAUNCH_COUNT(1);
             return;

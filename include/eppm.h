@@ -177,6 +177,22 @@ int eppm_selftest_affine_sites(int w, int h, int pw, int* table_out);
 int eppm_selftest_affine_sites_stride(int w, int h, int pw, int stride, int* table_out);
 int eppm_refine_uses_site_table(eppm_context* ctx, int level);
 
+/* Evaluation against ground truth on the device (d_flow, d_gt: [n][h][w][2] f32 device arrays; out: n host records; synchronises).
+ *   epe / aae_deg : bao_calc_flow_error (basic/bao_flow_tools.cpp:64-111): mean end-point error and mean angular error (degrees) over the
+ *                   pixels inside `border` whose ground truth is known (|.| <= 1e9) and non-zero; n_valid = their number
+ *   outlier_frac  : bao_calc_flow_error_percentage (:114-141): share of the pixels with known ground truth (n_known) whose end-point error
+ *                   exceeds outlier_thresh
+ * Per-pixel arithmetic is the reference's; the sums are double and order-deterministic. */
+typedef struct eppm_flow_error {
+    double epe, aae_deg, outlier_frac;
+    long long n_valid, n_known;
+} eppm_flow_error;
+int eppm_eval_flow(eppm_context* ctx, const float* d_flow, const float* d_gt, int n, int border, float outlier_thresh, eppm_flow_error* out);
+/* Middlebury .flo files (3rdparty/middlebury/flowIO.cpp:56-160) from / to the interleaved (u, v) host layout of this API: "PIEH", int32 w,
+ * int32 h, h*w*2 float32.  eppm_read_flo with flow_uv == NULL only returns the dimensions. */
+int eppm_write_flo(const char* path, const float* flow_uv, int h, int w);
+int eppm_read_flo(const char* path, float* flow_uv, int* h, int* w, size_t capacity_floats);
+
 /* Number of kernel launches issued by this library since the counter was last reset (bench.py's gpu_launches). */
 unsigned long long eppm_launch_count(int reset);
 

@@ -12,6 +12,7 @@
 #undef private
 #include "bao_basic.h"
 #include "defs.h"
+#include "bao_flow_tools.h"
 
 struct ref_ctx {
     bao_flow_patchmatch_multiscale_cuda* eppm;
@@ -132,4 +133,22 @@ extern "C" long ref_read_plane(void* p, int which, int level, void* out) {
     }
     }
     return -1;
+}
+
+// The reference's own evaluation and .flo writer (basic/bao_flow_tools.cpp:49-141) on interleaved (u, v) arrays, for the tests of
+// eppm_eval_flow / eppm_write_flo.
+extern "C" void ref_calc_flow_error(const float* flow_uv, const float* gt_uv, int h, int w, int border, int error_thresh, float* epe, float* aae, float* outlier_frac) {
+    float** u = bao_alloc<float>(h, w); float** v = bao_alloc<float>(h, w);
+    float** gu = bao_alloc<float>(h, w); float** gv = bao_alloc<float>(h, w);
+    for (size_t i = 0; i < (size_t)h * w; i++) { u[0][i] = flow_uv[2 * i]; v[0][i] = flow_uv[2 * i + 1]; gu[0][i] = gt_uv[2 * i]; gv[0][i] = gt_uv[2 * i + 1]; }
+    *epe = 0.f; *aae = 0.f;
+    bao_calc_flow_error(u, v, gu, gv, h, w, *epe, *aae, border, false);
+    *outlier_frac = bao_calc_flow_error_percentage(u, v, gu, gv, h, w, error_thresh, NULL);
+    bao_free(u); bao_free(v); bao_free(gu); bao_free(gv);
+}
+extern "C" void ref_save_flo(const char* path, const float* flow_uv, int h, int w) {
+    float** u = bao_alloc<float>(h, w); float** v = bao_alloc<float>(h, w);
+    for (size_t i = 0; i < (size_t)h * w; i++) { u[0][i] = flow_uv[2 * i]; v[0][i] = flow_uv[2 * i + 1]; }
+    bao_save_flo_file(path, u, v, h, w);
+    bao_free(u); bao_free(v);
 }

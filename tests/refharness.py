@@ -45,6 +45,9 @@ class Ref:
         lib.ref_tap_pm_step.argtypes = [I, I] + [P] * 6 + [I, I, S, S, S, S]
         lib.ref_tap_c2f_refine.argtypes = [P] * 5 + [I, I, S, S]
         lib.ref_probe_texture.argtypes = [P, P, I, P]
+        if hasattr(lib, "ref_calc_flow_error"):
+            lib.ref_calc_flow_error.argtypes = [P, P, I, I, I, I, P, P, P]
+            lib.ref_save_flo.argtypes = [C.c_char_p, P, I, I]
         for name, args in {
             "baoCudaLeftRightCheck": [P, P, P, P, I, I, S, S],
             "baoCudaOutlierRemoval": [P, P, I, I, S, S],
@@ -65,6 +68,17 @@ class Ref:
         b, c = C.c_ulonglong(), C.c_ulonglong()
         self.lib.ref_shim_stats(C.byref(b), C.byref(c))
         return int(b.value), int(c.value)
+
+    def calc_flow_error(self, flow, gt, border=0, error_thresh=3):
+        """bao_calc_flow_error + bao_calc_flow_error_percentage of the reference on interleaved [h,w,2] float32 arrays -> (epe, aae_deg, outlier_frac)."""
+        flow = np.ascontiguousarray(flow, np.float32); gt = np.ascontiguousarray(gt, np.float32)
+        e, a, o = C.c_float(), C.c_float(), C.c_float()
+        self.lib.ref_calc_flow_error(flow.ctypes.data, gt.ctypes.data, flow.shape[0], flow.shape[1], border, error_thresh, C.byref(e), C.byref(a), C.byref(o))
+        return e.value, a.value, o.value
+
+    def save_flo(self, path, flow):
+        flow = np.ascontiguousarray(flow, np.float32)
+        self.lib.ref_save_flo(str(path).encode(), flow.ctypes.data, flow.shape[0], flow.shape[1])
 
     def create(self, h, w):
         return self.lib.ref_create(h, w)

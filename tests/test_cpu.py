@@ -301,6 +301,49 @@ def test_flo_and_ppm_io(tmp_path):
     assert np.array_equal(synth.read_ppm(q), img)
 
 
+def test_c_abi_flo_io_and_argument_checks(tmp_path):
+    """eppm_write_flo / eppm_read_flo (host-only entry points of the C ABI) against the Python reader/writer, and the wrapper's refusal of
+    buffers whose dtype / shape / layout is not what the library reads through the raw pointer."""
+    import eppm_b200 as E
+    from eppm_b200 import api
+    fl = np.random.default_rng(3).normal(size=(11, 13, 2)).astype(np.float32)
+    p = str(tmp_path / "c.flo")
+    E.write_flo(p, fl)
+    assert np.array_equal(synth.read_flo(p), fl) and np.array_equal(E.read_flo(p), fl)
+    q = str(tmp_path / "py.flo")
+    synth.write_flo(q, fl)
+    assert open(p, "rb").read() == open(q, "rb").read()
+    with pytest.raises(api.EppmError):
+        E.write_flo(str(tmp_path / "c.txt"), fl)          # the reference's writer insists on the extension (flowIO.cpp:131-135)
+    with open(str(tmp_path / "bad.flo"), "wb") as f:
+        f.write(b"PIEX" + bytes(8))
+    with pytest.raises(api.EppmError):
+        E.read_flo(str(tmp_path / "bad.flo"))
+    ok = np.zeros((2, 4, 6, 3), np.uint8)
+    api._check_array(ok, (2, 4, 6, 3), np.uint8, "img")
+    for bad in (ok.astype(np.float32), ok[:, :, ::2], ok[:1], np.asfortranarray(ok)):
+        with pytest.raises(api.EppmError):
+            api._check_array(bad, (2, 4, 6, 3), np.uint8, "img")
+    with pytest.raises(api.EppmError):
+        api._check_array(ok, (2, 4, 6, 3), np.uint8, "d_img", device=0)   # host memory where a device tensor is required
+
+
+def test_bench_shard_plan_and_configs():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class A:
+        batch = 0; scaling = "strong"
+    for cfg_id, total in ((2, 64), (3, 256)):
+        cfg = bench.CONFIGS[cfg_id]
+        assert bench.shard_plan(A, cfg, 1) == (total, "weak")
+        for n in (2, 4, 8):
+            assert bench.shard_plan(A, cfg, n) == (total // n, "strong")   # BASELINE config: the batch is sharded over the GPUs
+    A.scaling = "weak"
+    assert bench.shard_plan(A, bench.CONFIGS[3], 8) == (256, "weak")
+    assert bench.CONFIGS[3]["metric"] == "frame_pairs_per_s_1080p" and (bench.CONFIGS[3]["h"], bench.CONFIGS[3]["w"]) == (1080, 1920)
+
+
 def test_algorithmic_counts_match_the_survey():
     sys.path.insert(0, ROOT)
     import bench

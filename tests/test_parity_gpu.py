@@ -184,11 +184,11 @@ def test_consistency_and_c2f_stage_by_stage(ref, mine, chain):
         assert torch.equal(x, y)
     # outlier removal: the reference reads and writes the same array (race); snapshot semantics may differ on a few pixels
     r2, m2 = _both(ref, mine, lambda lib, t: lib.baoCudaOutlierRemoval(P(t[0]), P(t[1]), wc, hc, wc * 4, wc * 4), [r[0], r[1]])
-    assert (r2[0] != m2[0]).any(-1).float().mean().item() <= 0.005
+    assert (r2[0] != m2[0]).any(-1).float().mean().item() <= 0.0015   # measured 0.089 % (17 of 19 200), profiles/r01_parity_stages.json
     # weighted median, 20 in-place sweeps in the reference (race) vs 20 snapshot sweeps
     wmf = lambda lib, t: lib.baoCudaWeightedMedianFilter(P(t[0]), P(t[1]), P(i1[0]), wc, hc, i1[1], wc * 4, wc * 4, 20, True)
     r3, m3 = _both(ref, mine, wmf, [r2[0], r2[1]])
-    assert (r3[0] != m3[0]).any(-1).float().mean().item() <= 0.03
+    assert (r3[0] != m3[0]).any(-1).float().mean().item() <= 0.015   # measured 0.96 % (184 of 19 200)
     left_r = ((r3[0] < 0).any(-1)).sum().item(); left_m = ((m3[0] < 0).any(-1)).sum().item()
     assert abs(left_r - left_m) <= 0.002 * n_px
     # hole filling on the reference's state: holes are isolated -> bit-exact
@@ -220,7 +220,7 @@ def test_consistency_and_c2f_stage_by_stage(ref, mine, chain):
         sm = lambda lib, t, l=l, hl=hl, wl=wl: lib.baoCudaFlowSmoothing(P(t[0]), P(img[0][l][0]), wl, hl, img[0][l][1], wl * 8)
         rs, ms = _both(ref, mine, sm, [rr[0]])
         d = (rs[0] - ms[0]).abs()
-        assert d.mean().item() <= 1e-3 and d.max().item() <= 0.5
+        assert d.mean().item() <= 1e-4 and d.max().item() <= 0.25   # measured mean 5e-5, max 0.12 px
         cur = rs[0]
 
 
@@ -501,6 +501,163 @@ def test_end_to_end_epe_vs_ground_truth_no_worse(ref, h, w, idx):
     # "mean EPE difference <= 0.05 px" against ground truth, and not worse than the reference beyond that tolerance
     assert abs(e_me - e_ref) <= 0.05, (e_me, e_ref)
     ref.destroy(rc); ctx.close()
+
+
+def _c2f_call(lib, flows_lp1, out, l, dims, img, cen):
+    nl = 3
+    PtrArr, IntArr, SzArr = C.c_void_p * nl, C.c_int * nl, C.c_size_t * nl
+    flows = [None] * nl
+    flows[l] = out; flows[l + 1] = flows_lp1
+    lib.baoCudaBLF_C2F.argtypes = [C.c_void_p] * 11 + [C.c_int]
+    lib.baoCudaBLF_C2F.restype = None
+    lib.baoCudaBLF_C2F(PtrArr(*[P(x) if x is not None else None for x in flows]), PtrArr(*[P(img[0][k][0]) for k in range(nl)]),
+                       PtrArr(*[P(img[1][k][0]) for k in range(nl)]), PtrArr(*[P(cen[0][k][0]) for k in range(nl)]),
+                       PtrArr(*[P(cen[1][k][0]) for k in range(nl)]), None, None, IntArr(*[d[0] for d in dims]), IntArr(*[d[1] for d in dims]),
+                       SzArr(*[img[0][k][1] for k in range(nl)]), SzArr(*[cen[0][k][1] for k in range(nl)]), l)
+    torch.cuda.synchronize()
+
+
+@needs_ref
+def test_full_hd_vs_reference(ref, mine):
+    """The benchmark resolution (BASELINE config 3, 1920x1080) against the reference build: pyramid / census / geometry, the whole
+    PatchMatch in both directions and the plane-fitting refine of levels 1 and 0 bit-exact; end to end the direct flow-vs-flow
+    difference is bounded at ~1.2x what was measured (profiles/r02_parity_e2e.json) and the EPE against ground truth within 0.05 px."""
+    h, w = 1080, 1920
+    a, b, gt, valid = synth.make_pair(h, w, 1000)
+    rc, dims, img, cen = _ref_level_planes(ref, h, w, a, b)
+    ctx = E.EppmContext(h, w, 1)
+    ctx.stage_prepare(dev(a[None]), dev(b[None]), 1)
+    for l in range(3):
+        assert ctx.level_dims(l) == tuple(dims[l])
+        for which in (E.PLANE_RGBA1, E.PLANE_RGBA2, E.PLANE_CENSUS1, E.PLANE_CENSUS2):
+            assert same_bits(ctx.read_plane(which, l), ref.read_plane(rc, which, l)), (which, l)
+    hc, wc = dims[2]
+    for swap in (False, True):
+        (nr, cr), (nm, cm) = _pm(ref.lib, img, cen, 2, wc, hc, swap), _pm(mine, img, cen, 2, wc, hc, swap)
+        assert torch.equal(nr, nm), f"{(nr != nm).any(-1).sum().item()} targets differ (swap={swap})"
+        assert same_bits(cr.cpu().numpy(), cm.cpu().numpy())
+    # the reference's own flow pyramid (after its consistency / smoothing stages) feeds the refine of both libraries
+    fr = ref.compute_flow(rc, h, w)
+    for l in (1, 0):
+        coarse = torch.from_numpy(ref.read_plane(rc, 8, l + 1)).cuda()
+        outs = []
+        for lib in (ref.lib, mine):
+            fine = torch.zeros((dims[l][0], dims[l][1], 2), dtype=torch.float32, device="cuda")
+            _c2f_call(lib, coarse, fine, l, dims, img, cen)
+            outs.append(fine.cpu().numpy())
+        assert same_bits(outs[0], outs[1]), f"plane-fitting refine differs at level {l}: {(outs[0].view(np.uint32) != outs[1].view(np.uint32)).sum()} floats"
+    fm = ctx.compute_batch_host(a[None], b[None])[0]
+    d = np.sqrt(((fm.astype(np.float64) - fr.astype(np.float64)) ** 2).sum(-1))
+    e_ref, e_me = synth.epe(fr, gt, valid), synth.epe(fm, gt, valid)
+    assert abs(e_me - e_ref) <= 0.05, (e_me, e_ref)
+    assert np.median(d) <= 1e-3, np.median(d)
+    assert d.mean() <= FLOW_VS_REF_BOUND[(h, w)], d.mean()
+    ref.destroy(rc); ctx.close()
+
+
+# direct flow-vs-flow mean end-point difference to the reference build on synthetic large-displacement pairs: ~1.2x the values measured on
+# B200 (tools/parity_e2e.py -> profiles/r02_parity_e2e.json).  The difference comes from the three filters the reference updates in place
+# (DESIGN.md §3); it is recorded here so that a regression shows.
+FLOW_VS_REF_BOUND = {(480, 640): 0.34, (436, 1024): 0.40, (1080, 1920): 0.36}   # measured 0.277, 0.330, 0.297 px (median 0: 3 % of the pixels carry it)
+
+
+@needs_ref
+@pytest.mark.parametrize("h,w,idx", [(480, 640, 0), (436, 1024, 1)])
+def test_flow_vs_reference_flow_is_recorded(ref, h, w, idx):
+    a, b, gt, valid = synth.make_pair(h, w, idx)
+    rc = ref.create(h, w)
+    ref.set_data(rc, a, b)
+    fr = ref.compute_flow(rc, h, w)
+    ctx = E.EppmContext(h, w, 1)
+    fm = ctx.compute_batch_host(a[None], b[None])[0]
+    d = np.sqrt(((fm.astype(np.float64) - fr.astype(np.float64)) ** 2).sum(-1))
+    assert np.median(d) <= 1e-3, np.median(d)
+    assert d.mean() <= FLOW_VS_REF_BOUND[(h, w)], d.mean()
+    ref.destroy(rc); ctx.close()
+
+
+@needs_ref
+def test_inplace_filter_mode(ref):
+    """inplace_filters = 1 (EPPM_INPLACE_LEGACY): outlier removal, weighted median and smoothing update in place with the reference's launch
+    geometry.  Same accuracy bar as the default mode; the deterministic stages in front of them are untouched (PatchMatch planes identical)."""
+    h, w = 480, 640
+    a, b, gt, valid = synth.make_pair(h, w, 0)
+    rc = ref.create(h, w)
+    ref.set_data(rc, a, b)
+    fr = ref.compute_flow(rc, h, w)
+    p = E.default_params()
+    p.inplace_filters = 1
+    ctx = E.EppmContext(h, w, 1, params=p)
+    ctx0 = E.EppmContext(h, w, 1)
+    fm = ctx.compute_batch_host(a[None], b[None])[0]
+    f0 = ctx0.compute_batch_host(a[None], b[None])[0]
+    assert same_bits(ctx.read_plane(E.PLANE_NNF_BWD), ctx0.read_plane(E.PLANE_NNF_BWD))
+    assert np.isfinite(fm).all()
+    assert abs(synth.epe(fm, gt, valid) - synth.epe(fr, gt, valid)) <= 0.05
+    d = np.sqrt(((fm.astype(np.float64) - fr.astype(np.float64)) ** 2).sum(-1))
+    assert np.median(d) <= 1e-3 and d.mean() <= 0.40   # measured 0.309 px: the in-place order does not land closer to the reference (profiles/r02_parity_e2e.json)
+    assert not same_bits(fm, f0)   # it really is a different update order
+    ref.destroy(rc); ctx.close(); ctx0.close()
+
+
+@needs_ref
+def test_video_stream_vs_reference_on_chained_frames(ref):
+    """eppm_compute_stream_* against the REFERENCE on a chained synthetic clip (frame t+1 = frame t moved): the reference is given every
+    consecutive pair through set_data + compute_flow; the stream entry points prepare each frame once.  Pyramid and census of every frame
+    bit-exact with the reference's, flows within the end-point bars, host-buffer entry identical to the device entry."""
+    h, w = 270, 480
+    frames, flows, valids = synth.make_stream(h, w, 4, first_idx=70, scale_to=0.25)
+    n = frames.shape[0] - 1
+    ctx = E.EppmContext(h, w, 3)   # max_batch 3 < 4 frames: the host entry has to chunk (2 pairs + 1 pair)
+    out_h = ctx.compute_stream_host(frames)
+    ctx4 = E.EppmContext(h, w, 4)
+    d_flow = torch.zeros((n, h, w, 2), dtype=torch.float32, device="cuda")
+    ctx4.compute_stream_device(dev(frames), n, d_flow)
+    ctx4.synchronize()
+    assert same_bits(out_h, d_flow.cpu().numpy())
+    rc = ref.create(h, w)
+    for t in range(n):
+        ref.set_data(rc, frames[t], frames[t + 1])
+        for l in range(3):   # frame t sits in plane t of the image-1 arrays of the stream context
+            assert same_bits(ctx4.read_plane(E.PLANE_RGBA1, l, pair=t), ref.read_plane(rc, 0, l)), (t, l)
+            assert same_bits(ctx4.read_plane(E.PLANE_CENSUS1, l, pair=t), ref.read_plane(rc, 2, l)), (t, l)
+        fr = ref.compute_flow(rc, h, w)
+        d = np.sqrt(((out_h[t].astype(np.float64) - fr.astype(np.float64)) ** 2).sum(-1))
+        assert synth.epe(out_h[t], flows[t], valids[t]) <= synth.epe(fr, flows[t], valids[t]) + 0.05, t   # no worse than the reference against ground truth
+        assert np.median(d) <= 1e-3, (t, np.median(d))
+    ref.destroy(rc); ctx.close(); ctx4.close()
+
+
+@needs_ref
+def test_device_flow_evaluation_and_flo_vs_reference(ref, tmp_path):
+    """eppm_eval_flow against the reference's bao_calc_flow_error / bao_calc_flow_error_percentage (basic/bao_flow_tools.cpp:64-141) and
+    eppm_write_flo against its .flo writer, on a computed flow with unknown (1e10) and zero ground-truth pixels mixed in."""
+    h, w = 240, 320
+    a, b, gt, valid = synth.make_batch(h, w, 2, first_idx=30, distinct=2)
+    ctx = E.EppmContext(h, w, 2)
+    d_flow = torch.zeros((2, h, w, 2), dtype=torch.float32, device="cuda")
+    ctx.compute_batch_device(dev(a), dev(b), 2, d_flow)
+    ctx.synchronize()
+    gt = gt.copy()
+    gt[0, 10:40, 20:90] = 1e10          # unknown ground truth
+    gt[1, 100:140, :] = 0.0             # zero motion: known, but excluded from EPE / AAE by the reference's test
+    gt[1, 5, 5] = (1e10, 2.5)           # one component unknown: the reference still counts the pixel
+    for border, thr in ((0, 3), (7, 1)):
+        res = ctx.eval_flow(d_flow, dev(gt), 2, border=border, outlier_thresh=float(thr))
+        fl = d_flow.cpu().numpy()
+        for i in range(2):
+            e, aae, out = ref.calc_flow_error(fl[i], gt[i], border, thr)
+            # the reference accumulates ~7e4 floats sequentially in single precision: relative error up to ~1e-4
+            assert abs(res[i]["epe"] - e) <= 2e-4 * max(1.0, abs(e)), (res[i], e)
+            assert abs(res[i]["aae_deg"] - aae) <= 2e-4 * max(1.0, abs(aae)), (res[i], aae)
+            assert abs(res[i]["outlier_frac"] - out) <= 1e-6, (res[i], out)
+            assert 0 < res[i]["n_valid"] < h * w and res[i]["n_known"] <= h * w
+    # .flo: byte-identical to the file the reference writes, and it reads back
+    p_me, p_ref = tmp_path / "me.flo", tmp_path / "ref.flo"
+    E.write_flo(p_me, fl[0]); ref.save_flo(p_ref, fl[0])
+    assert p_me.read_bytes() == p_ref.read_bytes()
+    assert same_bits(E.read_flo(p_me), fl[0])
+    ctx.close()
 
 
 # ------------------------------------------------------------------------------------------------ fixtures + CPU oracle
