@@ -149,6 +149,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->n_sm = v; }
     c->variant = getenv("EPPM_VARIANT") ? atoi(getenv("EPPM_VARIANT")) : 0;
     c->inplace = p.inplace_filters != 0 || (getenv("EPPM_INPLACE_LEGACY") && atoi(getenv("EPPM_INPLACE_LEGACY")) != 0);
+    c->pm_pad_kb = getenv("EPPM_PM_PAD_KB") ? atoi(getenv("EPPM_PM_PAD_KB")) : 0;
     c->profile = getenv("EPPM_PROFILE") && atoi(getenv("EPPM_PROFILE")) != 0;
     {
         // EPPM_STREAM_PRIORITY (measurement knob): CUDA stream priority of this context's compute stream (lower = more urgent), so that

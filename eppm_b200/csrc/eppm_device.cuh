@@ -150,6 +150,17 @@ __device__ __forceinline__ float max3abs_diff(const PixPk& a, const PixPk& b) {
 // (ex2 with the `t2 < -126` fix-up, which a group of samples can share one test for), w = e2*gg, and accumulates.
 __device__ __forceinline__ float census_lut_ref(const float* s, const float4& p1, const float4& p2) { return census_lut(s, p1, p2); }
 __device__ __forceinline__ float census_lut_ref(unsigned base, const float4& p1, const float4& p2) { return census_lut_at(base, p1, p2); }
+// Census LUT at a FIXED address of the shared window: the kernel keeps the table at the start of its dynamic shared memory and owns no
+// static shared memory, so the table sits at the window's user base (1 KB reserved by the system on sm_100, probed per device by
+// lut0_window_base_ok()) and popc(w1 ^ w2) + that constant is the whole address: the immediate field of LDS replaces one integer add per sample.
+constexpr unsigned SHARED_WINDOW_USER_BASE = 0x400;
+struct Lut0 {};
+__device__ __forceinline__ float census_lut_ref(Lut0, const float4& p1, const float4& p2) {
+    const unsigned off = __popc(__float_as_uint(p1.w) ^ __float_as_uint(p2.w));
+    float v;
+    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(off), "n"(SHARED_WINDOW_USER_BASE));
+    return v;
+}
 template <class LutRef>
 __device__ __forceinline__ void sample_eval(const float4& p1, const PixPk& p1k, const float4& p2, const PixPk& c2k, float d1, LutRef s_census,
                                             float& cost, float& t2) {

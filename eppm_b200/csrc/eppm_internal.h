@@ -34,7 +34,7 @@ enum {
     EPPM_VAR_PROP_NOMEMO = 262144,     // propagation: score candidates the pixel has scored before (the reference does; the memo skips them, same outcome)
     EPPM_VAR_PM_Q = 524288,            // PatchMatch kernels read parity-split (Q) planes with 256-bit loads, two samples per request (measured slower: 4.79-4.88 vs 4.67 ms per pair;
                                        //   a 256-bit request costs the L1 as many wavefronts as two 128-bit ones)
-    EPPM_VAR_REFINE_BRANCH = 1048576,  // table refine that branches around candidate rows outside the image (round-1 default) instead of scoring them at a clamped centre
+    EPPM_VAR_REFINE_COLUMN = 1048576,  // table refine with warp = candidate column, thread = three candidate rows (round-1 default) instead of warp = candidate row
     EPPM_VAR_PROP_WARP_FULL = 131072,  // propagation queue scored by one warp per evaluation with ALL samples staged in shared memory (13 KB per warp starves the L1)
     EPPM_VAR_PROP_NOSKIP = 8,      // propagation: evaluate candidates that equal the current target (the reference does)
 };
@@ -141,6 +141,7 @@ struct eppm_context {
     int aff_ok[eppm::MAX_LEVELS] = {};
     int variant = 0;                             // EPPM_VARIANT bit mask (A/B switches for measurements, see EPPM_VAR_*)
     int smooth_fast_div = 0;                     // set at create time when the constant-division fast path was verified exact
+    int pm_pad_kb = 0;                           // EPPM_PM_PAD_KB: dynamic shared memory (KB) the PatchMatch scoring kernels reserve without using it = residency cap (co-scheduling)
     int inplace = 0;                             // eppm_params::inplace_filters or EPPM_INPLACE_LEGACY=1: the three racy filters of the reference run in place (legacy_inplace.cu)
     int rng_ready = 0;                           // rng_init / rng_search expanded (lazily, before the first PatchMatch)
 };

@@ -84,6 +84,15 @@ void ensure_rng_tables(eppm_context* c) {
     c->rng_ready = 1;
 }
 
+// Residency cap of the PatchMatch kernels (co-scheduling with the refine kernel of another chunk, see eppm_compute_batch_host): a launch
+// that asks for pad bytes of dynamic shared memory it never touches limits how many of its CTAs an SM holds, which leaves registers
+// and warp slots to the kernel of the other stream.  0 = no cap.
+static size_t pm_pad_bytes(eppm_context* c, const void* func) {
+    const size_t pad = (size_t)c->pm_pad_kb * 1024;
+    if (pad > 48 * 1024) cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+    return pad;
+}
+
 struct PmArgs {
     const float4* pix[2];   // packed planes of image 1 / image 2 at the PatchMatch level, padded origin of pair 0
     const float4* pixT[2];  // column-major copies (pixel (x,y) at (x+PAD)*ph + (y+PAD)), padded origin of pair 0
@@ -772,7 +781,7 @@ static void launch_propagate_queue(eppm_context* c, const PmArgs& a, int n, int 
         if (mode == 2) k_prop_eval_r<STRIDE, RB, RW><<<rblocks, RW * 32, 0, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
         else if (mode == 1) k_prop_eval_w<STRIDE, WB, WW><<<wblocks, WW * 32, wsmem, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
         else if (STRIDE == 2 && a.q[0]) k_prop_eval<DIR, STRIDE, true><<<eval_blocks, 128, 0, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
-        else k_prop_eval<DIR, STRIDE, false><<<eval_blocks, 128, 0, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
+        else k_prop_eval<DIR, STRIDE, false><<<eval_blocks, 128, pm_pad_bytes(c, (const void*)k_prop_eval<DIR, STRIDE, false>), c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
     }
     EPPM_LAUNCH_COUNT(2 * sl);
 }
@@ -1520,7 +1529,7 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
             EPPM_LAUNCH_COUNT(1);
             continue;
         }
-#define EPPM_SEARCH(NT, NS, MB) k_pm_search_joint<STRIDE, 6, NT, NS, MB><<<grd, blk, 0, c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut)
+#define EPPM_SEARCH(NT, NS, MB) k_pm_search_joint<STRIDE, 6, NT, NS, MB><<<grd, blk, pm_pad_bytes(c, (const void*)k_pm_search_joint<STRIDE, 6, NT, NS, MB>), c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut)
         if (joint && ((v & EPPM_VAR_SEARCH_NOTEX) || !tex_ok)) EPPM_SEARCH(0, 1, 4);
         else if (joint && (v & EPPM_VAR_SEARCH_TEX3)) EPPM_SEARCH(3, 1, 4);
         else if (joint && (v & EPPM_VAR_SEARCH_SPLIT3)) EPPM_SEARCH(2, 3, 8);

@@ -356,6 +356,169 @@ EPPM_PRAGMA(unroll RF_JUNROLL)
     }
 }
 
+// ---- table-driven refine, warp = candidate ROW ----
+// k_c2f_refine_tab gives warp m the candidate COLUMN m and a thread its three candidate rows: the twelve image-2 sites of a sample are
+// twelve 64-bit address computations (two ALU instructions each: 2.3 of the 30.9 issued instructions per sample).  Here warp n owns the
+// candidate ROW n and a thread its three candidate columns: the three columns of a (row, model) are neighbouring pixels, base -16 / +0 /
+// +16 bytes, which the load instruction takes as an immediate -- four address computations per sample instead of twelve.  Everything
+// else (site table, sample order, grouped fix-up, strict '<' arg-min in the reference's order) is k_c2f_refine_tab's.
+// the sample loop of k_c2f_refine_row.  CHECK = false: every candidate of every lane of the warp is valid (all warps but those at the image
+// border), so the per-candidate divergence guard (BSSY / BSYNC / BRA: 1.5 of ~30 issued instructions per sample) is not compiled in.
+template <int STRIDE, bool CHECK, class LutRef>
+__device__ __forceinline__ void refine_row_loop(const RefineArgs& a, const CostLut& lut, const AffineTab& tab, const float4* a0, const float4* Pc, const PixPk& c1k,
+                                                const PixPk (&c2k)[3], const bool (&valid)[3], unsigned wmask, LutRef lut_ref, float (&cs)[3][4], float (&ws)[3][4]) {
+    int s = 0;
+#pragma unroll 1
+    for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
+        const int ai = i < 0 ? -i : i;
+        const int irow = i * a.pw;
+EPPM_PRAGMA(unroll RF_JUNROLL)
+        for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE, s++) {
+            const float4 p1 = ldpix(a0 + irow + j);
+            const PixPk p1k = pack_pix(p1);
+            const float d1 = max3abs_diff(c1k, p1k);
+            const float gg = lut.gg[ai][j < 0 ? -j : j];
+            int off[4];
+            off[0] = irow + j;  // identity model: the exact integer site (cx + j, cy + i)
+#pragma unroll
+            for (int q = 0; q < 3; q++) off[q + 1] = tab.off[q][s];
+            const float4* site[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) site[q] = pix_at(Pc, off[q]);
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                if (CHECK && !valid[m]) continue;
+                // CHECK = false: wmask is warp-uniform and all ones; the (uniform, never divergent) test keeps the three candidates in separate
+                // basic blocks -- scheduled as one block they need more registers than the kernel has
+                if (!CHECK && !(wmask & (1u << m))) continue;
+                float ct[4], t2[4], w[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) sample_eval(p1, p1k, ldpix(site[q] + (m - 1)), c2k[m], d1, lut_ref, ct[q], t2[q]);
+#pragma unroll
+                for (int q = 0; q < 4; q++) w[q] = __fmul_rn(ex2_mufu(t2[q]), gg);
+                if (fminf(fminf(t2[0], t2[1]), fminf(t2[2], t2[3])) < -126.0f) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (t2[q] < -126.0f) w[q] = __fmul_rn(ex2_tiny(t2[q]), gg);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    cs[m][q] = __fmaf_rn(ct[q], w[q], cs[m][q]);
+                    ws[m][q] = __fadd_rn(ws[m][q], w[q]);
+                }
+            }
+        }
+    }
+}
+
+// LUT0: the census table lives at the user base of the shared window (see Lut0); FAST: warps whose 96 candidates are all valid take a loop
+// without validity guards.
+template <int MINB, int STRIDE, bool LUT0, bool FAST>
+__global__ void __launch_bounds__(RF_PIX * 3, MINB)
+    k_c2f_refine_row(RefineArgs a, const __grid_constant__ CostLut lut, const __grid_constant__ AffineTab tab) {
+    extern __shared__ float s_dyn[];             // [0, 16): census table (9 used), then s_best[9][RF_PIX]; no static shared memory in this kernel
+    float* s_census = s_dyn;
+    float (*s_best)[RF_PIX] = reinterpret_cast<float (*)[RF_PIX]>(s_dyn + 16);
+    load_census_lut(s_census, lut);
+    const unsigned lut_base = census_lut_base(s_census);
+    const int n = threadIdx.x >> 5, pl = threadIdx.x & 31;   // n: candidate row of this warp
+    const int x = blockIdx.x * RF_PIX + pl, y = a.y0 + blockIdx.y;
+    const bool in = x < a.w;
+    const int b = blockIdx.z;
+    const float4* I1 = a.pix1 + (size_t)b * a.plane;
+    const float4* I2 = a.pix2 + (size_t)b * a.plane;
+    float2 fl = make_float2(0.f, 0.f);
+    if (in) fl = a.upsample ? upsample2(a.coarse + (size_t)b * a.ws * a.hs, a.ws, a.hs, x, y) : a.coarse[(size_t)b * a.w * a.h + (size_t)y * a.w + x];
+    const bool unknown = fl.x > EPPM_UNKNOWN_FLOW_THRESH || fl.y > EPPM_UNKNOWN_FLOW_THRESH;  // :2011
+    const short cxc = (short)((short)(int)fl.x + x), cyc = (short)((short)(int)fl.y + y);     // :2014-2019
+    const short cy = (short)(cyc + (n - 1));
+    float cost[3];
+    bool valid[3];
+    bool any = false, all = true;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const short cx = (short)(cxc + (m - 1));
+        cost[m] = FLT_MAX;
+        valid[m] = in && !unknown && !(cx < 0 || cy < 0 || cx >= a.w || cy >= a.h);  // :2029
+        any = any || valid[m];
+        all = all && valid[m];
+    }
+    const bool warp_all = FAST && __all_sync(0xffffffffu, all);
+    unsigned wmask = __ballot_sync(0xffffffffu, all) == 0xffffffffu ? 7u : 0u;
+    asm volatile("" : "+r"(wmask));   // opaque to the compiler: see refine_row_loop
+    if (any) {
+        float cs[3][4], ws[3][4];
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) cs[m][q] = ws[m][q] = 0.f;
+        const float4* a0 = I1 + (unsigned)((y + PAD) * a.pw + x + PAD);
+        const PixPk c1k = pack_pix(ldpix(a0));
+        // centre of the MIDDLE candidate of this row; a valid candidate has cx in [0, w), so the middle one lies in [-1, w]: inside the padded plane
+        const int cys = max(0, min(a.h - 1, (int)cy)), cxs = max(-1, min(a.w, (int)cxc));
+        const float4* Pc = I2 + (unsigned)((cys + PAD) * a.pw + cxs + PAD);
+        asm volatile("" : "+l"(Pc));
+        PixPk c2k[3];
+#pragma unroll
+        for (int m = 0; m < 3; m++) c2k[m] = pack_pix(ldpix(Pc + (m - 1)));
+        if (LUT0) {
+            if (warp_all) refine_row_loop<STRIDE, false>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws);
+            else refine_row_loop<STRIDE, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws);
+        } else {
+            if (warp_all) refine_row_loop<STRIDE, false>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, lut_base, cs, ws);
+            else refine_row_loop<STRIDE, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, lut_base, cs, ws);
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            if (!valid[m]) continue;
+            const float k1 = __fdiv_rn(cs[m][0], ws[m][0]), k2 = __fdiv_rn(cs[m][1], ws[m][1]);
+            const float k3 = __fdiv_rn(cs[m][2], ws[m][2]), k4 = __fdiv_rn(cs[m][3], ws[m][3]);
+            cost[m] = min_ref(k1, min_ref(k2, min_ref(k3, k4)));  // :512
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 3; m++) s_best[m * 3 + n][pl] = valid[m] ? cost[m] : __int_as_float(0x7f800000);   // index = m * 3 + n: the reference's order (m outer)
+    __syncthreads();
+    if (in && n == 0) {
+        float2 out;
+        if (unknown) out = make_float2(0.f, 0.f);
+        else {
+            float bcost = 999999.f;   // :2024,:2031 strict '<' against 999999, m outer, n inner
+            int bk = -1;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const float oc = s_best[k][pl];
+                if (oc < bcost) { bcost = oc; bk = k; }
+            }
+            short bx = cxc, by = cyc;   // :2020-2022 default = centre candidate
+            if (bk >= 0) { bx = (short)(cxc + (bk / 3 - 1)); by = (short)(cyc + (bk % 3 - 1)); }
+            out = make_float2((float)(bx - x), (float)(by - y));  // :2038-2039
+        }
+        a.flow[(size_t)b * a.w * a.h + (size_t)y * a.w + x] = out;
+    }
+}
+
+// the shared-window address of the first byte of dynamic shared memory in a kernel without static shared memory (Lut0 relies on it)
+__global__ void k_probe_shared_base(unsigned* out) {
+    extern __shared__ float s_dyn[];
+    s_dyn[threadIdx.x] = 0.f;
+    if (threadIdx.x == 0) *out = (unsigned)__cvta_generic_to_shared(s_dyn);
+}
+static bool lut0_window_base_ok(int device) {
+    static int cached[64] = {};   // 0 unknown, 1 ok, 2 not
+    if (device >= 0 && device < 64 && cached[device]) return cached[device] == 1;
+    unsigned* d = nullptr;
+    unsigned h = ~0u;
+    if (cudaMalloc((void**)&d, 4) == cudaSuccess) {
+        k_probe_shared_base<<<1, 32, 256>>>(d);
+        if (cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost) != cudaSuccess) h = ~0u;
+        cudaFree(d);
+    }
+    const bool ok = h == SHARED_WINDOW_USER_BASE;
+    if (device >= 0 && device < 64) cached[device] = ok ? 1 : 2;
+    return ok;
+}
+
 // ---- table-driven refine, models in packed pairs (default) ----
 // Same decomposition as k_c2f_refine_tab with NCT = 3 (warp m owns candidate column m, a thread its three candidate rows x four
 // models), but the four models of a candidate are evaluated as TWO PAIRS in the halves of packed FP32x2 instructions
@@ -882,11 +1045,20 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                 else if (v & EPPM_VAR_REFINE_PK_BRANCH) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, false><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else if (v & EPPM_VAR_REFINE_PK) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, true><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else {
-                    // tuning knob EPPM_REFINE_MODE = allrows + 2 * wide + 4 * (6 CTAs per SM instead of 7)
-                    static const int mode = getenv("EPPM_REFINE_MODE") ? atoi(getenv("EPPM_REFINE_MODE")) : 0;
-                    const int md = (v & EPPM_VAR_REFINE_BRANCH) ? 0 : mode;
+                    // Default (mode 10): warp = candidate row, census table at the shared-window base.  Measured per 1080p pair at level 0 (round 2,
+                    // tools/variant_times.py, 16 pairs): column kernel 8.28 ms; its knobs allrows 9.72, wide address 8.78, 6 CTAs 8.54; row kernel
+                    // 8.06-8.12, + fixed-address census table 7.85, + guard-free loop for interior warps 7.92 (spills).
+                    // Tuning knob EPPM_REFINE_MODE: 0-7 = column kernel with allrows + 2 * wide + 4 * (6 CTAs per SM), 8-11 = row kernel + 2 * table at base + guard-free
+                    static const int mode = getenv("EPPM_REFINE_MODE") ? atoi(getenv("EPPM_REFINE_MODE")) : 10;
+                    const int md = (v & EPPM_VAR_REFINE_COLUMN) ? 0 : mode;
 #define EPPM_RT(MB, AR, WD) k_c2f_refine_tab<true, 3, MB, 2, AR, WD><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp)
                     switch (md) {
+#define EPPM_RR(L0, FP) k_c2f_refine_row<7, 2, L0, FP><<<grd, blk, (16 + 9 * RF_PIX) * sizeof(float), c->stream>>>(a, c->cost_lut, *tabp)
+                    case 8: EPPM_RR(false, false); break;
+                    case 9: EPPM_RR(false, true); break;
+                    case 10: if (lut0_window_base_ok(c->device)) EPPM_RR(true, false); else EPPM_RR(false, false); break;
+                    case 11: if (lut0_window_base_ok(c->device)) EPPM_RR(true, true); else EPPM_RR(false, true); break;
+#undef EPPM_RR
                     case 1: EPPM_RT(RF_TAB2_MINBLOCKS, true, false); break;
                     case 2: EPPM_RT(RF_TAB2_MINBLOCKS, false, true); break;
                     case 3: EPPM_RT(RF_TAB2_MINBLOCKS, true, true); break;
