@@ -14,7 +14,7 @@ buffers (H2D of both frames and D2H of the flow inside the timed region).  Input
 exceed the 126 MB L2, so no L2 flush is needed between steps.
 
 Other configs: 2 = 64 pairs of 1024x436 (same code path, smaller frames); 4 = ONE 3840x2160 pair spatially tiled over the N GPUs
-(row bands + halo exchange, eppm_b200/tiled.py; N = 1 runs it untiled); 5 = a 300-frame 1080p video stream through
+(row bands + halo exchange inside the library, csrc/tiled.cu; N = 1 runs it untiled); 5 = a 300-frame 1080p video stream through
 eppm_compute_stream_* at the default sweep point (every frame prepared once; tools/stream_sweep.py runs the whole sweep).
 
 The reference has no CPU path (README.md:19 of linchaobao/EPPM): `--impl reference` times its own CUDA build on the same GPU(s)
@@ -427,7 +427,7 @@ def run_stream(args, cfg):
 
 def run_tiled(args, cfg):
     """BASELINE config 4: ONE 3840x2160 pair, row bands of the coarsest level over the N GPUs with a halo exchange per column pass
-    (eppm_b200/tiled.py; bit-identical to the untiled run).  A step = the whole path for that pair; e2e adds the H2D of the pair on every
+    (eppm_compute_tiled_*, csrc/tiled.cu; bit-identical to the untiled run).  A step = the whole path for that pair; e2e adds the H2D of the pair on every
     rank (every rank builds the full pyramids) and the D2H of the flow on rank 0."""
     H, W = cfg["h"], cfg["w"]
     rank, world, local = env_rank()
@@ -437,6 +437,8 @@ def run_tiled(args, cfg):
     from eppm_b200 import tiled
     dist_setup()
     ctx = E.EppmContext(H, W, 1, device=local)
+    if world > 1:
+        ctx.tiled_init(rank, world)
     h_a = torch.from_numpy(a).pin_memory(); h_b = torch.from_numpy(b).pin_memory()
     h_flow = torch.empty((1, H, W, 2), dtype=torch.float32).pin_memory()
     d_a = h_a.cuda(); d_b = h_b.cuda()
@@ -447,14 +449,13 @@ def run_tiled(args, cfg):
         if world == 1:
             ctx.compute_batch_device(d_a, d_b, 1, d_flow)
         else:
-            d_flow[0].copy_(tiled.compute_flow_tiled(ctx, d_a, d_b, rank, world))
+            ctx.compute_tiled_device(d_a, d_b, d_flow)   # the library drives the halo exchange and the band gathers (csrc/tiled.cu)
 
     def step_host():
-        with torch.cuda.stream(stream):
-            d_a.copy_(h_a, non_blocking=True); d_b.copy_(h_b, non_blocking=True)
-            step_resident()
-            if rank == 0:
-                h_flow.copy_(d_flow, non_blocking=True)
+        if world == 1:
+            ctx.compute_batch_host(h_a, h_b, out=h_flow)
+        else:
+            ctx.compute_tiled_host(h_a, h_b, out=h_flow if rank == 0 else None, want_flow=rank == 0)
 
     def timed(fn, steps):
         barrier(world)
@@ -490,7 +491,7 @@ def run_tiled(args, cfg):
                        "l2_policy": "packed planes of one 4K pair = 362 MB > 126 MB L2, no flush"},
             "mpix_per_s": round(value * H * W / 1e6, 2),
             "e2e": {"value": round(steps / (ms_e2e / 1e3), 3), "unit": "pairs/s", "h2d_bytes_per_step": int(H * W * 3 * 2),
-                    "d2h_bytes_per_step": int(H * W * 2 * 4), "api": "eppm_b200.tiled.compute_flow_tiled + pinned H2D/D2H"},
+                    "d2h_bytes_per_step": int(H * W * 2 * 4), "api": "eppm_compute_tiled_host (C ABI, pinned host buffers; NCCL enqueued by the library)" if world > 1 else "eppm_compute_batch_host"},
             "gpu_launches": int(launches), "clocks": clocks,
             "epe_vs_gt_px": round(float(S.epe(h_flow[0].numpy(), gt[0], va[0])), 4),
             "roofline": None, "cpu_baseline": None,

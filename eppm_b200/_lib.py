@@ -51,6 +51,11 @@ EPPM_SYMBOLS = {
     "eppm_tiled_pm_steps": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "eppm_tiled_c2f_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "eppm_device_plane": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
+    "eppm_tiled_unique_id": (C.c_int, [C.c_void_p]),
+    "eppm_tiled_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "eppm_compute_tiled_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "eppm_compute_tiled_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "eppm_tiled_shutdown": (C.c_int, [C.c_void_p]),
     "eppm_selftest_const_div": (C.c_longlong, [C.c_float, C.c_uint, C.c_uint]),
     "eppm_smooth_uses_fast_div": (C.c_int, [C.c_void_p]),
     "eppm_smooth_uses_tma": (C.c_int, [C.c_void_p]),

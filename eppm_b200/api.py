@@ -74,6 +74,7 @@ class EppmContext:
     def __init__(self, h, w, max_batch=1, device=0, params=None):
         self.lib = _lib.load()
         self.h, self.w, self.max_batch, self.device = h, w, max_batch, device
+        self.params = params if params is not None else default_params()   # what the context was created with (tiled.py derives its schedule from it)
         self._ctx = C.c_void_p()
         rc = self.lib.eppm_create(C.byref(self._ctx), device, h, w, max_batch, C.byref(params) if params is not None else None)
         if rc != 0:
@@ -242,6 +243,42 @@ class EppmContext:
     def c2f_step(self, level, kind):
         """One coarse-to-fine step on the context's band: 0 = upsample + refine (-> FLOW_TMP), 1 = smoothing, 2 = final smoothing."""
         self._check(self.lib.eppm_tiled_c2f_step(self._ctx, level, kind), "eppm_tiled_c2f_step")
+
+    # --- one large frame tiled over the GPUs of a box (BASELINE config 4), driven by the library over NCCL ------------------------------
+    def tiled_init(self, rank, world):
+        """Collective over torch.distributed's default group: rank 0 draws the NCCL id (eppm_tiled_unique_id), everyone joins
+        (eppm_tiled_init).  The library's own communicator is separate from torch's."""
+        import torch
+        import torch.distributed as dist
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            self._check(self.lib.eppm_tiled_unique_id(buf), "eppm_tiled_unique_id")
+        if world > 1:
+            t = torch.tensor(list(buf), dtype=torch.uint8)
+            if dist.get_backend() == "nccl":
+                t = t.cuda(self.device)
+            dist.broadcast(t, src=0)
+            buf = (C.c_ubyte * 128)(*t.cpu().tolist())
+        self._check(self.lib.eppm_tiled_init(self._ctx, rank, world, buf), "eppm_tiled_init")
+
+    def compute_tiled_device(self, d_img1, d_img2, d_flow):
+        """Collective: the same full pair [1,h,w,3] on every rank, the full flow [1,h,w,2] on every rank; stream-ordered."""
+        _check_array(d_img1, (d_img1.shape[0], self.h, self.w, 3), np.uint8, "d_img1", device=self.device)
+        _check_array(d_img2, (d_img2.shape[0], self.h, self.w, 3), np.uint8, "d_img2", device=self.device)
+        _check_array(d_flow, (d_flow.shape[0], self.h, self.w, 2), np.float32, "d_flow", device=self.device)
+        with self._ordered():
+            self._check(self.lib.eppm_compute_tiled_device(self._ctx, _ptr(d_img1), _ptr(d_img2), _ptr(d_flow)), "eppm_compute_tiled_device")
+
+    def compute_tiled_host(self, img1, img2, out=None, want_flow=True):
+        """Collective, host buffers [1,h,w,3]; returns the flow [1,h,w,2] (None when want_flow is False)."""
+        _check_array(img1, (1, self.h, self.w, 3), np.uint8, "img1")
+        _check_array(img2, (1, self.h, self.w, 3), np.uint8, "img2")
+        if want_flow and out is None:
+            out = np.empty((1, self.h, self.w, 2), np.float32)
+        if out is not None:
+            _check_array(out, (1, self.h, self.w, 2), np.float32, "out")
+        self._check(self.lib.eppm_compute_tiled_host(self._ctx, _ptr(img1), _ptr(img2), _ptr(out) if want_flow else None), "eppm_compute_tiled_host")
+        return out if want_flow else None
 
     def eval_flow(self, d_flow, d_gt, n, border=0, outlier_thresh=3.0):
         """Device-side EPE / AAE / outlier share of n flows against ground truth (bao_calc_flow_error semantics); list of dicts."""

@@ -45,6 +45,31 @@ static void host_luts(eppm_context* c) {
     for (int i = 0; i < 21; i++) c->smooth_lut.g[i] = i <= 2 * p.blf_sig_s ? expf(-float(i * i) / float(bs * bs)) : 0.f;  // refine:812
 }
 
+bool ensure_pm_buffers(eppm_context* c) {
+    if (c->pm_arena.base) return true;
+    const eppm_params& p = c->prm;
+    const LevelGeom& gc = c->lv[c->n_levels - 1];
+    const size_t B = c->max_batch, nc = (size_t)gc.w * gc.h;
+    for (int pass = 0; pass < 2; pass++) {
+        Arena& A = c->pm_arena;
+        A.used = 0;
+        if (pass == 1 && !cuda_ok(cudaMalloc((void**)&A.base, A.size), "cudaMalloc(PatchMatch arena)")) { A.base = nullptr; return false; }
+        const int sl = p.prop_seg_length;
+        // chains of a pass: scan lines (rounded up to whole warps) x segments per line
+        const size_t thr_row = (size_t)((gc.h + 31) & ~31) * ((gc.w + sl - 1) / sl), thr_col = (size_t)((gc.w + 31) & ~31) * ((gc.h + sl - 1) / sl);
+        const size_t thr = 2 * B * (thr_row > thr_col ? thr_row : thr_col);
+        c->prop_prev = A.take<short2>(thr);
+        c->prop_queue = A.take<int4>(thr);
+        c->prop_memo = A.take<int4>(2 * B * nc);
+        c->prop_count = A.take<int>((size_t)(p.num_iter > 0 ? p.num_iter : 1) * 4 * sl);
+        c->rng_init = A.take<short2>(nc);
+        c->rng_search = A.take<short2>((size_t)(p.num_iter > 0 ? p.num_iter : 1) * (p.num_rand_guess > 0 ? p.num_rand_guess : 1) * nc);
+        if (pass == 0) A.size = A.used;
+    }
+    cudaMemsetAsync(c->prop_memo, 0xff, (size_t)2 * B * nc * sizeof(int4), c->stream);
+    return true;
+}
+
 // Every entry point runs on the context's device and puts the caller's current device back afterwards (a process that drives several
 // GPUs from one thread, or Python's garbage collector calling eppm_destroy at an arbitrary moment, must not find its device changed).
 struct DeviceScope {
@@ -147,7 +172,6 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         return EPPM_ERR_ARG;
     }
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->n_sm = v; }
-    c->variant = getenv("EPPM_VARIANT") ? atoi(getenv("EPPM_VARIANT")) : 0;
     c->inplace = p.inplace_filters != 0 || (getenv("EPPM_INPLACE_LEGACY") && atoi(getenv("EPPM_INPLACE_LEGACY")) != 0);
     c->pm_pad_kb = getenv("EPPM_PM_PAD_KB") ? atoi(getenv("EPPM_PM_PAD_KB")) : 0;
     c->profile = getenv("EPPM_PROFILE") && atoi(getenv("EPPM_PROFILE")) != 0;
@@ -168,6 +192,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming);
     }
 
+    c->variant = getenv("EPPM_VARIANT") ? atoi(getenv("EPPM_VARIANT")) : 0;
     // ---- arena: two passes (measure, then carve) ----
     const size_t B = max_batch;
     for (int pass = 0; pass < 2; pass++) {
@@ -192,7 +217,8 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         for (int i = 0; i < c->n_levels; i++) c->gauss[i].d_w = A.take<float>(7 * 7 + 1);
         const size_t nc = (size_t)gc.w * gc.h;
         for (int img = 0; img < 2; img++) c->pixT[img] = A.take<float4>(B * gc.plane);
-        for (int img = 0; img < 2; img++) c->pixQ[img] = A.take<float4>(B * (size_t)make_qgeom(gc.pw, gc.ph).plane);
+        if (c->variant & EPPM_VAR_PM_Q)
+            for (int img = 0; img < 2; img++) c->pixQ[img] = A.take<float4>(B * (size_t)make_qgeom(gc.pw, gc.ph).plane);
         for (int d = 0; d < 2; d++) {
             c->nnf[d] = A.take<short2>(B * nc);
             c->cost[d] = A.take<float>(B * nc);
@@ -200,18 +226,9 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         c->nnf_tmp = A.take<short2>(B * nc);
         c->occl_list = A.take<int>(B * nc);
         c->occl_count = A.take<int>(64);
-        {
-            const int sl = p.prop_seg_length;
-            // chains of a pass: scan lines (rounded up to whole warps) x segments per line
-            const size_t thr_row = (size_t)((gc.h + 31) & ~31) * ((gc.w + sl - 1) / sl), thr_col = (size_t)((gc.w + 31) & ~31) * ((gc.h + sl - 1) / sl);
-            const size_t thr = 2 * B * (thr_row > thr_col ? thr_row : thr_col);
-            c->prop_prev = A.take<short2>(thr);
-            c->prop_queue = A.take<int4>(thr);
-            c->prop_memo = A.take<int4>(2 * B * nc);
-            c->prop_count = A.take<int>((size_t)(p.num_iter > 0 ? p.num_iter : 1) * 4 * sl);
-        }
-        c->rng_init = A.take<short2>(nc);
-        c->rng_search = A.take<short2>((size_t)(p.num_iter > 0 ? p.num_iter : 1) * (p.num_rand_guess > 0 ? p.num_rand_guess : 1) * nc);
+        // the PatchMatch-only buffers (random tables, propagation queue, memo) live in a second arena that the first PatchMatch of the
+        // context allocates (ensure_pm_buffers): the legacy stage functions create single-level contexts for levels that never run
+        // PatchMatch, and rng_search alone is 500 MB at 1920 x 1080
         for (int i = 0; i < c->n_levels; i++) c->flow[i] = A.take<float2>(B * c->lv[i].w * c->lv[i].h);
         c->flow_tmp = A.take<float2>(B * c->lv[0].w * c->lv[0].h);
         if (pass == 0) A.size = A.used;
@@ -276,9 +293,11 @@ void eppm_destroy(eppm_context* c) {
     if (!c) return;
     DeviceScope dev_scope(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->tile_comm) eppm_tiled_shutdown(c);
     for (int img = 0; img < 2; img++)
         if (c->tex_pm[img]) cudaDestroyTextureObject(c->tex_pm[img]);
     if (c->arena.base) cudaFree(c->arena.base);
+    if (c->pm_arena.base) cudaFree(c->pm_arena.base);
     for (int i = 0; i < 2; i++)
         if (c->h_pinned_in[i]) cudaFreeHost(c->h_pinned_in[i]);
     if (c->h_pinned_out) cudaFreeHost(c->h_pinned_out);
@@ -642,7 +661,7 @@ long eppm_write_plane(eppm_context* c, int which, int level, int pair, const voi
         return EPPM_ERR_ARG;
     }
     // a caller-written field voids what the propagation remembers about candidates it has already scored
-    if (which != EPPM_PLANE_FLOW) cudaMemset(c->prop_memo, 0xff, (size_t)2 * c->max_batch * nc * sizeof(int4));
+    if (which != EPPM_PLANE_FLOW && c->prop_memo) cudaMemset(c->prop_memo, 0xff, (size_t)2 * c->max_batch * nc * sizeof(int4));
     return cuda_ok(e, "write_plane copy") ? bytes : EPPM_ERR_CUDA;
 }
 

@@ -96,6 +96,7 @@ struct eppm_context {
     float stage_ms[5] = {};
 
     eppm::Arena arena;
+    eppm::Arena pm_arena;                        // PatchMatch-only buffers, allocated by the first PatchMatch of the context (ensure_pm_buffers)
     // inputs staged on the device for the host-buffer API
     uint8_t* d_rgb[2] = {nullptr, nullptr};      // [B][h][w][3]
     float* d_flow_out = nullptr;                 // [B][h][w][2]
@@ -136,6 +137,8 @@ struct eppm_context {
     CUtensorMap tmap_pix0[eppm::MAX_LEVELS];     // TMA descriptors of the image-1 packed planes (smoothing tile loads)
     int tmap_ok[eppm::MAX_LEVELS] = {};
     int tmap_box_h = 0;                          // tile height the tensor maps were encoded for
+    void* tile_comm = nullptr;                   // ncclComm_t of the tiling group (tiled.cu); rank / size below
+    int tile_rank = 0, tile_world = 0;
     int band_y0 = 0, band_y1 = 0;                // rows of the coarsest level this context owns (whole level unless tiled across GPUs)
     eppm::AffineTab aff_tab[eppm::MAX_LEVELS];   // per level (pitch): verified sample-site tables of the plane-fitting refine
     int aff_ok[eppm::MAX_LEVELS] = {};
@@ -163,6 +166,7 @@ void band_rows(const eppm_context* c, int level, int* y0, int* y1);
 void run_consistency(eppm_context* c);
 void run_c2f(eppm_context* c, float* d_flow_out);
 void build_rng_tables(eppm_context* c);
+bool ensure_pm_buffers(eppm_context* c);   // second arena: random tables, propagation queue / memo (lazily, legacy single-level contexts rarely need them)
 void ensure_rng_tables(eppm_context* c);   // builds them on the context's stream the first time a PatchMatch is queued
 void build_gauss_tables(eppm_context* c);
 bool build_affine_tab(AffineTab& t, int pw, int w, int h, int stride = 2, bool allow_exception = false);

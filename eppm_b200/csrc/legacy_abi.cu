@@ -18,27 +18,45 @@ using namespace eppm;
 namespace {
 
 std::mutex g_mu;
+// One legacy call at a time: like the reference (file-scope textures and __constant__ tables, one global RNG state) the stage functions are
+// not re-entrant -- two host threads would otherwise share one cached context.  Held by Scope for the duration of a call.
+std::recursive_mutex g_call_mu;
+constexpr size_t MAX_CACHED = 8;   // contexts per cache; the least recently used one is destroyed beyond that (a caller cycling through frame sizes)
+unsigned long long g_use_clock = 0;
+std::map<eppm_context*, unsigned long long> g_last_use;
 typedef std::map<std::tuple<int, int, int>, eppm_context*> CtxCache;   // keyed by (device, h, w)
 CtxCache g_single;    // single-level contexts
 CtxCache g_pyramid;   // full-pyramid contexts, (h, w) of level 0
 
 void complain(const char* where) { fprintf(stderr, "EPPM(b200) %s: %s\n", where, eppm_last_error()); }
 
+// Returns with g_call_mu HELD when it returns a context (the caller's Scope adopts and releases it): the context cannot be evicted or
+// used by another thread between the lookup and the end of the call.
 eppm_context* get_ctx(CtxCache& cache, int h, int w, int levels) {
+    g_call_mu.lock();
     std::lock_guard<std::mutex> lk(g_mu);
     int dev = 0;
     cudaGetDevice(&dev);   // the caller's current device, like the reference's implicit context
     const std::tuple<int, int, int> key(dev, h, w);
     auto it = cache.find(key);
-    if (it != cache.end() && it->second->n_levels == levels) return it->second;
-    if (it != cache.end()) { eppm_destroy(it->second); cache.erase(it); }
+    if (it != cache.end() && it->second->n_levels == levels) { g_last_use[it->second] = ++g_use_clock; return it->second; }
+    if (it != cache.end()) { g_last_use.erase(it->second); eppm_destroy(it->second); cache.erase(it); }
+    while (cache.size() >= MAX_CACHED) {   // evict the least recently used context
+        auto lru = cache.begin();
+        for (auto jt = cache.begin(); jt != cache.end(); ++jt)
+            if (g_last_use[jt->second] < g_last_use[lru->second]) lru = jt;
+        g_last_use.erase(lru->second);
+        eppm_destroy(lru->second);
+        cache.erase(lru);
+    }
     eppm_params p;
     eppm_default_params(&p);
     p.pyr_levels = levels;
     eppm_context* c = nullptr;
-    if (eppm_create(&c, dev, h, w, 1, &p) != EPPM_OK) { complain("context"); return nullptr; }
+    if (eppm_create(&c, dev, h, w, 1, &p) != EPPM_OK) { complain("context"); g_call_mu.unlock(); return nullptr; }
     c->n_cur = 1;
     cache[key] = c;
+    g_last_use[c] = ++g_use_clock;
     return c;
 }
 
@@ -46,7 +64,8 @@ eppm_context* get_ctx(CtxCache& cache, int h, int w, int levels) {
 struct Scope {
     eppm_context* c;
     const char* name;
-    Scope(eppm_context* c_, const char* n) : c(c_), name(n) { cudaStreamSynchronize(0); }
+    std::unique_lock<std::recursive_mutex> lk;
+    Scope(eppm_context* c_, const char* n) : c(c_), name(n), lk(g_call_mu, std::adopt_lock) { cudaStreamSynchronize(0); }
     ~Scope() {
         if (c && !cuda_ok(cudaStreamSynchronize(c->stream), name)) complain(name);
     }

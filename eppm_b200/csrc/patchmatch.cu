@@ -80,6 +80,7 @@ void build_rng_tables(eppm_context* c) {
 
 void ensure_rng_tables(eppm_context* c) {
     if (c->rng_ready) return;
+    if (!ensure_pm_buffers(c)) return;   // the launches that follow fail with the recorded error
     build_rng_tables(c);   // same stream as the PatchMatch kernels that follow
     c->rng_ready = 1;
 }

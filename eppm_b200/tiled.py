@@ -1,4 +1,6 @@
-"""Spatial tiling of ONE large frame pair across the GPUs of a box (BASELINE config 4).
+"""Spatial tiling of ONE large frame pair across the GPUs of a box (BASELINE config 4) -- the Python REFERENCE of the
+schedule.  The product path is in the library (eppm_compute_tiled_device / _host, csrc/tiled.cu: the same schedule with NCCL calls enqueued
+by the library); this module keeps the schedule testable on CPU with gloo (tests/test_cpu.py) and serves as its executable description.
 
 One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Every rank holds the full frame pair and builds the full
 pyramids itself (prepare is ~0.2 ms; targets of the NNF are unbounded, so the images cannot be banded), but owns only a band of
@@ -109,7 +111,7 @@ def compute_flow_tiled(ctx, d_img1, d_img2, rank, world):
 
     chk(lib.eppm_set_band(c, rank, world), "eppm_set_band")
     try:
-        seg = 10
+        seg = int(ctx.params.prop_seg_length)   # the schedule follows the context's parameters (a band is whole propagation segments)
         bands = band_partition(hc, seg, world)
         y0 = C.c_int(); y1 = C.c_int()
         chk(lib.eppm_band_rows(c, L, C.byref(y0), C.byref(y1)), "eppm_band_rows")
@@ -118,7 +120,7 @@ def compute_flow_tiled(ctx, d_img1, d_img2, rank, world):
         cost = [device_tensor(lib.eppm_device_plane(c, api.PLANE_COST_FWD + d, L), (hc, wc), torch.float32) for d in range(2)]
         with torch.cuda.stream(stream):
             ctx.stage_prepare(d_img1, d_img2, 1)
-            n_iter = 10
+            n_iter = int(ctx.params.num_iter)
             chk(lib.eppm_tiled_pm_steps(c, 0, 1), "pm init")
             for it in range(n_iter):
                 s = 1 + 5 * it

@@ -155,6 +155,20 @@ int eppm_tiled_pm_steps(eppm_context* ctx, int first_step, int end_step);
 int eppm_tiled_c2f_step(eppm_context* ctx, int level, int kind);
 void* eppm_device_plane(eppm_context* ctx, int which, int level);
 
+/* The same tiling driven BY THE LIBRARY (BASELINE config 4): one process and one context (max_batch >= 1) per GPU, every rank calls the same
+ * functions in the same order.  Halo rows and band gathers travel through NCCL (NVLink / NVSwitch), enqueued on the context's stream; NCCL is
+ * loaded at run time (libnccl.so.2; EPPM_NCCL_LIB overrides), the library does not link against it.
+ *   eppm_tiled_unique_id(id): 128 bytes (ncclUniqueId) from ONE rank, which the caller hands to all ranks by any means (MPI, torch.distributed, a file)
+ *   eppm_tiled_init(ctx, rank, world, id): collective; joins the communicator and fixes the rank's band (whole propagation segments; needs at least two per band)
+ *   eppm_compute_tiled_device / _host: collective; inputs are the SAME full frame pair on every rank, the full flow [h][w][2] arrives on every rank
+ *       (host variant: flow may be NULL on ranks that do not want the copy).  Bit-identical to eppm_compute_batch_* on one GPU.
+ *   eppm_tiled_shutdown(ctx): leaves the communicator (also done by eppm_destroy). */
+int eppm_tiled_unique_id(void* id_out_128_bytes);
+int eppm_tiled_init(eppm_context* ctx, int rank, int world, const void* unique_id);
+int eppm_compute_tiled_device(eppm_context* ctx, const uint8_t* d_img1, const uint8_t* d_img2, float* d_flow);
+int eppm_compute_tiled_host(eppm_context* ctx, const uint8_t* img1, const uint8_t* img2, float* flow);
+int eppm_tiled_shutdown(eppm_context* ctx);
+
 /* Exhaustive device self-test: number of floats x with bit patterns in [lo_bits, hi_bits) for which the 3-instruction
  * constant division (q0 = x*r; q = fma(fma(q0,-d,x), r, q0), r = RN(1/d)) differs from div.rn(x, d); 0 = exact everywhere.
  * eppm_smooth_uses_fast_div reports whether a context's smoothing kernel was allowed to use it. */
