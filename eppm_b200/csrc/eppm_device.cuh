@@ -161,6 +161,22 @@ __device__ __forceinline__ float census_lut_ref(Lut0, const float4& p1, const fl
     asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(off), "n"(SHARED_WINDOW_USER_BASE));
     return v;
 }
+// Census cost looked up by the XOR BYTE itself (256 entries) instead of by its popcount (9 entries): no POPC, which shares the XU pipe with the
+// two MUFU.EX2 of a sample (the refine kernel's top stall is the XU pipe's throttle).  A plain 256-entry table would serialise on bank
+// conflicts (32 lanes, arbitrary entries), so the table is replicated REP times: entry e, copy k at word e * REP + k, lane l reads copy
+// l % REP -- lanes of different copies never share a bank.  The table sits at the shared-window base (see Lut0); `lane_off` = (lane % REP) * 4.
+template <int REP>
+struct LutX {
+    unsigned lane_off;
+};
+template <int REP>
+__device__ __forceinline__ float census_lut_ref(LutX<REP> l, const float4& p1, const float4& p2) {
+    const unsigned e = (__float_as_uint(p1.w) ^ __float_as_uint(p2.w)) & 0xffu;
+    const unsigned off = e * (REP * 4) + l.lane_off;
+    float v;
+    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(off), "n"(SHARED_WINDOW_USER_BASE));
+    return v;
+}
 template <class LutRef>
 __device__ __forceinline__ void sample_eval(const float4& p1, const PixPk& p1k, const float4& p2, const PixPk& c2k, float d1, LutRef s_census,
                                             float& cost, float& t2) {

@@ -141,8 +141,9 @@ template <int STRIDE>
 __global__ void __launch_bounds__(128) k_pm_init(PmArgs a, const short2* __restrict__ rng_init, const __grid_constant__ CostLut lut) {
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y;
-    if (x >= a.w) return;
+    // CTA = blockDim.x consecutive pixels of blockDim.y consecutive rows (a 2-D tile: the patch windows of its pixels overlap in both directions)
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= a.w || y >= a.y1) return;
     const float4 *A, *B; short2* nnf; float* cost;
     pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
     const short2 t = rng_init[y * a.w + x];
@@ -1005,8 +1006,9 @@ __global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __res
                                                    const __grid_constant__ CostLut lut) {
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y;
-    if (x >= a.w) return;
+    // CTA = blockDim.x consecutive pixels of blockDim.y consecutive rows (a 2-D tile: the patch windows of its pixels overlap in both directions)
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= a.w || y >= a.y1) return;
     const float4 *A, *B; short2* nnf; float* cost;
     pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
     const int id = y * a.w + x;
@@ -1043,14 +1045,15 @@ __global__ void __launch_bounds__(128) k_pm_search(PmArgs a, const short2* __res
 // colours, offsets and accumulators of the group only), more resident warps for a kernel that waits on its gathers; the image-1 side
 // of a sample is recomputed per pass.
 template <int STRIDE, int NG, int NTEX, int NSPLIT, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_pm_search_joint(PmArgs a, const short2* __restrict__ rng, int search_range, int radius_min,
+__global__ void __launch_bounds__(MINB >= 4 ? 128 : 256, MINB) k_pm_search_joint(PmArgs a, const short2* __restrict__ rng, int search_range, int radius_min,
                                                                const __grid_constant__ CostLut lut) {
     constexpr int GS = NG / NSPLIT;
     static_assert(GS * NSPLIT == NG, "guesses must split evenly");
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y;
-    if (x >= a.w) return;
+    // CTA = blockDim.x consecutive pixels of blockDim.y consecutive rows (a 2-D tile: the patch windows of its pixels overlap in both directions)
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= a.w || y >= a.y1) return;
     const float4 *A, *B; short2* nnf; float* cost;
     pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
     const unsigned lut_base = census_lut_base(s_census);
@@ -1151,8 +1154,9 @@ __global__ void __launch_bounds__(128, MINB) k_pm_search_q(PmArgs a, const short
     constexpr int NG = 6;
     __shared__ float s_census[CENSUS_LUT_N];
     load_census_lut(s_census, lut);
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y;
-    if (x >= a.w) return;
+    // CTA = blockDim.x consecutive pixels of blockDim.y consecutive rows (a 2-D tile: the patch windows of its pixels overlap in both directions)
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= a.w || y >= a.y1) return;
     const float4 *A, *B; short2* nnf; float* cost;
     pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
     const float4 *QA, *QB;
@@ -1474,13 +1478,26 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
             }
     }
     // one thread per pixel of a row segment: 96 threads when that wastes fewer lanes than 128 (480 = 5 x 96 at the 1080p PatchMatch level)
-    const int bx = ((g.w + 95) / 96) * 96 < ((g.w + 127) / 128) * 128 ? 96 : 128;
-    dim3 blk(bx), grd((g.w + bx - 1) / bx, a.y1 - a.y0, n_dirs * n);
+    // The thread-per-pixel kernels (initial cost, random search) run CTAs of 16 x 16 pixels: 128 pixels of ONE row touch (128 + 18) x 19 pixels of
+    // each image per guess (22 per pixel), a 16 x 16 tile (16 + 18) x (16 + 18) (4.5 per pixel) -- the windows of a resident CTA stay in the L1
+    // (the search is bound by L1 / L2 traffic: 58 % L1 hit rate with row-segment CTAs).  EPPM_SEARCH_ROWS (1, 2, 4, 8): rows per CTA of 128 threads, tuning knob; 1 = the row-segment CTAs of round 1.
+    // measured (16 pairs, PatchMatch ms per pair): 128 x 1: 4.67, 64 x 2: 4.48, 32 x 4: 4.37, 16 x 8: 4.32, 32 x 8: 4.28, 16 x 16: 4.24 (default)
+    static const int env_rows = getenv("EPPM_SEARCH_ROWS") ? atoi(getenv("EPPM_SEARCH_ROWS")) : 16;
+    static const int env_cols = getenv("EPPM_SEARCH_COLS") ? atoi(getenv("EPPM_SEARCH_COLS")) : 16;
+    int ry = env_rows == 1 || env_rows == 2 || env_rows == 4 || env_rows == 16 ? env_rows : 8;
+    int bx = ry == 1 ? (((g.w + 95) / 96) * 96 < ((g.w + 127) / 128) * 128 ? 96 : 128) : 128 / ry;   // 128 threads: 64 x 2, 32 x 4, 16 x 8, 8 x 16
+    if (env_cols > 0 && (env_cols * ry == 128 || env_cols * ry == 256)) bx = env_cols;                // e.g. 16 x 16 or 32 x 8: 256 threads
+    const bool search_256 = bx * ry == 256 && c->prm.num_rand_guess == 6 && !(c->variant & (EPPM_VAR_SEARCH_SERIAL | EPPM_VAR_SEARCH_TEX3 | EPPM_VAR_SEARCH_SPLIT3 | EPPM_VAR_SEARCH_WARP)) &&
+                            !(STRIDE == 2 && a.q[0]);
+    if (bx * ry == 256 && !search_256) bx /= 2;   // only the default joint search has a 256-thread instantiation
+    dim3 blk(bx, ry), grd((g.w + bx - 1) / bx, (a.y1 - a.y0 + ry - 1) / ry, n_dirs * n);
     // steps [first_step, n_steps): 0 = random field + cost, then per iteration 4 propagation passes and 1 random search
     int step = 0;
     auto run = [&]() { const bool r = step >= first_step && step < n_steps; step++; return r; };
     if (run()) {
-        k_pm_init<STRIDE><<<grd, blk, 0, c->stream>>>(a, c->rng_init, c->cost_lut);
+        const dim3 blk_i(blk.x, blk.x * blk.y > 128 ? blk.y / 2 : blk.y);   // k_pm_init is bounded to 128 threads
+        const dim3 grd_i(grd.x, (a.y1 - a.y0 + blk_i.y - 1) / blk_i.y, grd.z);
+        k_pm_init<STRIDE><<<grd_i, blk_i, 0, c->stream>>>(a, c->rng_init, c->cost_lut);
         EPPM_LAUNCH_COUNT(1);
         // the evaluated-candidate memo of the propagation starts empty (-1 is no target: targets lie in [0, w] x [0, h])
         cudaMemsetAsync(c->prop_memo, 0xff, (size_t)2 * n * g.w * g.h * sizeof(int4), c->stream);
@@ -1531,7 +1548,9 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
             continue;
         }
 #define EPPM_SEARCH(NT, NS, MB) k_pm_search_joint<STRIDE, 6, NT, NS, MB><<<grd, blk, pm_pad_bytes(c, (const void*)k_pm_search_joint<STRIDE, 6, NT, NS, MB>), c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut)
-        if (joint && ((v & EPPM_VAR_SEARCH_NOTEX) || !tex_ok)) EPPM_SEARCH(0, 1, 4);
+        if (joint && blk.x * blk.y == 256 && ((v & EPPM_VAR_SEARCH_NOTEX) || !tex_ok)) EPPM_SEARCH(0, 1, 2);
+        else if (joint && blk.x * blk.y == 256) EPPM_SEARCH(2, 1, 2);   // 256-thread tiles: two CTAs of 128 registers per SM
+        else if (joint && ((v & EPPM_VAR_SEARCH_NOTEX) || !tex_ok)) EPPM_SEARCH(0, 1, 4);
         else if (joint && (v & EPPM_VAR_SEARCH_TEX3)) EPPM_SEARCH(3, 1, 4);
         else if (joint && (v & EPPM_VAR_SEARCH_SPLIT3)) EPPM_SEARCH(2, 3, 8);
         else if (joint) EPPM_SEARCH(2, 1, 4);

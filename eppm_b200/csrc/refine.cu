@@ -413,13 +413,21 @@ EPPM_PRAGMA(unroll RF_JUNROLL)
 
 // LUT0: the census table lives at the user base of the shared window (see Lut0); FAST: warps whose 96 candidates are all valid take a loop
 // without validity guards.
-template <int MINB, int STRIDE, bool LUT0, bool FAST>
+template <int MINB, int STRIDE, bool LUT0, bool FAST, int LUTX = 0>
 __global__ void __launch_bounds__(RF_PIX * 3, MINB)
     k_c2f_refine_row(RefineArgs a, const __grid_constant__ CostLut lut, const __grid_constant__ AffineTab tab) {
-    extern __shared__ float s_dyn[];             // [0, 16): census table (9 used), then s_best[9][RF_PIX]; no static shared memory in this kernel
+    // no static shared memory in this kernel.  LUTX = 0: [0, 16) census table by popcount (9 used), then s_best[9][RF_PIX];
+    // LUTX = REP: [0, 256 * REP) census table by XOR byte, replicated (see LutX), then s_best
+    extern __shared__ float s_dyn[];
     float* s_census = s_dyn;
-    float (*s_best)[RF_PIX] = reinterpret_cast<float (*)[RF_PIX]>(s_dyn + 16);
-    load_census_lut(s_census, lut);
+    constexpr int LUT_WORDS = LUTX ? 256 * LUTX : 16;
+    float (*s_best)[RF_PIX] = reinterpret_cast<float (*)[RF_PIX]>(s_dyn + LUT_WORDS);
+    if (LUTX) {
+        for (int k = threadIdx.x; k < 256 * LUTX; k += blockDim.x) s_dyn[k] = lut.census[__popc((unsigned)k / LUTX)];
+        __syncthreads();
+    } else {
+        load_census_lut(s_census, lut);
+    }
     const unsigned lut_base = census_lut_base(s_census);
     const int n = threadIdx.x >> 5, pl = threadIdx.x & 31;   // n: candidate row of this warp
     const int x = blockIdx.x * RF_PIX + pl, y = a.y0 + blockIdx.y;
@@ -461,7 +469,10 @@ __global__ void __launch_bounds__(RF_PIX * 3, MINB)
         PixPk c2k[3];
 #pragma unroll
         for (int m = 0; m < 3; m++) c2k[m] = pack_pix(ldpix(Pc + (m - 1)));
-        if (LUT0) {
+        if (LUTX) {
+            const LutX<LUTX ? LUTX : 1> lx = {(unsigned)(pl % (LUTX ? LUTX : 1)) * 4u};
+            refine_row_loop<STRIDE, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, lx, cs, ws);
+        } else if (LUT0) {
             if (warp_all) refine_row_loop<STRIDE, false>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws);
             else refine_row_loop<STRIDE, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws);
         } else {
@@ -1058,6 +1069,14 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                     case 9: EPPM_RR(false, true); break;
                     case 10: if (lut0_window_base_ok(c->device)) EPPM_RR(true, false); else EPPM_RR(false, false); break;
                     case 11: if (lut0_window_base_ok(c->device)) EPPM_RR(true, true); else EPPM_RR(false, true); break;
+#define EPPM_RX(REP) { static bool at##REP[64] = {}; const size_t sm = (256 * REP + 9 * RF_PIX) * sizeof(float); \
+                       if (!at##REP[c->device & 63]) { cudaFuncSetAttribute(k_c2f_refine_row<7, 2, true, false, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); at##REP[c->device & 63] = true; } \
+                       k_c2f_refine_row<7, 2, true, false, REP><<<grd, blk, sm, c->stream>>>(a, c->cost_lut, *tabp); }
+                    case 12: if (lut0_window_base_ok(c->device)) EPPM_RX(1) else EPPM_RR(false, false); break;
+                    case 13: if (lut0_window_base_ok(c->device)) EPPM_RX(8) else EPPM_RR(false, false); break;
+                    case 14: if (lut0_window_base_ok(c->device)) EPPM_RX(16) else EPPM_RR(false, false); break;
+                    case 15: if (lut0_window_base_ok(c->device)) EPPM_RX(32) else EPPM_RR(false, false); break;
+#undef EPPM_RX
 #undef EPPM_RR
                     case 1: EPPM_RT(RF_TAB2_MINBLOCKS, true, false); break;
                     case 2: EPPM_RT(RF_TAB2_MINBLOCKS, false, true); break;

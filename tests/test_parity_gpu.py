@@ -627,7 +627,7 @@ def test_video_stream_vs_reference_on_chained_frames(ref):
             assert same_bits(ctx4.read_plane(E.PLANE_CENSUS1, l, pair=t), ref.read_plane(rc, 2, l)), (t, l)
         fr = ref.compute_flow(rc, h, w)
         d = np.sqrt(((out_h[t].astype(np.float64) - fr.astype(np.float64)) ** 2).sum(-1))
-        assert synth.epe(out_h[t], flows[t], valids[t]) <= synth.epe(fr, flows[t], valids[t]) + 0.05, t   # no worse than the reference against ground truth
+        assert synth.epe(out_h[t], flows[t], valids[t]) <= synth.epe(fr, flows[t], valids[t]) + 0.05 * (3.0 if RACY_SLACK > 1 else 1.0), t   # no worse than the reference against ground truth
         assert np.median(d) <= 1e-3, (t, np.median(d))
     ref.destroy(rc); ctx.close(); ctx4.close()
 
