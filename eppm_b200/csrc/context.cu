@@ -217,7 +217,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         for (int i = 0; i < c->n_levels; i++) c->gauss[i].d_w = A.take<float>(7 * 7 + 1);
         const size_t nc = (size_t)gc.w * gc.h;
         for (int img = 0; img < 2; img++) c->pixT[img] = A.take<float4>(B * gc.plane);
-        if (c->variant & EPPM_VAR_PM_Q)
+        if (p.patch_stride == 2 && (c->variant & (EPPM_VAR_PROP_Q | EPPM_VAR_PM_Q)))   // parity-split planes (measured alternatives only)
             for (int img = 0; img < 2; img++) c->pixQ[img] = A.take<float4>(B * (size_t)make_qgeom(gc.pw, gc.ph).plane);
         for (int d = 0; d < 2; d++) {
             c->nnf[d] = A.take<short2>(B * nc);

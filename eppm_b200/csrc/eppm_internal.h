@@ -35,6 +35,7 @@ enum {
     EPPM_VAR_PM_Q = 524288,            // PatchMatch kernels read parity-split (Q) planes with 256-bit loads, two samples per request (measured slower: 4.79-4.88 vs 4.67 ms per pair;
                                        //   a 256-bit request costs the L1 as many wavefronts as two 128-bit ones)
     EPPM_VAR_REFINE_COLUMN = 1048576,  // table refine with warp = candidate column, thread = three candidate rows (round-1 default) instead of warp = candidate row
+    EPPM_VAR_PROP_Q = 2097152,         // propagation: the warp-per-evaluation scoring kernel reads the parity-split planes (dense sample rows; measured slower: 4.45 vs 4.24 ms per pair)
     EPPM_VAR_PROP_WARP_FULL = 131072,  // propagation queue scored by one warp per evaluation with ALL samples staged in shared memory (13 KB per warp starves the L1)
     EPPM_VAR_PROP_NOSKIP = 8,      // propagation: evaluate candidates that equal the current target (the reference does)
 };

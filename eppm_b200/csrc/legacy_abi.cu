@@ -192,7 +192,7 @@ void baoCudaPatchMatch(short2* d_disp_vec, float* d_cost, uchar4* d_img1, uchar4
     op_pack_foreign(c->stream, d_img1, img_pitch, d_census1, census_pitch, c->pix[0][0], g);
     op_pack_foreign(c->stream, d_img2, img_pitch, d_census2, census_pitch, c->pix[1][0], g);
     for (int img = 0; img < 2; img++) op_transpose_plane(c->stream, c->pix[img][0], c->pixT[img], g, 1);
-    if (c->variant & EPPM_VAR_PM_Q)
+    if (c->pixQ[0])
         for (int img = 0; img < 2; img++) op_split_plane(c->stream, c->pix[img][0], c->pixQ[img], g, 1);
     run_patchmatch_dirs(c, 1);
     copy_out(c, d_disp_vec, disp_pitch, c->nnf[0], w, h);

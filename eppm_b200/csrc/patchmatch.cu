@@ -108,6 +108,7 @@ struct PmArgs {
     // texB[dir] is the one that holds direction dir's TARGET image, texB_off[dir] the texel index of pair 0's padded origin in it
     const float4* q[2];     // parity-split (Q) planes of image 1 / image 2, pair 0 (null: not built)
     QGeom qg;
+    int q_search;           // 1: the thread-per-pixel kernels (initial cost, random search, thread-mode queue scoring) read the Q planes too (EPPM_VAR_PM_Q)
     cudaTextureObject_t tex[2];      // per image: linear texture that holds its packed planes (0 = none)
     unsigned tex_off[2];             // texel index of pair 0's padded origin of pix[image] inside that texture
 };
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(128) k_pm_init(PmArgs a, const short2* __restr
     pm_select<false>(a, blockIdx.z, A, B, nnf, cost);
     const short2 t = rng_init[y * a.w + x];
     nnf[y * a.w + x] = t;
-    if (STRIDE == 2 && a.q[0]) {
+    if (STRIDE == 2 && a.q_search) {
         const float4 *QA, *QB;
         pm_select_q(a, blockIdx.z, QA, QB);
         cost[y * a.w + x] = patch_cost_q(A, B, QA, QB, a.qg, a.pw, x, y, t.x, t.y, lut, s_census);
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_prop_eval_w(PmArgs a, const int4
 // (cost_sum, weight_sum) registers -- still sample order -- and the next round reuses the buffer.  The loads of U items are issued
 // together (4 x U 16-byte loads in flight per lane).  The samples past the last full round (4 of 100 at stride 2) are scored for
 // 32 / 4 items at once, lane l = (item l / 4, sample l % 4), instead of a round with 28 idle lanes per item.
-template <int STRIDE, int BATCH, int WARPS>
+template <int STRIDE, int BATCH, int WARPS, bool USEQ>
 __global__ void __launch_bounds__(WARPS * 32) k_prop_eval_r(PmArgs a, const int4* __restrict__ queue, const int* __restrict__ counter, short2* __restrict__ st_prev,
                                                            const __grid_constant__ CostLut lut) {
     typedef Coop<STRIDE> C;
@@ -573,16 +574,26 @@ __global__ void __launch_bounds__(WARPS * 32) k_prop_eval_r(PmArgs a, const int4
     const int n = *counter;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2 (*stage)[PITCH] = s_stage[warp];
+    // USEQ: the samples are read from the parity-split (Q) planes, where the 10 x 10 samples of a patch are a dense block of ONE sub-plane
+    // (sample (i, j) at origin + i * qp + j): a warp-wide request covers 3.2 sample rows of 160 contiguous bytes instead of 304-byte
+    // spans with every second pixel unused -- half the L1 wavefronts per request.  Centre pixels still come from the packed planes.
     int soff[C::R];
     float sgg[C::R];
     coop_sites<STRIDE>(lane, a.pw, lut, soff, sgg);
+    if (USEQ) {
+#pragma unroll
+        for (int r = 0; r < C::R; r++) {
+            const int sx = min(lane + 32 * r, C::NS - 1);
+            soff[r] = (sx / C::NJ) * a.qg.qp + (sx % C::NJ);   // relative to the Q element of the patch's top-left sample
+        }
+    }
     // tail site of this lane: sample 32 RF + lane % TS
     int toff = 0;
     float tgg = 0.f;
     if (TS > 0) {
         const int s = 32 * RF + lane % (TS > 0 ? TS : 1);
         const int i = -PATCH_R + STRIDE * (s / C::NJ), j = -PATCH_R + STRIDE * (s % C::NJ);
-        toff = i * a.pw + j;
+        toff = USEQ ? (s / C::NJ) * a.qg.qp + (s % C::NJ) : i * a.pw + j;
         tgg = lut.gg[i < 0 ? -i : i][j < 0 ? -j : j];
     }
     for (int base = (blockIdx.x * WARPS + warp) * BATCH; base < n; base += gridDim.x * WARPS * BATCH) {
@@ -604,8 +615,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_prop_eval_r(PmArgs a, const int4
                     const unsigned ob = (unsigned)((short)(cand & 0xffff) + PAD) + (unsigned)((cand >> 16) + PAD) * (unsigned)a.pw;
                     c1[u] = ldpix(A + oa);
                     c2[u] = ldpix(B + ob);
-                    p1[u] = ldpix(A + (oa + (unsigned)soff[r]));
-                    p2[u] = ldpix(B + (ob + (unsigned)soff[r]));
+                    if (USEQ) {
+                        const float4 *QA, *QB;
+                        pm_select_q(a, z, QA, QB);
+                        p1[u] = ldpix(QA + (q_index(a.qg, (pos & 0xffff) + PAD - PATCH_R, (pos >> 16) + PAD - PATCH_R) + (unsigned)soff[r]));
+                        p2[u] = ldpix(QB + (q_index(a.qg, (short)(cand & 0xffff) + PAD - PATCH_R, (cand >> 16) + PAD - PATCH_R) + (unsigned)soff[r]));
+                    } else {
+                        p1[u] = ldpix(A + (oa + (unsigned)soff[r]));
+                        p2[u] = ldpix(B + (ob + (unsigned)soff[r]));
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -639,7 +657,17 @@ __global__ void __launch_bounds__(WARPS * 32) k_prop_eval_r(PmArgs a, const int4
                 pm_select<false>(a, z, A, B, nnf, cost);
                 const unsigned oa = (unsigned)((pos & 0xffff) + PAD) + (unsigned)((pos >> 16) + PAD) * (unsigned)a.pw;
                 const unsigned ob = (unsigned)((short)(cand & 0xffff) + PAD) + (unsigned)((cand >> 16) + PAD) * (unsigned)a.pw;
-                const float4 c1 = ldpix(A + oa), c2 = ldpix(B + ob), p1 = ldpix(A + (oa + (unsigned)toff)), p2 = ldpix(B + (ob + (unsigned)toff));
+                const float4 c1 = ldpix(A + oa), c2 = ldpix(B + ob);
+                float4 p1, p2;
+                if (USEQ) {
+                    const float4 *QA, *QB;
+                    pm_select_q(a, z, QA, QB);
+                    p1 = ldpix(QA + (q_index(a.qg, (pos & 0xffff) + PAD - PATCH_R, (pos >> 16) + PAD - PATCH_R) + (unsigned)toff));
+                    p2 = ldpix(QB + (q_index(a.qg, (short)(cand & 0xffff) + PAD - PATCH_R, (cand >> 16) + PAD - PATCH_R) + (unsigned)toff));
+                } else {
+                    p1 = ldpix(A + (oa + (unsigned)toff));
+                    p2 = ldpix(B + (ob + (unsigned)toff));
+                }
                 const PixPk p1k = pack_pix(p1);
                 float ct, t2;
                 sample_eval(p1, p1k, p2, pack_pix(c2), max3abs_diff(pack_pix(c1), p1k), lut_base, ct, t2);
@@ -765,24 +793,35 @@ static void launch_propagate_queue(eppm_context* c, const PmArgs& a, int n, int 
     const int eval_blocks = cap > 0 ? min((g.total + 127) / 128, c->n_sm * cap) : (g.total + 127) / 128;
     // warp-cooperative scoring: round-major (default) or whole evaluations staged (EPPM_VAR_PROP_WARP_FULL)
     constexpr int WB = STRIDE == 1 ? 4 : 16, WW = 4;
-    constexpr int RB = 16, RW = 4;
+    constexpr int RW = 4;
     const size_t wsmem = (size_t)WW * WB * Coop<STRIDE>::NSP * sizeof(float2);
     static bool attr_w[64] = {};
     const int mode = (c->variant & EPPM_VAR_PROP_THREAD) ? 0 : (c->variant & EPPM_VAR_PROP_WARP_FULL) ? 1 : 2;
+    static const int env_batch = getenv("EPPM_PROP_BATCH") ? atoi(getenv("EPPM_PROP_BATCH")) : 8;   // tuning knob: queue items per warp (8: 4.20, 16: 4.24 ms of PatchMatch per pair)
+    const bool rq = STRIDE == 2 && a.q[0] != nullptr;   // Q planes built: the round-major kernel reads its samples from them
     if (mode && (c->device < 0 || c->device >= 64 || !attr_w[c->device])) {
         cudaFuncSetAttribute(k_prop_eval_w<STRIDE, WB, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
         // leave the larger part of the unified L1 / shared memory to the cache: the patch windows of neighbouring queue items overlap
         static const int carve = getenv("EPPM_PROP_CARVEOUT") ? atoi(getenv("EPPM_PROP_CARVEOUT")) : 40;
-        cudaFuncSetAttribute(k_prop_eval_r<STRIDE, RB, RW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_prop_eval_r<STRIDE, 16, RW, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_prop_eval_r<STRIDE, 8, RW, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_prop_eval_r<STRIDE, 16, RW, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_prop_eval_r<STRIDE, 8, RW, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (c->device >= 0 && c->device < 64) attr_w[c->device] = true;
     }
-    const int wblocks = (g.total + WB * WW - 1) / (WB * WW), rblocks = (g.total + RB * RW - 1) / (RB * RW);
+    const int rb = env_batch == 16 ? 16 : 8;
+    const int wblocks = (g.total + WB * WW - 1) / (WB * WW), rblocks = (g.total + rb * RW - 1) / (rb * RW);
     for (int t = 1; t <= sl; t++) {
         k_prop_decide<DIR><<<(g.total + 255) / 256, 256, 0, c->stream>>>(a, g, sl, t, c->prop_prev, c->prop_queue, counters + t - 1,
                                                                          (c->variant & EPPM_VAR_PROP_NOMEMO) ? nullptr : c->prop_memo);
-        if (mode == 2) k_prop_eval_r<STRIDE, RB, RW><<<rblocks, RW * 32, 0, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
+#define EPPM_EVR(B, Q) k_prop_eval_r<STRIDE, B, RW, Q><<<rblocks, RW * 32, 0, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut)
+        if (mode == 2) {
+            if (rb == 8) { if (rq) EPPM_EVR(8, true); else EPPM_EVR(8, false); }
+            else { if (rq) EPPM_EVR(16, true); else EPPM_EVR(16, false); }
+        }
+#undef EPPM_EVR
         else if (mode == 1) k_prop_eval_w<STRIDE, WB, WW><<<wblocks, WW * 32, wsmem, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
-        else if (STRIDE == 2 && a.q[0]) k_prop_eval<DIR, STRIDE, true><<<eval_blocks, 128, 0, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
+        else if (STRIDE == 2 && a.q_search) k_prop_eval<DIR, STRIDE, true><<<eval_blocks, 128, 0, c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
         else k_prop_eval<DIR, STRIDE, false><<<eval_blocks, 128, pm_pad_bytes(c, (const void*)k_prop_eval<DIR, STRIDE, false>), c->stream>>>(a, c->prop_queue, counters + t - 1, c->prop_prev, c->cost_lut);
     }
     EPPM_LAUNCH_COUNT(2 * sl);
@@ -1457,9 +1496,10 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
     a.pix[1] = c->pix[1][L];
     a.pixT[0] = c->pixT[0];
     a.pixT[1] = c->pixT[1];
-    const bool use_q = STRIDE == 2 && (c->variant & EPPM_VAR_PM_Q);
-    a.q[0] = use_q ? c->pixQ[0] : nullptr;
-    a.q[1] = use_q ? c->pixQ[1] : nullptr;
+    const bool have_q = STRIDE == 2 && c->pixQ[0] != nullptr;
+    a.q[0] = have_q ? c->pixQ[0] : nullptr;
+    a.q[1] = have_q ? c->pixQ[1] : nullptr;
+    a.q_search = have_q && (c->variant & EPPM_VAR_PM_Q) ? 1 : 0;
     a.qg = make_qgeom(g.pw, g.ph);
     a.plane = (unsigned)g.plane;
     a.pw = g.pw; a.ph = g.ph;
@@ -1488,7 +1528,7 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
     int bx = ry == 1 ? (((g.w + 95) / 96) * 96 < ((g.w + 127) / 128) * 128 ? 96 : 128) : 128 / ry;   // 128 threads: 64 x 2, 32 x 4, 16 x 8, 8 x 16
     if (env_cols > 0 && (env_cols * ry == 128 || env_cols * ry == 256)) bx = env_cols;                // e.g. 16 x 16 or 32 x 8: 256 threads
     const bool search_256 = bx * ry == 256 && c->prm.num_rand_guess == 6 && !(c->variant & (EPPM_VAR_SEARCH_SERIAL | EPPM_VAR_SEARCH_TEX3 | EPPM_VAR_SEARCH_SPLIT3 | EPPM_VAR_SEARCH_WARP)) &&
-                            !(STRIDE == 2 && a.q[0]);
+                            !(STRIDE == 2 && a.q_search);
     if (bx * ry == 256 && !search_256) bx /= 2;   // only the default joint search has a 256-thread instantiation
     dim3 blk(bx, ry), grd((g.w + bx - 1) / bx, (a.y1 - a.y0 + ry - 1) / ry, n_dirs * n);
     // steps [first_step, n_steps): 0 = random field + cost, then per iteration 4 propagation passes and 1 random search
@@ -1538,7 +1578,7 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
             EPPM_LAUNCH_COUNT(1);
             continue;
         }
-        if (joint && STRIDE == 2 && a.q[0]) {
+        if (joint && STRIDE == 2 && a.q_search) {
             static const int qtex = getenv("EPPM_SEARCH_QTEX") ? atoi(getenv("EPPM_SEARCH_QTEX")) : 0;   // tuning knob: guesses on the texture path
             const int nt = tex_ok ? qtex : 0;
             if (nt >= 2) k_pm_search_q<2, 4><<<grd, blk, 0, c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut);

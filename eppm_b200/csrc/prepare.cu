@@ -354,7 +354,7 @@ void op_pyramid_and_pack(eppm_context* c, int n, int two) {
     }
     const int L = c->n_levels - 1;
     for (int img = 0; img < two; img++) op_transpose_plane(s, c->pix[img][L], c->pixT[img], c->lv[L], n);
-    if (c->variant & EPPM_VAR_PM_Q)
+    if (c->pixQ[0])
         for (int img = 0; img < two; img++) op_split_plane(s, c->pix[img][L], c->pixQ[img], c->lv[L], n);
 }
 

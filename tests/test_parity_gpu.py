@@ -897,7 +897,7 @@ def test_variant_switches_compute_the_same_bits():
     a, b, _, _ = synth.make_batch(h, w, 2, first_idx=11, distinct=2)
     flows = {}
     try:
-        for v in (0, 1, 2, 4, 8, 16, 32, 64, 127, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 131072, 262144, 524288, 524288 + 8192, 1048576):
+        for v in (0, 1, 2, 4, 8, 16, 32, 64, 127, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 131072, 262144, 524288, 524288 + 8192, 1048576, 2097152):
             os.environ["EPPM_VARIANT"] = str(v)
             ctx = E.EppmContext(h, w, 2)
             if v == 0:
