@@ -307,7 +307,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(batch * H * W * 2 * 4), "api": "eppm_compute_batch_host (C ABI, pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_c2f_refine_tab (level 0)", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_c2f_refine_row (level 0)", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
                          "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
                          "note": "the path is FP32-issue bound, not HBM bound (SURVEY.md §8d); see roofline_alu"},
             "roofline_alu": {"bound": "fp32 issue", "kernel_samples_per_s": round(cnt["refine_l0_samples"] * n_last / (k_ms / 1e3), 1),

@@ -413,7 +413,7 @@ EPPM_PRAGMA(unroll RF_JUNROLL)
 
 // LUT0: the census table lives at the user base of the shared window (see Lut0); FAST: warps whose 96 candidates are all valid take a loop
 // without validity guards.
-template <int MINB, int STRIDE, bool LUT0, bool FAST, int LUTX = 0>
+template <int MINB, int STRIDE, bool LUT0, bool FAST, int LUTX = 0, int UNI = 0>
 __global__ void __launch_bounds__(RF_PIX * 3, MINB)
     k_c2f_refine_row(RefineArgs a, const __grid_constant__ CostLut lut, const __grid_constant__ AffineTab tab) {
     // no static shared memory in this kernel.  LUTX = 0: [0, 16) census table by popcount (9 used), then s_best[9][RF_PIX];
@@ -453,6 +453,9 @@ __global__ void __launch_bounds__(RF_PIX * 3, MINB)
     }
     const bool warp_all = FAST && __all_sync(0xffffffffu, all);
     unsigned wmask = __ballot_sync(0xffffffffu, all) == 0xffffffffu ? 7u : 0u;
+    if (UNI) {   // candidate m is scored by the whole warp when ANY lane needs it (lanes that do not discard their result; their sites are clamped into the plane)
+        wmask = (__any_sync(0xffffffffu, valid[0]) ? 1u : 0u) | (__any_sync(0xffffffffu, valid[1]) ? 2u : 0u) | (__any_sync(0xffffffffu, valid[2]) ? 4u : 0u);
+    }
     asm volatile("" : "+r"(wmask));   // opaque to the compiler: see refine_row_loop
     if (any) {
         float cs[3][4], ws[3][4];
@@ -469,7 +472,9 @@ __global__ void __launch_bounds__(RF_PIX * 3, MINB)
         PixPk c2k[3];
 #pragma unroll
         for (int m = 0; m < 3; m++) c2k[m] = pack_pix(ldpix(Pc + (m - 1)));
-        if (LUTX) {
+        if (UNI) {
+            refine_row_loop<STRIDE, false>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws);
+        } else if (LUTX) {
             const LutX<LUTX ? LUTX : 1> lx = {(unsigned)(pl % (LUTX ? LUTX : 1)) * 4u};
             refine_row_loop<STRIDE, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, lx, cs, ws);
         } else if (LUT0) {
@@ -1058,7 +1063,8 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                 else {
                     // Default (mode 10): warp = candidate row, census table at the shared-window base.  Measured per 1080p pair at level 0 (round 2,
                     // tools/variant_times.py, 16 pairs): column kernel 8.28 ms; its knobs allrows 9.72, wide address 8.78, 6 CTAs 8.54; row kernel
-                    // 8.06-8.12, + fixed-address census table 7.85, + guard-free loop for interior warps 7.92 (spills).
+                    // 8.06-8.12, + fixed-address census table 7.85, + guard-free loop for interior warps 7.92 (spills), warp-uniform guards (mode 16) 7.88,
+                    // census table indexed by the XOR byte instead of POPC (modes 12-15: plain 7.94, replicated x8 / x16 / x32 8.23 / 8.27 / 12.3).
                     // Tuning knob EPPM_REFINE_MODE: 0-7 = column kernel with allrows + 2 * wide + 4 * (6 CTAs per SM), 8-11 = row kernel + 2 * table at base + guard-free
                     static const int mode = getenv("EPPM_REFINE_MODE") ? atoi(getenv("EPPM_REFINE_MODE")) : 10;
                     const int md = (v & EPPM_VAR_REFINE_COLUMN) ? 0 : mode;
@@ -1069,6 +1075,7 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                     case 9: EPPM_RR(false, true); break;
                     case 10: if (lut0_window_base_ok(c->device)) EPPM_RR(true, false); else EPPM_RR(false, false); break;
                     case 11: if (lut0_window_base_ok(c->device)) EPPM_RR(true, true); else EPPM_RR(false, true); break;
+                    case 16: if (lut0_window_base_ok(c->device)) k_c2f_refine_row<7, 2, true, false, 0, 1><<<grd, blk, (16 + 9 * RF_PIX) * sizeof(float), c->stream>>>(a, c->cost_lut, *tabp); else EPPM_RR(false, false); break;
 #define EPPM_RX(REP) { static bool at##REP[64] = {}; const size_t sm = (256 * REP + 9 * RF_PIX) * sizeof(float); \
                        if (!at##REP[c->device & 63]) { cudaFuncSetAttribute(k_c2f_refine_row<7, 2, true, false, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); at##REP[c->device & 63] = true; } \
                        k_c2f_refine_row<7, 2, true, false, REP><<<grd, blk, sm, c->stream>>>(a, c->cost_lut, *tabp); }
