@@ -137,6 +137,8 @@ struct eppm_context {
     eppm::WmfLut wmf_lut;
     CUtensorMap tmap_pix0[eppm::MAX_LEVELS];     // TMA descriptors of the image-1 packed planes (smoothing tile loads)
     int tmap_ok[eppm::MAX_LEVELS] = {};
+    CUtensorMap tmap_refine[eppm::MAX_LEVELS];   // ... and of the refine kernel's image-1 tile (default refine: EPPM_REFINE_MODE=18)
+    int tmap_refine_ok[eppm::MAX_LEVELS] = {};
     int tmap_box_h = 0;                          // tile height the tensor maps were encoded for
     void* tile_comm = nullptr;                   // ncclComm_t of the tiling group (tiled.cu); rank / size below
     int tile_rank = 0, tile_world = 0;

@@ -1588,7 +1588,13 @@ static void run_patchmatch_t(eppm_context* c, int n_dirs, int n_steps, int first
             continue;
         }
 #define EPPM_SEARCH(NT, NS, MB) k_pm_search_joint<STRIDE, 6, NT, NS, MB><<<grd, blk, pm_pad_bytes(c, (const void*)k_pm_search_joint<STRIDE, 6, NT, NS, MB>), c->stream>>>(a, rng, c->prm.search_range, c->prm.search_radius_min, c->cost_lut)
+        // tuning knob for the 256-thread tiles (measured alternatives of the default's 2 texture guesses / 1 pass / 2 CTAs per SM)
+        static const int s256 = getenv("EPPM_SEARCH_256MODE") ? atoi(getenv("EPPM_SEARCH_256MODE")) : 0;
         if (joint && blk.x * blk.y == 256 && ((v & EPPM_VAR_SEARCH_NOTEX) || !tex_ok)) EPPM_SEARCH(0, 1, 2);
+        else if (joint && blk.x * blk.y == 256 && s256 == 1) EPPM_SEARCH(2, 3, 3);   // three passes of two guesses: 85 registers, three CTAs per SM
+        else if (joint && blk.x * blk.y == 256 && s256 == 2) EPPM_SEARCH(3, 1, 2);   // three guesses through the texture unit
+        else if (joint && blk.x * blk.y == 256 && s256 == 3) EPPM_SEARCH(3, 3, 3);
+        else if (joint && blk.x * blk.y == 256 && s256 == 4) EPPM_SEARCH(4, 1, 2);   // four guesses through the texture unit
         else if (joint && blk.x * blk.y == 256) EPPM_SEARCH(2, 1, 2);   // 256-thread tiles: two CTAs of 128 registers per SM
         else if (joint && ((v & EPPM_VAR_SEARCH_NOTEX) || !tex_ok)) EPPM_SEARCH(0, 1, 4);
         else if (joint && (v & EPPM_VAR_SEARCH_TEX3)) EPPM_SEARCH(3, 1, 4);

@@ -356,17 +356,40 @@ EPPM_PRAGMA(unroll RF_JUNROLL)
     }
 }
 
+// mbarrier / TMA helpers (PTX, sm_90+): one thread arms the barrier with the byte count, issues the bulk tensor copy, everyone waits.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // ---- table-driven refine, warp = candidate ROW ----
 // k_c2f_refine_tab gives warp m the candidate COLUMN m and a thread its three candidate rows: the twelve image-2 sites of a sample are
 // twelve 64-bit address computations (two ALU instructions each: 2.3 of the 30.9 issued instructions per sample).  Here warp n owns the
 // candidate ROW n and a thread its three candidate columns: the three columns of a (row, model) are neighbouring pixels, base -16 / +0 /
 // +16 bytes, which the load instruction takes as an immediate -- four address computations per sample instead of twelve.  Everything
 // else (site table, sample order, grouped fix-up, strict '<' arg-min in the reference's order) is k_c2f_refine_tab's.
+constexpr int RF_TILE_W = RF_PIX + 2 * PATCH_R, RF_TILE_H = PATCH_R + 1;   // image-1 tile of a CTA at stride 2: 50 pixels x 10 sampled rows (8000 bytes)
 // the sample loop of k_c2f_refine_row.  CHECK = false: every candidate of every lane of the warp is valid (all warps but those at the image
 // border), so the per-candidate divergence guard (BSSY / BSYNC / BRA: 1.5 of ~30 issued instructions per sample) is not compiled in.
-template <int STRIDE, bool CHECK, class LutRef>
+template <int STRIDE, bool CHECK, class LutRef, bool TILE = false>
 __device__ __forceinline__ void refine_row_loop(const RefineArgs& a, const CostLut& lut, const AffineTab& tab, const float4* a0, const float4* Pc, const PixPk& c1k,
-                                                const PixPk (&c2k)[3], const bool (&valid)[3], unsigned wmask, LutRef lut_ref, float (&cs)[3][4], float (&ws)[3][4]) {
+                                                const PixPk (&c2k)[3], const bool (&valid)[3], unsigned wmask, LutRef lut_ref, float (&cs)[3][4], float (&ws)[3][4],
+                                                const float4* tile = nullptr) {
     int s = 0;
 #pragma unroll 1
     for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
@@ -374,7 +397,8 @@ __device__ __forceinline__ void refine_row_loop(const RefineArgs& a, const CostL
         const int irow = i * a.pw;
 EPPM_PRAGMA(unroll RF_JUNROLL)
         for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE, s++) {
-            const float4 p1 = ldpix(a0 + irow + j);
+            // TILE: the image-1 samples of the CTA's 32 pixels (every second row of a (32 + 18)-pixel strip) were staged in shared memory by TMA
+            const float4 p1 = TILE ? tile[((i + PATCH_R) / STRIDE) * RF_TILE_W + (j + PATCH_R)] : ldpix(a0 + irow + j);
             const PixPk p1k = pack_pix(p1);
             const float d1 = max3abs_diff(c1k, p1k);
             const float gg = lut.gg[ai][j < 0 ? -j : j];
@@ -413,9 +437,9 @@ EPPM_PRAGMA(unroll RF_JUNROLL)
 
 // LUT0: the census table lives at the user base of the shared window (see Lut0); FAST: warps whose 96 candidates are all valid take a loop
 // without validity guards.
-template <int MINB, int STRIDE, bool LUT0, bool FAST, int LUTX = 0, int UNI = 0>
+template <int MINB, int STRIDE, bool LUT0, bool FAST, int LUTX = 0, int UNI = 0, bool TMA1 = false>
 __global__ void __launch_bounds__(RF_PIX * 3, MINB)
-    k_c2f_refine_row(RefineArgs a, const __grid_constant__ CostLut lut, const __grid_constant__ AffineTab tab) {
+    k_c2f_refine_row(RefineArgs a, const __grid_constant__ CostLut lut, const __grid_constant__ AffineTab tab, const __grid_constant__ CUtensorMap tmap1) {
     // no static shared memory in this kernel.  LUTX = 0: [0, 16) census table by popcount (9 used), then s_best[9][RF_PIX];
     // LUTX = REP: [0, 256 * REP) census table by XOR byte, replicated (see LutX), then s_best
     extern __shared__ float s_dyn[];
@@ -433,6 +457,17 @@ __global__ void __launch_bounds__(RF_PIX * 3, MINB)
     const int x = blockIdx.x * RF_PIX + pl, y = a.y0 + blockIdx.y;
     const bool in = x < a.w;
     const int b = blockIdx.z;
+    // TMA1 (default): the image-1 samples of the CTA -- columns x0-9 .. x0+40, rows y-9, y-7, .. y+9 of the packed plane -- as ONE bulk tensor
+    // copy with an element stride of 2 in y (cp.async.bulk.tensor + mbarrier), instead of one L1-resident 16-byte load per sample and thread
+    float4* s_tile = reinterpret_cast<float4*>(reinterpret_cast<char*>(s_dyn) + 1280);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(s_dyn) + 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4));
+    if (TMA1) {
+        if (threadIdx.x == 0) {
+            mbar_init(s_bar, 1);
+            mbar_expect_tx(s_bar, RF_TILE_W * RF_TILE_H * sizeof(float4));
+            tma_load_3d(s_tile, &tmap1, (blockIdx.x * RF_PIX + PAD - PATCH_R) * 4, y + PAD - PATCH_R, b, s_bar);
+        }
+    }
     const float4* I1 = a.pix1 + (size_t)b * a.plane;
     const float4* I2 = a.pix2 + (size_t)b * a.plane;
     float2 fl = make_float2(0.f, 0.f);
@@ -440,6 +475,10 @@ __global__ void __launch_bounds__(RF_PIX * 3, MINB)
     const bool unknown = fl.x > EPPM_UNKNOWN_FLOW_THRESH || fl.y > EPPM_UNKNOWN_FLOW_THRESH;  // :2011
     const short cxc = (short)((short)(int)fl.x + x), cyc = (short)((short)(int)fl.y + y);     // :2014-2019
     const short cy = (short)(cyc + (n - 1));
+    if (TMA1) {
+        __syncthreads();          // the barrier object is initialised before anyone polls it
+        mbar_wait(s_bar, 0);
+    }
     float cost[3];
     bool valid[3];
     bool any = false, all = true;
@@ -472,7 +511,9 @@ __global__ void __launch_bounds__(RF_PIX * 3, MINB)
         PixPk c2k[3];
 #pragma unroll
         for (int m = 0; m < 3; m++) c2k[m] = pack_pix(ldpix(Pc + (m - 1)));
-        if (UNI) {
+        if (TMA1) {
+            refine_row_loop<STRIDE, true, Lut0, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl);
+        } else if (UNI) {
             refine_row_loop<STRIDE, false>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws);
         } else if (LUTX) {
             const LutX<LUTX ? LUTX : 1> lx = {(unsigned)(pl % (LUTX ? LUTX : 1)) * 4u};
@@ -743,27 +784,6 @@ __device__ __forceinline__ void smooth_tap(const SmoothArgs& a, const float4& c,
     nx = __fmaf_rn(wgt, fl.x, nx);                                                    // :782-783
     ny = __fmaf_rn(wgt, fl.y, ny);
     wsum = __fadd_rn(wsum, wgt);
-}
-
-// mbarrier / TMA helpers (PTX, sm_90+): one thread arms the barrier with the byte count, issues the bulk tensor copy, everyone waits.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
-                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-                 : "memory");
 }
 
 __global__ void __launch_bounds__(SM_TX* SM_TY) k_flow_smooth(SmoothArgs a, const __grid_constant__ SmoothLut lut, const __grid_constant__ CUtensorMap tmap,
@@ -1061,24 +1081,36 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                 else if (v & EPPM_VAR_REFINE_PK_BRANCH) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, false><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else if (v & EPPM_VAR_REFINE_PK) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, true><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else {
-                    // Default (mode 10): warp = candidate row, census table at the shared-window base.  Measured per 1080p pair at level 0 (round 2,
+                    // Default (mode 18): warp = candidate row, census table at the shared-window base, the CTA's image-1 samples staged in shared memory by ONE
+                    // TMA copy (50 pixels x every second of 19 rows; 7.75 ms per 1080p pair at level 0 against 7.85 for mode 10, which reads them through L1).  Measured per 1080p pair at level 0 (round 2,
                     // tools/variant_times.py, 16 pairs): column kernel 8.28 ms; its knobs allrows 9.72, wide address 8.78, 6 CTAs 8.54; row kernel
                     // 8.06-8.12, + fixed-address census table 7.85, + guard-free loop for interior warps 7.92 (spills), warp-uniform guards (mode 16) 7.88,
                     // census table indexed by the XOR byte instead of POPC (modes 12-15: plain 7.94, replicated x8 / x16 / x32 8.23 / 8.27 / 12.3).
                     // Tuning knob EPPM_REFINE_MODE: 0-7 = column kernel with allrows + 2 * wide + 4 * (6 CTAs per SM), 8-11 = row kernel + 2 * table at base + guard-free
-                    static const int mode = getenv("EPPM_REFINE_MODE") ? atoi(getenv("EPPM_REFINE_MODE")) : 10;
+                    static const int mode = getenv("EPPM_REFINE_MODE") ? atoi(getenv("EPPM_REFINE_MODE")) : 18;
+                    static const CUtensorMap dummy_map = {};
                     const int md = (v & EPPM_VAR_REFINE_COLUMN) ? 0 : mode;
 #define EPPM_RT(MB, AR, WD) k_c2f_refine_tab<true, 3, MB, 2, AR, WD><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp)
                     switch (md) {
-#define EPPM_RR(L0, FP) k_c2f_refine_row<7, 2, L0, FP><<<grd, blk, (16 + 9 * RF_PIX) * sizeof(float), c->stream>>>(a, c->cost_lut, *tabp)
+#define EPPM_RR(L0, FP) k_c2f_refine_row<7, 2, L0, FP><<<grd, blk, (16 + 9 * RF_PIX) * sizeof(float), c->stream>>>(a, c->cost_lut, *tabp, dummy_map)
                     case 8: EPPM_RR(false, false); break;
                     case 9: EPPM_RR(false, true); break;
+                    case 18: {   // default: image-1 tile staged by TMA (needs the level's refine tensor map and the table-at-base addressing); else mode 10
+                        int lvl = -1;
+                        for (int l = 0; l < c->n_levels; l++)
+                            if (pix1 == c->pix[0][l] && c->tmap_refine_ok[l]) lvl = l;
+                        if (lvl >= 0 && lut0_window_base_ok(c->device)) {
+                            k_c2f_refine_row<7, 2, true, false, 0, 0, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
+                            break;
+                        }
+                    }
+                    // fall through
                     case 10: if (lut0_window_base_ok(c->device)) EPPM_RR(true, false); else EPPM_RR(false, false); break;
                     case 11: if (lut0_window_base_ok(c->device)) EPPM_RR(true, true); else EPPM_RR(false, true); break;
-                    case 16: if (lut0_window_base_ok(c->device)) k_c2f_refine_row<7, 2, true, false, 0, 1><<<grd, blk, (16 + 9 * RF_PIX) * sizeof(float), c->stream>>>(a, c->cost_lut, *tabp); else EPPM_RR(false, false); break;
+                    case 16: if (lut0_window_base_ok(c->device)) k_c2f_refine_row<7, 2, true, false, 0, 1><<<grd, blk, (16 + 9 * RF_PIX) * sizeof(float), c->stream>>>(a, c->cost_lut, *tabp, dummy_map); else EPPM_RR(false, false); break;
 #define EPPM_RX(REP) { static bool at##REP[64] = {}; const size_t sm = (256 * REP + 9 * RF_PIX) * sizeof(float); \
                        if (!at##REP[c->device & 63]) { cudaFuncSetAttribute(k_c2f_refine_row<7, 2, true, false, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); at##REP[c->device & 63] = true; } \
-                       k_c2f_refine_row<7, 2, true, false, REP><<<grd, blk, sm, c->stream>>>(a, c->cost_lut, *tabp); }
+                       k_c2f_refine_row<7, 2, true, false, REP><<<grd, blk, sm, c->stream>>>(a, c->cost_lut, *tabp, dummy_map); }
                     case 12: if (lut0_window_base_ok(c->device)) EPPM_RX(1) else EPPM_RR(false, false); break;
                     case 13: if (lut0_window_base_ok(c->device)) EPPM_RX(8) else EPPM_RR(false, false); break;
                     case 14: if (lut0_window_base_ok(c->device)) EPPM_RX(16) else EPPM_RR(false, false); break;
@@ -1279,6 +1311,12 @@ bool build_smooth_tensor_maps(eppm_context* c) {
         CUresult r = ((encode_fn)fn)(&c->tmap_pix0[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->pix[0][l], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         c->tmap_ok[l] = r == CUDA_SUCCESS;
+        // image-1 tile of the refine kernel (EPPM_REFINE_MODE=18): 50 pixels x 19 rows visited with an element stride of 2 in y = 10 rows
+        const cuuint32_t rbox[3] = {(cuuint32_t)RF_TILE_W * 4, (cuuint32_t)(2 * PATCH_R + 1), 1};
+        const cuuint32_t restr[3] = {1, 2, 1};
+        r = ((encode_fn)fn)(&c->tmap_refine[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->pix[0][l], dims, strides, rbox, restr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        c->tmap_refine_ok[l] = r == CUDA_SUCCESS;
     }
     return true;
 }

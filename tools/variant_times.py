@@ -22,7 +22,13 @@ from eppm_b200 import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 variants = [int(v) for v in sys.argv[2:]] or [0, 1, 2, 4, 8, 15]
 h, w = int(os.environ.get("VT_H", 1080)), int(os.environ.get("VT_W", 1920))
-a, b, _, _ = synth.make_batch(h, w, n, first_idx=0, distinct=min(n, 4))
+_cache = f"/tmp/vt_cache_{h}_{w}_{n}.npz"   # the knobs read from the environment need one process per setting: generate the batch once per box
+if os.path.exists(_cache):
+    _z = np.load(_cache)
+    a, b = _z["a"], _z["b"]
+else:
+    a, b, _, _ = synth.make_batch(h, w, n, first_idx=0, distinct=min(n, 4))
+    np.savez(_cache, a=a, b=b)
 da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
 out = torch.empty((n, h, w, 2), dtype=torch.float32, device="cuda")
 res = {}
