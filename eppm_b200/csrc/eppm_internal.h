@@ -162,6 +162,7 @@ extern std::atomic<unsigned long long> g_launches;
 void run_prepare(eppm_context* c, const uint8_t* d_img1, const uint8_t* d_img2, int n);
 void run_patchmatch(eppm_context* c);
 void run_patchmatch_dirs(eppm_context* c, int n_dirs, int n_steps = 1 << 30, int first_step = 0);
+bool run_patchmatch_scaled(eppm_context* c, float* d_scale);   // baoCudaPatchMatch_Scaled: forward direction of pair 0; d_scale = dense [h][w] device plane
 bool run_patchmatch_planefitting(eppm_context* c);   // baoCudaPatchMatch_PlaneFitting: forward direction of pair 0, coarsest-level planes
 void run_c2f_step(eppm_context* c, int level, int kind, float2* out);
 bool build_smooth_tensor_maps(eppm_context* c);

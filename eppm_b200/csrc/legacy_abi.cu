@@ -199,15 +199,37 @@ void baoCudaPatchMatch(short2* d_disp_vec, float* d_cost, uchar4* d_img1, uchar4
     copy_out(c, d_cost, cost_pitch, c->cost[0], w, h);
 }
 
-// Declared by the reference's host class, called nowhere, and unfinished upstream (its row pass stores the candidate's scale into the cost
-// plane, bao_pmflow_kernel.cu:1207; its cost ignores the census planes it is given): exported so that any caller links, refuses loudly.
+// Declared by the reference's host class, called nowhere, and unfinished upstream (its forward row pass stores the candidate's scale into
+// the cost plane, bao_pmflow_kernel.cu:1207; its cost ignores the census planes it is given).  Mirrored as it stands (run_patchmatch_scaled),
+// bit-exact against the reference build.  Like the reference's random-field kernel (:151) it assumes scale_pitch == disp_pitch.
 void baoCudaPatchMatch_Scaled(short2* d_disp_vec, float* d_scale, float* d_cost, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1,
                               unsigned char* d_census2, int w, int h, size_t img_pitch, size_t cost_pitch, size_t disp_pitch, size_t scale_pitch,
                               size_t census_pitch) {
-    (void)d_disp_vec; (void)d_scale; (void)d_cost; (void)d_img1; (void)d_img2; (void)d_census1; (void)d_census2; (void)w; (void)h;
-    (void)img_pitch; (void)cost_pitch; (void)disp_pitch; (void)scale_pitch; (void)census_pitch;
-    set_error("baoCudaPatchMatch_Scaled is not implemented (unfinished in the reference); outputs untouched");
-    complain("baoCudaPatchMatch_Scaled");
+    if (!d_disp_vec || !d_scale || !d_cost || !d_img1 || !d_img2 || w < 1 || h < 1 || scale_pitch != disp_pitch) {
+        set_error("baoCudaPatchMatch_Scaled: null plane, empty frame, or scale_pitch != disp_pitch (the reference indexes the scale plane with the displacement pitch)");
+        complain("baoCudaPatchMatch_Scaled");
+        return;
+    }
+    eppm_context* c = get_ctx(g_single, h, w, 1);
+    if (!c) return;
+    Scope sc(c, "baoCudaPatchMatch_Scaled");
+    const LevelGeom& g = c->lv[0];
+    // the census planes are optional here: the scaled cost never reads them (:596-609)
+    if (d_census1 && d_census2) {
+        op_pack_foreign(c->stream, d_img1, img_pitch, d_census1, census_pitch, c->pix[0][0], g);
+        op_pack_foreign(c->stream, d_img2, img_pitch, d_census2, census_pitch, c->pix[1][0], g);
+    } else {
+        k_pack_planes(c->stream, d_img1, img_pitch, 0, c->pix[0][0], g, 1);
+        k_pack_planes(c->stream, d_img2, img_pitch, 0, c->pix[1][0], g, 1);
+    }
+    float* scale = nullptr;
+    if (cudaMalloc((void**)&scale, (size_t)w * h * sizeof(float)) != cudaSuccess) { set_error("baoCudaPatchMatch_Scaled: out of device memory"); complain("baoCudaPatchMatch_Scaled"); return; }
+    if (!run_patchmatch_scaled(c, scale)) { cudaFree(scale); complain("baoCudaPatchMatch_Scaled"); return; }
+    copy_out(c, d_disp_vec, disp_pitch, c->nnf[0], w, h);
+    copy_out(c, d_scale, scale_pitch, scale, w, h);
+    copy_out(c, d_cost, cost_pitch, c->cost[0], w, h);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(scale);
 }
 
 void baoCudaPatchMatch_PlaneFitting(short2* d_disp_vec, float* d_cost, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1,

@@ -1472,6 +1472,222 @@ bool run_patchmatch_planefitting(eppm_context* c) {
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// baoCudaPatchMatch_Scaled (bao_pmflow_kernel.cu:1828-1895): PatchMatch over (target, patch scale).  Declared by the reference's host
+// class, called nowhere, and visibly unfinished upstream -- mirrored as it stands, quirks included, so that it is bit-exact against the
+// reference build on identical buffers:
+//  * the cost is the bilateral AD term only (_d_compute_patch_dist_scaled :588-634; the census lines are commented out), image-2 samples
+//    at (x2 + float(j)*scale, y2 + float(i)*scale) -- contracted by nvcc to fma(scale, float(j), float(x2)) (read from the reference
+//    SASS) -- through a point-filtered clamped fetch = floor + replicated border;
+//  * scale = float(10 + (r2 % 9) - 4) / 10.0f in UNSIGNED arithmetic = (r2 % 9 + 6) / 10 in [0.6, 1.4] (:138, :1631; the comment there
+//    says 0.9~1.3), from the SECOND draw of a pixel -- the one that also gives the target's y;
+//  * the forward row pass stores the candidate's SCALE into the cost plane when the candidate wins (:1207), so later comparisons at that
+//    pixel run against a scale, and a candidate equal to the pixel's current (target, scale) can win: nothing is skipped here;
+//  * the random field kernel indexes the scale plane with the displacement pitch (:151): the entry point requires the two pitches equal.
+// One direction, one pair (legacy stage ABI only), plain one-thread-per-evaluation kernels with the CTA lock-step of k_pm_propagate.
+__device__ __forceinline__ float scale_of_draw(unsigned r2) { return __fdiv_rn((float)(r2 % 9u + 6u), 10.0f); }
+
+__global__ void k_rng_scale_tables(float* __restrict__ init, float* __restrict__ search, int w, int h, int gx, int gy, int num_iter, int num_guess,
+                                   unsigned long long seed, int philox) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (philox) {   // same stream layout as k_rng_tables_philox
+        if (tid >= w * h) return;
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, (unsigned long long)tid, 0, &st);
+        (void)curand(&st);
+        init[tid] = scale_of_draw(curand(&st));
+        for (int k = 0; k < num_iter * num_guess; k++) {
+            (void)curand(&st);
+            search[(size_t)k * w * h + tid] = scale_of_draw(curand(&st));
+        }
+        return;
+    }
+    if (tid >= gx * gy) return;
+    const int bx = tid % gx, by = tid / gx;
+    curandState st;
+    curand_init(seed, tid, 0, &st);
+    for (int i = 0; i < RB; i++)
+        for (int j = 0; j < RB; j++) {
+            (void)curand(&st);
+            const unsigned r2 = curand(&st);
+            const int x = bx * RB + j, y = by * RB + i;
+            if (x < w && y < h) init[(size_t)y * w + x] = scale_of_draw(r2);   // :138
+        }
+    for (int k = 0; k < num_iter * num_guess; k++)
+        for (int i = 0; i < RB; i++)
+            for (int j = 0; j < RB; j++) {
+                (void)curand(&st);
+                const unsigned r2 = curand(&st);
+                const int x = bx * RB + j, y = by * RB + i;
+                if (x < w && y < h) search[((size_t)k * h + y) * w + x] = scale_of_draw(r2);   // :1631
+            }
+}
+
+__device__ float patch_cost_scaled(const float4* __restrict__ A, const float4* __restrict__ B, int pw, int x1, int y1, int x2, int y2, float scale,
+                                   const CostLut& lut) {
+    const float4* a0 = A + (unsigned)((y1 + PAD) * pw + x1 + PAD);
+    const float4 c1 = ldpix(a0);
+    const float4 c2 = ldpix(B + (unsigned)((y2 + PAD) * pw + x2 + PAD));
+    const float fx2 = (float)x2, fy2 = (float)y2;
+    float cs = 0.f, ws = 0.f;
+#pragma unroll 1
+    for (int i = -PATCH_R; i <= PATCH_R; i += 2) {
+        const int ai = i < 0 ? -i : i;
+        const int sy = __float2int_rd(__fmaf_rn(scale, (float)i, fy2));   // |i| * 1.4 = 12.6 < PAD: the replicated border is the clamp
+#pragma unroll 2
+        for (int j = -PATCH_R; j <= PATCH_R; j += 2) {
+            const int sx = __float2int_rd(__fmaf_rn(scale, (float)j, fx2));
+            const float4 p1 = ldpix(a0 + i * pw + j);
+            const float4 p2 = ldpix(B + (unsigned)((sy + PAD) * pw + sx + PAD));
+            const float cost = exp_ad_cost(max3abs_diff(p1, p2));                                       // :610-611
+            const float d1 = max3abs_diff(c1, p1), d2 = max3abs_diff(c2, p2);
+            const float e = exp_ref(div_neg_0p01(__fmaf_rn(d1, d1, __fmul_rn(d2, d2))));               // :613-617 as contracted
+            const float wgt = __fmul_rn(e, lut.gg[ai][j < 0 ? -j : j]);
+            cs = __fmaf_rn(cost, wgt, cs);                                                              // :619,:622 as contracted
+            ws = __fadd_rn(ws, wgt);
+        }
+    }
+    return __fdiv_rn(cs, ws);
+}
+
+struct ScaledArgs {
+    const float4* pix[2];
+    int pw, w, h;
+    short2* nnf;
+    float* scale;
+    float* cost;
+};
+
+__global__ void __launch_bounds__(128) k_sc_init(ScaledArgs a, const short2* __restrict__ rng_init, const float* __restrict__ scale_init,
+                                                 const __grid_constant__ CostLut lut) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.w) return;
+    const int id = y * a.w + x;
+    const short2 t = rng_init[id];
+    const float s = scale_init[id];
+    a.nnf[id] = t;
+    a.scale[id] = s;
+    a.cost[id] = patch_cost_scaled(a.pix[0], a.pix[1], a.pw, x, y, t.x, t.y, s, lut);   // :647-656
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(896) k_sc_propagate(ScaledArgs a, int seg_len, const __grid_constant__ CostLut lut) {
+    constexpr bool ROW = (DIR == 0 || DIR == 2), FWD = (DIR < 2);
+    const int line = blockIdx.x * blockDim.x + threadIdx.x, seg = threadIdx.y;
+    const int n_line = ROW ? a.h : a.w, len = ROW ? a.w : a.h;
+    int start, steps;
+    if (FWD) {
+        start = seg == 0 ? 0 : seg * seg_len - 1;   // :1189-1192
+        steps = min(len - 1, start + seg_len) - start;
+    } else {
+        start = (seg + 1) * seg_len;                // :1225-1227
+        if (start >= len) start = len - 1;
+        steps = start - seg * seg_len;
+    }
+    if (line >= n_line) steps = 0;
+    auto idx = [&](int i) -> int { return ROW ? line * a.w + i : i * a.w + line; };
+    short2 prev = make_short2(0, 0);
+    float prev_scale = 0.f;
+    if (steps > 0) { prev = a.nnf[idx(start)]; prev_scale = a.scale[idx(start)]; }
+    __syncthreads();
+    for (int t = 1; t <= seg_len; t++) {
+        if (t <= steps) {
+            const int i = FWD ? start + t : start - t, id = idx(i);
+            if (DIR == 0) prev.x = min(prev.x + 1, a.w - 1);
+            if (DIR == 1) prev.y = min(prev.y + 1, a.h - 1);
+            if (DIR == 2) prev.x = max(prev.x - 1, 0);
+            if (DIR == 3) prev.y = max(prev.y - 1, 0);
+            const float cv = patch_cost_scaled(a.pix[0], a.pix[1], a.pw, ROW ? i : line, ROW ? line : i, prev.x, prev.y, prev_scale, lut);
+            if (cv < a.cost[id]) {
+                a.nnf[id] = prev;
+                a.scale[id] = prev_scale;
+                a.cost[id] = DIR == 0 ? prev_scale : cv;   // :1207: the forward row pass stores the SCALE into the cost plane
+            } else {
+                prev = a.nnf[id];
+                prev_scale = a.scale[id];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128) k_sc_search(ScaledArgs a, const short2* __restrict__ rng, const float* __restrict__ rng_scale, int num_guess,
+                                                   int search_range, int radius_min, const __grid_constant__ CostLut lut) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.w) return;
+    const int id = y * a.w + x;
+    short2 best = a.nnf[id];
+    float best_scale = a.scale[id], best_cost = a.cost[id];
+    const short2 entry = best;   // :1637-1638: every window is centred on the target the pixel entered with
+    int mag = search_range;
+    for (int k = 0; k < num_guess; k++) {
+        const short2 rr = rng[(size_t)k * a.w * a.h + id];
+        const float gs = rng_scale[(size_t)k * a.w * a.h + id];
+        const unsigned r1 = (unsigned)(int)rr.x, r2 = (unsigned)(int)rr.y;   // :1635-1636: the 16-bit draws, sign-extended
+        const short xmin = (short)max(entry.x - mag, 0), xmax = (short)min(entry.x + mag + 1, a.w + 1);
+        const short ymin = (short)max(entry.y - mag, 0), ymax = (short)min(entry.y + mag + 1, a.h + 1);
+        const short gx = (short)(xmin + r1 % (unsigned)(xmax - xmin)), gy = (short)(ymin + r2 % (unsigned)(ymax - ymin));
+        if (mag / 2 >= radius_min) mag /= 2;
+        const float cv = patch_cost_scaled(a.pix[0], a.pix[1], a.pw, x, y, gx, gy, gs, lut);
+        if (cv < best_cost) { best = make_short2(gx, gy); best_scale = gs; best_cost = cv; }
+    }
+    a.nnf[id] = best;
+    a.scale[id] = best_scale;
+    a.cost[id] = best_cost;
+}
+
+template <int DIR>
+static void launch_sc_propagate(eppm_context* c, const ScaledArgs& a) {
+    const bool row = (DIR == 0 || DIR == 2);
+    const int sl = c->prm.prop_seg_length;
+    const int n_line = row ? a.h : a.w, n_seg = ((row ? a.w : a.h) + sl - 1) / sl;
+    int lines = 32;
+    while (lines > 1 && lines * n_seg > 896) lines >>= 1;
+    k_sc_propagate<DIR><<<dim3((n_line + lines - 1) / lines), dim3(lines, n_seg), 0, c->stream>>>(a, sl, c->cost_lut);
+    EPPM_LAUNCH_COUNT(1);
+}
+
+// forward direction of pair 0 on the context's coarsest-level planes; d_scale: dense float plane [h][w] of the caller (device memory)
+bool run_patchmatch_scaled(eppm_context* c, float* d_scale) {
+    if (c->prm.patch_stride != 2) { set_error("scaled PatchMatch is built for patch stride 2"); return false; }
+    ensure_rng_tables(c);
+    const int L = c->n_levels - 1;
+    const LevelGeom& g = c->lv[L];
+    if ((g.w + c->prm.prop_seg_length - 1) / c->prm.prop_seg_length > 896 || (g.h + c->prm.prop_seg_length - 1) / c->prm.prop_seg_length > 896) {
+        set_error("scaled PatchMatch: more than 896 segments per scan line");
+        return false;
+    }
+    const size_t n = (size_t)g.w * g.h, n_search = (size_t)c->prm.num_iter * c->prm.num_rand_guess;
+    float* tab = nullptr;   // scale draws: [1 + iterations * guesses][h][w]; this uncalled stage allocates per call like the reference does (:1835)
+    if (cudaMalloc((void**)&tab, (1 + n_search) * n * sizeof(float)) != cudaSuccess) { set_error("scaled PatchMatch: out of device memory"); return false; }
+    const int gx = (g.w + RB - 1) / RB, gy = (g.h + RB - 1) / RB;
+    const int philox = c->prm.rng_mode == EPPM_RNG_PHILOX;
+    const int n_thr = philox ? g.w * g.h : gx * gy;
+    k_rng_scale_tables<<<(n_thr + 63) / 64, 64, 0, c->stream>>>(tab, tab + n, g.w, g.h, gx, gy, c->prm.num_iter, c->prm.num_rand_guess, c->prm.seed, philox);
+    EPPM_LAUNCH_COUNT(1);
+    ScaledArgs a = {};
+    a.pix[0] = c->pix[0][L]; a.pix[1] = c->pix[1][L];
+    a.pw = g.pw; a.w = g.w; a.h = g.h;
+    a.nnf = c->nnf[0]; a.cost = c->cost[0]; a.scale = d_scale;
+    dim3 blk(128), grd((g.w + 127) / 128, g.h);
+    k_sc_init<<<grd, blk, 0, c->stream>>>(a, c->rng_init, tab, c->cost_lut);
+    EPPM_LAUNCH_COUNT(1);
+    for (int it = 0; it < c->prm.num_iter; it++) {
+        launch_sc_propagate<0>(c, a);   // :1327-1330: row, column, row reverse, column reverse
+        launch_sc_propagate<1>(c, a);
+        launch_sc_propagate<2>(c, a);
+        launch_sc_propagate<3>(c, a);
+        const size_t off = (size_t)it * c->prm.num_rand_guess * n;
+        k_sc_search<<<grd, blk, 0, c->stream>>>(a, c->rng_search + off, tab + n + off, c->prm.num_rand_guess, c->prm.search_range, c->prm.search_radius_min,
+                                                c->cost_lut);
+        EPPM_LAUNCH_COUNT(1);
+    }
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(tab);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return false; }
+    return true;
+}
+
 void run_patchmatch(eppm_context* c) { run_patchmatch_dirs(c, 2); }
 
 template <int STRIDE>

@@ -386,13 +386,15 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 constexpr int RF_TILE_W = RF_PIX + 2 * PATCH_R, RF_TILE_H = PATCH_R + 1;   // image-1 tile of a CTA at stride 2: 50 pixels x 10 sampled rows (8000 bytes)
 // the sample loop of k_c2f_refine_row.  CHECK = false: every candidate of every lane of the warp is valid (all warps but those at the image
 // border), so the per-candidate divergence guard (BSSY / BSYNC / BRA: 1.5 of ~30 issued instructions per sample) is not compiled in.
-template <int STRIDE, bool CHECK, class LutRef, bool TILE = false>
+// TINY = false: the `t2 < -126` fix-up of __expf is not compiled in (a bare MUFU.EX2.ftz returns 0 there): only valid for rows behind a prefix
+// after which every accumulator is large enough to absorb any such weight unchanged (see k_c2f_refine_row, FASTW).  Rows [i_lo, i_hi].
+template <int STRIDE, bool CHECK, class LutRef, bool TILE = false, bool TINY = true>
 __device__ __forceinline__ void refine_row_loop(const RefineArgs& a, const CostLut& lut, const AffineTab& tab, const float4* a0, const float4* Pc, const PixPk& c1k,
                                                 const PixPk (&c2k)[3], const bool (&valid)[3], unsigned wmask, LutRef lut_ref, float (&cs)[3][4], float (&ws)[3][4],
-                                                const float4* tile = nullptr) {
-    int s = 0;
+                                                const float4* tile = nullptr, int i_lo = -PATCH_R, int i_hi = PATCH_R) {
+    int s = ((i_lo + PATCH_R) / STRIDE) * ((2 * PATCH_R) / STRIDE + 1);
 #pragma unroll 1
-    for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
+    for (int i = i_lo; i <= i_hi; i += STRIDE) {
         const int ai = i < 0 ? -i : i;
         const int irow = i * a.pw;
 EPPM_PRAGMA(unroll RF_JUNROLL)
@@ -420,7 +422,7 @@ EPPM_PRAGMA(unroll RF_JUNROLL)
                 for (int q = 0; q < 4; q++) sample_eval(p1, p1k, ldpix(site[q] + (m - 1)), c2k[m], d1, lut_ref, ct[q], t2[q]);
 #pragma unroll
                 for (int q = 0; q < 4; q++) w[q] = __fmul_rn(ex2_mufu(t2[q]), gg);
-                if (fminf(fminf(t2[0], t2[1]), fminf(t2[2], t2[3])) < -126.0f) {
+                if (TINY && fminf(fminf(t2[0], t2[1]), fminf(t2[2], t2[3])) < -126.0f) {
 #pragma unroll
                     for (int q = 0; q < 4; q++)
                         if (t2[q] < -126.0f) w[q] = __fmul_rn(ex2_tiny(t2[q]), gg);
@@ -437,7 +439,12 @@ EPPM_PRAGMA(unroll RF_JUNROLL)
 
 // LUT0: the census table lives at the user base of the shared window (see Lut0); FAST: warps whose 96 candidates are all valid take a loop
 // without validity guards.
-template <int MINB, int STRIDE, bool LUT0, bool FAST, int LUTX = 0, int UNI = 0, bool TMA1 = false>
+// FASTW (with TMA1): the first patch row is scored with the exact __expf fix-up; if afterwards EVERY accumulator of every lane's valid candidates is
+// at least 2^-99, the other rows run without the fix-up test (1.5 of ~28.7 issued instructions per sample).  Exact, not approximate: a weight that
+// needs the fix-up is below 2^-126 (its cost term below 2^-125), the sums never decrease (all terms are non-negative), and adding a
+// non-negative value below half an ulp of a sum leaves the sum unchanged under round-to-nearest -- so both forms produce the same bits.
+// Warps that fail the test (static scenes: cost sums exactly 0; pixels boxed in by saturated edges) keep the exact loop.
+template <int MINB, int STRIDE, bool LUT0, bool FAST, int LUTX = 0, int UNI = 0, bool TMA1 = false, bool FASTW = false>
 __global__ void __launch_bounds__(RF_PIX * 3, MINB)
     k_c2f_refine_row(RefineArgs a, const __grid_constant__ CostLut lut, const __grid_constant__ AffineTab tab, const __grid_constant__ CUtensorMap tmap1) {
     // no static shared memory in this kernel.  LUTX = 0: [0, 16) census table by popcount (9 used), then s_best[9][RF_PIX];
@@ -496,6 +503,7 @@ __global__ void __launch_bounds__(RF_PIX * 3, MINB)
         wmask = (__any_sync(0xffffffffu, valid[0]) ? 1u : 0u) | (__any_sync(0xffffffffu, valid[1]) ? 2u : 0u) | (__any_sync(0xffffffffu, valid[2]) ? 4u : 0u);
     }
     asm volatile("" : "+r"(wmask));   // opaque to the compiler: see refine_row_loop
+    const unsigned any_mask = FASTW ? __ballot_sync(0xffffffffu, any) : 0u;   // the lanes that enter the scoring branch (FASTW votes among them)
     if (any) {
         float cs[3][4], ws[3][4];
 #pragma unroll
@@ -511,7 +519,19 @@ __global__ void __launch_bounds__(RF_PIX * 3, MINB)
         PixPk c2k[3];
 #pragma unroll
         for (int m = 0; m < 3; m++) c2k[m] = pack_pix(ldpix(Pc + (m - 1)));
-        if (TMA1) {
+        if (TMA1 && FASTW) {
+            refine_row_loop<STRIDE, true, Lut0, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl, -PATCH_R, -PATCH_R);
+            float lo = FLT_MAX;   // smallest accumulator among the valid candidates of this lane after the first row
+#pragma unroll
+            for (int m = 0; m < 3; m++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (valid[m]) lo = fminf(lo, fminf(cs[m][q], ws[m][q]));
+            if (__all_sync(any_mask, lo >= 1.57772181e-30f))   // 2^-99; any_mask: lanes outside this branch (image border, unknown flow) do not vote
+                refine_row_loop<STRIDE, true, Lut0, true, false>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl, -PATCH_R + STRIDE, PATCH_R);
+            else
+                refine_row_loop<STRIDE, true, Lut0, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl, -PATCH_R + STRIDE, PATCH_R);
+        } else if (TMA1) {
             refine_row_loop<STRIDE, true, Lut0, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl);
         } else if (UNI) {
             refine_row_loop<STRIDE, false>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws);
@@ -1095,12 +1115,14 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
 #define EPPM_RR(L0, FP) k_c2f_refine_row<7, 2, L0, FP><<<grd, blk, (16 + 9 * RF_PIX) * sizeof(float), c->stream>>>(a, c->cost_lut, *tabp, dummy_map)
                     case 8: EPPM_RR(false, false); break;
                     case 9: EPPM_RR(false, true); break;
+                    case 19:     // mode 18 + fix-up-free loop behind an exact first patch row (FASTW)
                     case 18: {   // default: image-1 tile staged by TMA (needs the level's refine tensor map and the table-at-base addressing); else mode 10
                         int lvl = -1;
                         for (int l = 0; l < c->n_levels; l++)
                             if (pix1 == c->pix[0][l] && c->tmap_refine_ok[l]) lvl = l;
                         if (lvl >= 0 && lut0_window_base_ok(c->device)) {
-                            k_c2f_refine_row<7, 2, true, false, 0, 0, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
+                            if (md == 19) k_c2f_refine_row<7, 2, true, false, 0, 0, true, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
+                            else k_c2f_refine_row<7, 2, true, false, 0, 0, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
                             break;
                         }
                     }

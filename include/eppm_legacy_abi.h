@@ -65,8 +65,11 @@ void baoCudaImageSmoothing(uchar4* d_img_smoothed, uchar4* d_img, int w, int h, 
  * without any known tap keep their content (the spelling of the name is the reference's) */
 void baoCudaFlowBilteralUpsampling(float2* d_flow_vec, uchar4* d_img, int w, int h, size_t img_pitch, float2* d_flow_vec_small, int w_s, int h_s,
                                    float ratio_up);
-/* bao_pmflow_kernel.cu:1828-1895: NOT IMPLEMENTED -- exported so that callers link; prints to stderr, sets eppm_last_error() and leaves the
- * outputs untouched.  The upstream function is unfinished (its row pass writes the candidate's scale into the cost plane, :1207). */
+/* bao_pmflow_kernel.cu:1828-1895: PatchMatch over (target, patch scale in [0.6, 1.4]) scored with the bilateral AD cost alone.  Unfinished
+ * upstream and mirrored as it stands (its forward row pass writes the winning candidate's scale into the cost plane, :1207; the census planes
+ * are never read and may be NULL here): bit-exact against the reference build.  scale_pitch must equal disp_pitch (the reference's random-field
+ * kernel indexes the scale plane with the displacement pitch, :151); otherwise, or on a null plane, it reports on stderr, sets
+ * eppm_last_error() and leaves the outputs untouched. */
 void baoCudaPatchMatch_Scaled(short2* d_disp_vec, float* d_scale, float* d_cost, uchar4* d_img1, uchar4* d_img2, unsigned char* d_census1,
                               unsigned char* d_census2, int w, int h, size_t img_pitch, size_t cost_pitch, size_t disp_pitch, size_t scale_pitch,
                               size_t census_pitch);

@@ -47,13 +47,14 @@ def test_library_exports_every_declared_symbol():
     assert set(_declared("eppm_legacy_abi.h")) == set(_lib.LEGACY_SYMBOLS)
 
 
-def test_unimplemented_stage_function_refuses_loudly(capfd):
-    """baoCudaPatchMatch_Scaled (unfinished upstream) is exported so that callers link, but must not pretend to work: it reports on stderr and
+def test_scaled_patchmatch_rejects_bad_arguments_loudly(capfd):
+    """baoCudaPatchMatch_Scaled keeps the reference's void signature, so a call it cannot run (null planes; a scale pitch different from the
+    displacement pitch, which the reference's own random-field kernel silently mis-indexes, bao_pmflow_kernel.cu:151) reports on stderr and
     through eppm_last_error() and touches nothing.  No GPU needed: it returns before any CUDA call."""
     lib = _lib.load()
     lib.eppm_last_error.restype = C.c_char_p
     lib.baoCudaPatchMatch_Scaled(*([None] * 7), 8, 8, 0, 0, 0, 0, 0)
-    assert b"not implemented" in lib.eppm_last_error()
+    assert b"baoCudaPatchMatch_Scaled" in lib.eppm_last_error()
     assert "baoCudaPatchMatch_Scaled" in capfd.readouterr().err
 
 

@@ -327,6 +327,31 @@ def test_patchmatch_planefitting_bit_exact(ref, mine, chain):
 
 
 @needs_ref
+def test_patchmatch_scaled_bit_exact(ref, mine, chain):
+    """baoCudaPatchMatch_Scaled (declared, never called, unfinished upstream: bao_pmflow_kernel.cu:1828-1895): PatchMatch over (target, patch
+    scale) with the AD-only cost, mirrored with its quirks (the forward row pass stores the winning scale into the cost plane).  Same random
+    stream (the scale comes from the second draw of a pixel), same lock-step order -> targets, scales and the cost plane bit-exact."""
+    img, cen, wc, hc = chain["img"], chain["cen"], chain["wc"], chain["hc"]
+    S, I, V = C.c_size_t, C.c_int, C.c_void_p
+    outs = {}
+    for name, lib in (("ref", ref.lib), ("mine", mine)):
+        lib.baoCudaPatchMatch_Scaled.argtypes = [V] * 7 + [I, I, S, S, S, S, S]; lib.baoCudaPatchMatch_Scaled.restype = None
+        nnf = torch.zeros((hc, wc, 2), dtype=torch.int16, device="cuda")
+        scale = torch.zeros((hc, wc), dtype=torch.float32, device="cuda"); cost = torch.zeros((hc, wc), dtype=torch.float32, device="cuda")
+        lib.baoCudaPatchMatch_Scaled(P(nnf), P(scale), P(cost), P(img[0][2][0]), P(img[1][2][0]), P(cen[0][2][0]), P(cen[1][2][0]), wc, hc,
+                                     img[0][2][1], wc * 4, wc * 4, wc * 4, cen[0][2][1])
+        torch.cuda.synchronize()
+        outs[name] = (nnf.cpu().numpy(), scale.cpu().numpy(), cost.cpu().numpy())
+    assert np.array_equal(outs["ref"][0], outs["mine"][0]), f"{(outs['ref'][0] != outs['mine'][0]).any(-1).sum()} targets differ"
+    assert same_bits(outs["ref"][1], outs["mine"][1]), f"{(outs['ref'][1] != outs['mine'][1]).sum()} scales differ"
+    assert same_bits(outs["ref"][2], outs["mine"][2]), f"{(outs['ref'][2] != outs['mine'][2]).sum()} costs differ"
+    sc = outs["mine"][1]
+    assert sc.min() >= 0.6 - 1e-6 and sc.max() <= 1.4 + 1e-6 and len(np.unique(sc)) == 9   # (r % 9 + 6) / 10
+    (nf, _), _ = chain["pm_ref"]
+    assert (outs["ref"][0] != nf.cpu().numpy()).any()   # and it is not the plain PatchMatch
+
+
+@needs_ref
 def test_subpixel_refine_and_bicubic_census_vs_reference(mine, chain, tmp_path):
     """baoCudaCensusTransform_Bicubic + baoCudaSubpixRefine (declared by the reference's host class, not called by
     compute_flow).  Both are deterministic -> bit-exact on identical buffers.  The reference build is loaded from a PRIVATE copy of its
