@@ -37,6 +37,7 @@ enum {
     EPPM_VAR_REFINE_COLUMN = 1048576,  // table refine with warp = candidate column, thread = three candidate rows (round-1 default) instead of warp = candidate row
     EPPM_VAR_PROP_Q = 2097152,         // propagation: the warp-per-evaluation scoring kernel reads the parity-split planes (dense sample rows; measured slower: 4.45 vs 4.24 ms per pair)
     EPPM_VAR_PROP_WARP_FULL = 131072,  // propagation queue scored by one warp per evaluation with ALL samples staged in shared memory (13 KB per warp starves the L1)
+    EPPM_VAR_REFINE_NOFASTW = 4194304, // refine: every patch row with the __expf fix-up test (default: only the first row, then a test-free loop where that provably changes no bit)
     EPPM_VAR_PROP_NOSKIP = 8,      // propagation: evaluate candidates that equal the current target (the reference does)
 };
 

@@ -1101,22 +1101,23 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                 else if (v & EPPM_VAR_REFINE_PK_BRANCH) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, false><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else if (v & EPPM_VAR_REFINE_PK) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, true><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else {
-                    // Default (mode 18): warp = candidate row, census table at the shared-window base, the CTA's image-1 samples staged in shared memory by ONE
-                    // TMA copy (50 pixels x every second of 19 rows; 7.75 ms per 1080p pair at level 0 against 7.85 for mode 10, which reads them through L1).  Measured per 1080p pair at level 0 (round 2,
+                    // Default (mode 19): warp = candidate row, census table at the shared-window base, the CTA's image-1 samples staged in shared memory by ONE
+                    // TMA copy (50 pixels x every second of 19 rows; 7.75 ms per 1080p pair at level 0 against 7.85 for mode 10, which reads them through L1), and the
+                    // __expf fix-up test dropped behind an exact first patch row where that provably changes no bit (FASTW: 7.75 -> 7.54).  Measured per 1080p pair at level 0 (round 2,
                     // tools/variant_times.py, 16 pairs): column kernel 8.28 ms; its knobs allrows 9.72, wide address 8.78, 6 CTAs 8.54; row kernel
                     // 8.06-8.12, + fixed-address census table 7.85, + guard-free loop for interior warps 7.92 (spills), warp-uniform guards (mode 16) 7.88,
                     // census table indexed by the XOR byte instead of POPC (modes 12-15: plain 7.94, replicated x8 / x16 / x32 8.23 / 8.27 / 12.3).
                     // Tuning knob EPPM_REFINE_MODE: 0-7 = column kernel with allrows + 2 * wide + 4 * (6 CTAs per SM), 8-11 = row kernel + 2 * table at base + guard-free
-                    static const int mode = getenv("EPPM_REFINE_MODE") ? atoi(getenv("EPPM_REFINE_MODE")) : 18;
+                    static const int mode = getenv("EPPM_REFINE_MODE") ? atoi(getenv("EPPM_REFINE_MODE")) : 19;
                     static const CUtensorMap dummy_map = {};
-                    const int md = (v & EPPM_VAR_REFINE_COLUMN) ? 0 : mode;
+                    const int md = (v & EPPM_VAR_REFINE_COLUMN) ? 0 : (mode == 19 && (v & EPPM_VAR_REFINE_NOFASTW)) ? 18 : mode;
 #define EPPM_RT(MB, AR, WD) k_c2f_refine_tab<true, 3, MB, 2, AR, WD><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp)
                     switch (md) {
 #define EPPM_RR(L0, FP) k_c2f_refine_row<7, 2, L0, FP><<<grd, blk, (16 + 9 * RF_PIX) * sizeof(float), c->stream>>>(a, c->cost_lut, *tabp, dummy_map)
                     case 8: EPPM_RR(false, false); break;
                     case 9: EPPM_RR(false, true); break;
-                    case 19:     // mode 18 + fix-up-free loop behind an exact first patch row (FASTW)
-                    case 18: {   // default: image-1 tile staged by TMA (needs the level's refine tensor map and the table-at-base addressing); else mode 10
+                    case 19:     // default: mode 18 + fix-up-free loop behind an exact first patch row (FASTW)
+                    case 18: {   // image-1 tile staged by TMA (needs the level's refine tensor map and the table-at-base addressing); else mode 10
                         int lvl = -1;
                         for (int l = 0; l < c->n_levels; l++)
                             if (pix1 == c->pix[0][l] && c->tmap_refine_ok[l]) lvl = l;
