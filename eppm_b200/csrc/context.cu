@@ -253,6 +253,7 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         }
         c->smooth_fast_div = checked_ok;
     }
+    c->vol_ok = p.patch_stride == 2 && build_vol_tab(c->vol_tab);
     for (int l = 0; l + 1 < c->n_levels; l++) c->aff_ok[l] = build_affine_tab(c->aff_tab[l], c->lv[l].pw, c->lv[l].w, c->lv[l].h, p.patch_stride, true);
     build_gauss_tables(c);
     // the random tables are expanded on the first PatchMatch of the context (ensure_rng_tables): the legacy stage functions create

@@ -37,6 +37,7 @@ enum {
     EPPM_VAR_REFINE_COLUMN = 1048576,  // table refine with warp = candidate column, thread = three candidate rows (round-1 default) instead of warp = candidate row
     EPPM_VAR_PROP_Q = 2097152,         // propagation: the warp-per-evaluation scoring kernel reads the parity-split planes (dense sample rows; measured slower: 4.45 vs 4.24 ms per pair)
     EPPM_VAR_PROP_WARP_FULL = 131072,  // propagation queue scored by one warp per evaluation with ALL samples staged in shared memory (13 KB per warp starves the L1)
+    EPPM_VAR_REFINE_VOLUME = 8388608,  // refine with the AD + census terms of a CTA computed once per (image-1 column, displacement) into shared memory (k_c2f_refine_vol; measured slower: 8.75 vs 7.54 ms per pair at level 0, bound by L1 wavefronts)
     EPPM_VAR_REFINE_NOFASTW = 4194304, // refine: every patch row with the __expf fix-up test (default: only the first row, then a test-free loop where that provably changes no bit)
     EPPM_VAR_PROP_NOSKIP = 8,      // propagation: evaluate candidates that equal the current target (the reference does)
 };
@@ -71,6 +72,21 @@ struct AffineTab {
     int exc_s;         // sample index of that site, -1 = none
     int exc_q;         // its model (0..2)
     float exc_cj, exc_ci;
+};
+
+// Shared AD + census volume of the refine kernel (k_c2f_refine_vol, stride 2).  The AD + census half of a patch sample depends only on the
+// image-1 pixel q1 = x + j of patch row i and on the displacement (dX, dY) = D(x) + candidate + site offset of the model -- not on the pixel x
+// that asks for it.  Per patch row r = (i + 9) / 2 the displacements all models and candidates of a CTA can ask for (relative to the CTA's
+// smallest integer flow, flows spreading by at most 1 in x and y inside the CTA) fill a box of bx[r] x by[r] "lines"; a line holds the term
+// for the CTA's 50 image-1 columns.  T[q][s] is the byte offset of (model q, sample s) inside the volume for the centre candidate (m = 1,
+// n = 1) of a lane whose flow is the CTA minimum, column of lane 0; used[r][sx + 2 sy] marks the lines some lane can read when the flows
+// spread by sx / sy.
+constexpr int VOL_COLS = 32 + 2 * PATCH_R;   // image-1 columns of a CTA of 32 pixels
+constexpr int VOL_MAX_LINES = 104;           // >= max over rows of bx * by (98 for the reference's coefficient sets; checked by build_vol_tab)
+struct VolTab {
+    int T[4][100];
+    int xlo[10], ylo[10], bx[10], by[10];
+    unsigned used[10][4][4];
 };
 
 struct SmoothLut {
@@ -144,6 +160,8 @@ struct eppm_context {
     void* tile_comm = nullptr;                   // ncclComm_t of the tiling group (tiled.cu); rank / size below
     int tile_rank = 0, tile_world = 0;
     int band_y0 = 0, band_y1 = 0;                // rows of the coarsest level this context owns (whole level unless tiled across GPUs)
+    eppm::VolTab vol_tab;                        // shared AD + census volume tables of the refine kernel (stride 2 only)
+    int vol_ok = 0;
     eppm::AffineTab aff_tab[eppm::MAX_LEVELS];   // per level (pitch): verified sample-site tables of the plane-fitting refine
     int aff_ok[eppm::MAX_LEVELS] = {};
     int variant = 0;                             // EPPM_VARIANT bit mask (A/B switches for measurements, see EPPM_VAR_*)
@@ -175,6 +193,7 @@ bool ensure_pm_buffers(eppm_context* c);   // second arena: random tables, propa
 void ensure_rng_tables(eppm_context* c);   // builds them on the context's stream the first time a PatchMatch is queued
 void build_gauss_tables(eppm_context* c);
 bool build_affine_tab(AffineTab& t, int pw, int w, int h, int stride = 2, bool allow_exception = false);
+bool build_vol_tab(VolTab& v);   // stride 2; false if the boxes do not fit VOL_MAX_LINES
 
 // building blocks reused by the legacy stage ABI (foreign buffers)
 void op_lr_check(cudaStream_t s, short2* nnf, float* cost, const short2* nnf2, int w, int h, int n);

@@ -596,6 +596,248 @@ static bool lut0_window_base_ok(int device) {
     return ok;
 }
 
+// ---- table-driven refine with a SHARED AD + census volume (default at stride 2) ----
+// k_c2f_refine_row scores 36 (candidate, model) pairs x 100 samples per pixel, each sample = an AD + census term (13 of its ~24 issued
+// instructions, the POPC and one of its two MUFU.EX2) times a bilateral weight.  The AD + census term depends only on the image-1 pixel
+// q1 = x + j of patch row i and on the displacement between the two sampled pixels, (dX, dY) = D(x) + (m - 1, n - 1) + site offset of the
+// model -- not on the pixel x that asks for it: along a patch row, pixel x at sample j + 2 and pixel x + 2 at sample j ask for the same term
+// whenever their integer flows agree.  Per patch row the CTA therefore first fills a volume V[line(dX, dY)][q1] for its 50 image-1 columns
+// and the box of displacements its 32 pixels x 9 candidates x 4 models can ask for (VolTab; 21-48 of the box's lines are ever read, against
+// 360 direct evaluations per column), coalesced and with the very instruction sequence of sample_eval, and the scoring loop reads the term
+// back with one LDS per sample.  The weight half of a sample -- which depends on the candidate's centre pixel -- is computed as before, in
+// the reference's sample order: the same bits.  CTAs whose integer flows spread by more than 1, that touch the image border, or that
+// hold an unknown flow keep the direct loop of k_c2f_refine_row.
+// MEASURED SLOWER than k_c2f_refine_row and therefore not the default (EPPM_VARIANT bit 8388608 / EPPM_REFINE_MODE 20-22; same bits): 8.75 ms per
+// 1080p pair at level 0 against 7.54.  The scoring loop drops from ~25 to 15.2 issued instructions per sample and the XU pipe from 63 % to 34 %,
+// but (a) filling the volume costs ~80 instructions per line (342-495 lines per CTA, 50 of 64 lane slots used), which brings the total back
+// to the direct kernel's count (24.8e9 against 25.5e9 warp instructions per 4 pairs), (b) the 30 KB of shared memory per CTA leave 6 CTAs per
+// SM and 42 KB of L1 (7 CTAs / 11 KB of L1: 12.3 ms), and (c) both forms need the same five L1 wavefronts per sample -- four for the 16-byte
+// image-2 load the weight needs, one for the census table or the volume -- and with fewer instructions the L1 data pipe becomes the limit
+// (82 % of its peak, 60 % of the issue slots): profiles/r02_ncu_refine_vol_l0_summary.txt.
+__device__ __forceinline__ float ad_census_term(const float4& p1, const float4& p2) {
+    const float c = max3abs_diff(pack_pix(p1), pack_pix(p2));
+    return __fadd_rn(exp_ad_cost(c), census_lut_ref(Lut0(), p1, p2));   // (1 - e) + census: sample_eval's two roundings
+}
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ float lds_f32_imm(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+
+// one patch row of the scoring loop: weights as in refine_row_loop, AD + census from the volume.  lane_row: shared-window byte address of
+// this lane's column in line ((n - 1 + ddy) * bx + ddx) of the volume.
+template <bool TINY>
+__device__ __forceinline__ void vol_use_row(const RefineArgs& a, const CostLut& lut, const AffineTab& tab, const VolTab& vt, int r, const float4* trow,
+                                            const float4* Pc, const PixPk& c1k, const PixPk (&c2k)[3], unsigned wmask, unsigned lane_row,
+                                            float (&cs)[3][4], float (&ws)[3][4]) {
+    const int i = -PATCH_R + 2 * r;
+    const int ai = i < 0 ? -i : i;
+    const int irow = i * a.pw;
+    int s = r * 10;
+EPPM_PRAGMA(unroll RF_JUNROLL)
+    for (int j = -PATCH_R; j <= PATCH_R; j += 2, s++) {
+        const PixPk p1k = pack_pix(trow[j + PATCH_R]);
+        const float d1 = max3abs_diff(c1k, p1k);
+        const float gg = lut.gg[ai][j < 0 ? -j : j];
+        const float4* site[4];
+        unsigned va[4];
+        site[0] = pix_at(Pc, irow + j);
+        va[0] = lane_row + (unsigned)vt.T[0][s];
+#pragma unroll
+        for (int q = 1; q < 4; q++) {
+            site[q] = pix_at(Pc, tab.off[q - 1][s]);
+            va[q] = lane_row + (unsigned)vt.T[q][s];
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            if (!(wmask & (1u << m))) continue;   // uniform, never taken: keeps the three candidates in separate basic blocks (see refine_row_loop)
+            float arg[4], t2[4], w[4], ct[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float d2 = max3abs_diff(c2k[m], pack_pix(ldpix(site[q] + (m - 1))));
+                arg[q] = __fmaf_rn(d1, d1, __fmul_rn(d2, d2));
+            }
+            const f32x2 R = pk2(-99.99999237060546875f, -99.99999237060546875f), D = pk2(0.010000000707805156708f, 0.010000000707805156708f);
+            const f32x2 Z = pk2(0.f, 0.f), L2E = pk2(1.4426950216293334961f, 1.4426950216293334961f);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {   // div_neg_0p01 and the log2e multiply on two models per packed instruction (IEEE per half)
+                const f32x2 x = pk2(arg[2 * h], arg[2 * h + 1]);
+                const f32x2 q0 = fma2(x, R, Z);
+                const f32x2 qq = fma2(R, fma2(q0, D, x), q0);
+                upk2(mul2(qq, L2E), t2[2 * h], t2[2 * h + 1]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) w[q] = __fmul_rn(ex2_mufu(t2[q]), gg);
+            if (TINY && fminf(fminf(t2[0], t2[1]), fminf(t2[2], t2[3])) < -126.0f) {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (t2[q] < -126.0f) w[q] = __fmul_rn(ex2_tiny(t2[q]), gg);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                ct[q] = m == 0 ? lds_f32_imm<-4 * VOL_COLS>(va[q]) : m == 1 ? lds_f32_imm<0>(va[q]) : lds_f32_imm<4 * VOL_COLS>(va[q]);
+                cs[m][q] = __fmaf_rn(ct[q], w[q], cs[m][q]);
+                ws[m][q] = __fadd_rn(ws[m][q], w[q]);
+            }
+        }
+    }
+}
+
+constexpr int RF_VOL_TILE_OFF = 1280;                                                              // byte offsets inside the dynamic shared memory
+constexpr int RF_VOL_BAR_OFF = RF_VOL_TILE_OFF + RF_TILE_W * RF_TILE_H * (int)sizeof(float4);
+constexpr int RF_VOL_V_OFF = RF_VOL_BAR_OFF + 16;
+constexpr int RF_VOL_SMEM = RF_VOL_V_OFF + VOL_MAX_LINES * VOL_COLS * (int)sizeof(float);
+
+template <int MINB>
+__global__ void __launch_bounds__(RF_PIX * 3, MINB)
+    k_c2f_refine_vol(RefineArgs a, const __grid_constant__ CostLut lut, const __grid_constant__ AffineTab tab, const __grid_constant__ CUtensorMap tmap1,
+                     const __grid_constant__ VolTab vt) {
+    // no static shared memory in this kernel (Lut0): [0, 16) census table, s_best[9][RF_PIX], image-1 tile, mbarrier, volume
+    extern __shared__ float s_dyn[];
+    float (*s_best)[RF_PIX] = reinterpret_cast<float (*)[RF_PIX]>(s_dyn + 16);
+    float4* s_tile = reinterpret_cast<float4*>(reinterpret_cast<char*>(s_dyn) + RF_VOL_TILE_OFF);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(s_dyn) + RF_VOL_BAR_OFF);
+    float* s_vol = reinterpret_cast<float*>(reinterpret_cast<char*>(s_dyn) + RF_VOL_V_OFF);
+    load_census_lut(s_dyn, lut);
+    const int n = threadIdx.x >> 5, pl = threadIdx.x & 31;   // n: candidate row of this warp
+    const int x0 = blockIdx.x * RF_PIX, x = x0 + pl, y = a.y0 + blockIdx.y;
+    const bool in = x < a.w;
+    const int b = blockIdx.z;
+    if (threadIdx.x == 0) {
+        mbar_init(s_bar, 1);
+        mbar_expect_tx(s_bar, RF_TILE_W * RF_TILE_H * sizeof(float4));
+        tma_load_3d(s_tile, &tmap1, (x0 + PAD - PATCH_R) * 4, y + PAD - PATCH_R, b, s_bar);
+    }
+    const float4* I1 = a.pix1 + (size_t)b * a.plane;
+    const float4* I2 = a.pix2 + (size_t)b * a.plane;
+    float2 fl = make_float2(0.f, 0.f);
+    if (in) fl = a.upsample ? upsample2(a.coarse + (size_t)b * a.ws * a.hs, a.ws, a.hs, x, y) : a.coarse[(size_t)b * a.w * a.h + (size_t)y * a.w + x];
+    const bool unknown = fl.x > EPPM_UNKNOWN_FLOW_THRESH || fl.y > EPPM_UNKNOWN_FLOW_THRESH;  // :2011
+    const short cxc = (short)((short)(int)fl.x + x), cyc = (short)((short)(int)fl.y + y);     // :2014-2019
+    const short cy = (short)(cyc + (n - 1));
+    __syncthreads();          // the barrier object is initialised before anyone polls it
+    mbar_wait(s_bar, 0);
+    float cost[3];
+    bool valid[3];
+    bool any = false, all = true;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const short cx = (short)(cxc + (m - 1));
+        cost[m] = FLT_MAX;
+        valid[m] = in && !unknown && !(cx < 0 || cy < 0 || cx >= a.w || cy >= a.h);  // :2029
+        any = any || valid[m];
+        all = all && valid[m];
+    }
+    // CTA-uniform choice (the three warps hold the same 32 pixels, so each of them computes the same answer): the volume needs every lane's nine
+    // candidates inside the image -- then no site leaves the padded plane, see build_affine_tab -- and integer flows within one step of each other
+    const int dxl = (int)cxc - x, dyl = (int)cyc - y;
+    const bool inside = in && !unknown && cxc >= 1 && cxc + 1 < a.w && cyc >= 1 && cyc + 1 < a.h;
+    const bool full = __all_sync(0xffffffffu, inside);
+    const int Dx0 = __reduce_min_sync(0xffffffffu, dxl), Dx1 = __reduce_max_sync(0xffffffffu, dxl);
+    const int Dy0 = __reduce_min_sync(0xffffffffu, dyl), Dy1 = __reduce_max_sync(0xffffffffu, dyl);
+    const bool use_vol = full && Dx1 - Dx0 <= 1 && Dy1 - Dy0 <= 1;
+    unsigned wmask = 7u;
+    asm volatile("" : "+r"(wmask));   // opaque to the compiler: see refine_row_loop
+    float cs[3][4], ws[3][4];
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) cs[m][q] = ws[m][q] = 0.f;
+    if (use_vol) {
+        const PixPk c1k = pack_pix(ldpix(I1 + (unsigned)((y + PAD) * a.pw + x + PAD)));
+        const float4* Pc = I2 + (unsigned)(((int)cy + PAD) * a.pw + (int)cxc + PAD);
+        PixPk c2k[3];
+#pragma unroll
+        for (int m = 0; m < 3; m++) c2k[m] = pack_pix(ldpix(Pc + (m - 1)));
+        const int sxy = (Dx1 - Dx0) | ((Dy1 - Dy0) << 1);
+        const unsigned vs = (unsigned)__cvta_generic_to_shared(s_vol);
+        bool fast = false;
+#pragma unroll 1
+        for (int r = 0; r < 10; r++) {
+            const int bxr = vt.bx[r], nl = bxr * vt.by[r];
+            {   // fill the lines of this patch row: warp n takes lines n, n + 3, ...; a lane its column and, for lanes < 18, column + 32
+                const int i = -PATCH_R + 2 * r;
+                const unsigned rowbase = (unsigned)((y + i + Dy0 + vt.ylo[r] + PAD) * a.pw + (x0 - PATCH_R + Dx0 + vt.xlo[r] + PAD));
+                const float4* trow = s_tile + r * RF_TILE_W;
+                int dXi = n, dYi = 0;
+#pragma unroll 1
+                for (int L = n; L < nl; L += 3) {
+                    if ((vt.used[r][sxy][L >> 5] >> (L & 31)) & 1u) {
+                        const float4* rp = I2 + (rowbase + (unsigned)(dYi * a.pw + dXi));
+                        float* vrow = s_vol + L * VOL_COLS;
+                        const float4 p2a = ldpix(rp + pl);
+                        float4 p2b = p2a;
+                        if (pl < VOL_COLS - 32) p2b = ldpix(rp + pl + 32);
+                        vrow[pl] = ad_census_term(trow[pl], p2a);
+                        if (pl < VOL_COLS - 32) vrow[pl + 32] = ad_census_term(trow[pl + 32], p2b);
+                    }
+                    dXi += 3;
+                    if (dXi >= bxr) { dXi -= bxr; dYi++; }
+                }
+            }
+            __syncthreads();
+            const unsigned lane_row = vs + 4u * (unsigned)(((n - 1 + (dyl - Dy0)) * bxr + (dxl - Dx0)) * VOL_COLS + pl);
+            const float4* trow = s_tile + r * RF_TILE_W + pl;
+            if (fast) vol_use_row<false>(a, lut, tab, vt, r, trow, Pc, c1k, c2k, wmask, lane_row, cs, ws);
+            else vol_use_row<true>(a, lut, tab, vt, r, trow, Pc, c1k, c2k, wmask, lane_row, cs, ws);
+            if (r == 0) {   // FASTW (see k_c2f_refine_row): every accumulator >= 2^-99 absorbs any weight that would need the __expf fix-up
+                float lo = FLT_MAX;
+#pragma unroll
+                for (int m = 0; m < 3; m++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) lo = fminf(lo, fminf(cs[m][q], ws[m][q]));
+                fast = __all_sync(0xffffffffu, lo >= 1.57772181e-30f);
+            }
+            __syncthreads();   // the next patch row overwrites the volume
+        }
+    } else if (any) {
+        const float4* a0 = I1 + (unsigned)((y + PAD) * a.pw + x + PAD);
+        const PixPk c1k = pack_pix(ldpix(a0));
+        const int cys = max(0, min(a.h - 1, (int)cy)), cxs = max(-1, min(a.w, (int)cxc));
+        const float4* Pc = I2 + (unsigned)((cys + PAD) * a.pw + cxs + PAD);
+        asm volatile("" : "+l"(Pc));
+        PixPk c2k[3];
+#pragma unroll
+        for (int m = 0; m < 3; m++) c2k[m] = pack_pix(ldpix(Pc + (m - 1)));
+        refine_row_loop<2, true, Lut0, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl);
+    }
+    if (any) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            if (!valid[m]) continue;
+            const float k1 = __fdiv_rn(cs[m][0], ws[m][0]), k2 = __fdiv_rn(cs[m][1], ws[m][1]);
+            const float k3 = __fdiv_rn(cs[m][2], ws[m][2]), k4 = __fdiv_rn(cs[m][3], ws[m][3]);
+            cost[m] = min_ref(k1, min_ref(k2, min_ref(k3, k4)));  // :512
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 3; m++) s_best[m * 3 + n][pl] = valid[m] ? cost[m] : __int_as_float(0x7f800000);   // index = m * 3 + n: the reference's order (m outer)
+    __syncthreads();
+    if (in && n == 0) {
+        float2 out;
+        if (unknown) out = make_float2(0.f, 0.f);
+        else {
+            float bcost = 999999.f;   // :2024,:2031 strict '<' against 999999, m outer, n inner
+            int bk = -1;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const float oc = s_best[k][pl];
+                if (oc < bcost) { bcost = oc; bk = k; }
+            }
+            short bx = cxc, by = cyc;   // :2020-2022 default = centre candidate
+            if (bk >= 0) { bx = (short)(cxc + (bk / 3 - 1)); by = (short)(cyc + (bk % 3 - 1)); }
+            out = make_float2((float)(bx - x), (float)(by - y));  // :2038-2039
+        }
+        a.flow[(size_t)b * a.w * a.h + (size_t)y * a.w + x] = out;
+    }
+}
+
 // ---- table-driven refine, models in packed pairs (default) ----
 // Same decomposition as k_c2f_refine_tab with NCT = 3 (warp m owns candidate column m, a thread its three candidate rows x four
 // models), but the four models of a candidate are evaluated as TWO PAIRS in the halves of packed FP32x2 instructions
@@ -767,6 +1009,52 @@ bool build_affine_tab(AffineTab& t, int pw, int w, int h, int stride, bool allow
                 if (abs(dy + i) >= PAD) return false;
                 t.off[q][s] = (dy + i) * pw + (dx + j);
             }
+    return true;
+}
+
+// Tables of the shared AD + census volume (see VolTab).  Site offsets as in build_affine_tab (whose check that they do not depend on the
+// coordinate is what makes a table legitimate; the volume kernel is only used at levels whose affine table verified).
+bool build_vol_tab(VolTab& v) {
+    static const float pf[3][4] = {{0.177f, -0.011f, -0.003f, 0.301f}, {0.125f, -0.357f, 0.009f, 0.308f}, {0.205f, 0.370f, 0.011f, 0.296f}};
+    auto site = [](float fi, float fj, float cj, float ci, int X) { return (int)floorf(fmaf(fi, ci, fmaf(fj, cj, (float)X))) - X; };
+    static int ox[4][100], oy[4][100];
+    int s = 0;
+    for (int i = -PATCH_R; i <= PATCH_R; i += 2)
+        for (int j = -PATCH_R; j <= PATCH_R; j += 2, s++) {
+            ox[0][s] = oy[0][s] = 0;
+            for (int q = 0; q < 3; q++) {
+                ox[q + 1][s] = site((float)i, (float)j, pf[q][0], pf[q][1], 1000);
+                oy[q + 1][s] = site((float)i, (float)j, pf[q][2], pf[q][3], 1000);
+            }
+        }
+    memset(&v, 0, sizeof(v));
+    for (int r = 0; r < 10; r++) {
+        int xmin = 1 << 20, xmax = -(1 << 20), ymin = 1 << 20, ymax = -(1 << 20);
+        for (int q = 0; q < 4; q++)
+            for (int jj = 0; jj < 10; jj++) {
+                const int k = r * 10 + jj;
+                xmin = ox[q][k] < xmin ? ox[q][k] : xmin; xmax = ox[q][k] > xmax ? ox[q][k] : xmax;
+                ymin = oy[q][k] < ymin ? oy[q][k] : ymin; ymax = oy[q][k] > ymax ? oy[q][k] : ymax;
+            }
+        // box = site offsets + candidate column / row (-1..1) + flow spread inside the CTA (0..1)
+        v.xlo[r] = xmin - 1; v.bx[r] = xmax - xmin + 4;
+        v.ylo[r] = ymin - 1; v.by[r] = ymax - ymin + 4;
+        if (v.bx[r] < 4 || v.bx[r] * v.by[r] > VOL_MAX_LINES || v.bx[r] * v.by[r] > 128) return false;
+        for (int q = 0; q < 4; q++)
+            for (int jj = 0; jj < 10; jj++) {
+                const int k = r * 10 + jj;
+                const int line = (oy[q][k] - v.ylo[r]) * v.bx[r] + (ox[q][k] - v.xlo[r]);
+                v.T[q][k] = 4 * (line * VOL_COLS + 2 * jj);   // column of lane 0 at sample j = -9 + 2 jj: (j + 9)
+                for (int sxy = 0; sxy < 4; sxy++)
+                    for (int m = -1; m <= 1; m++)
+                        for (int n = -1; n <= 1; n++)
+                            for (int ddx = 0; ddx <= (sxy & 1); ddx++)
+                                for (int ddy = 0; ddy <= (sxy >> 1); ddy++) {
+                                    const int L = line + (n + ddy) * v.bx[r] + m + ddx;
+                                    v.used[r][sxy][L >> 5] |= 1u << (L & 31);
+                                }
+            }
+    }
     return true;
 }
 
@@ -1110,12 +1398,31 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                     // Tuning knob EPPM_REFINE_MODE: 0-7 = column kernel with allrows + 2 * wide + 4 * (6 CTAs per SM), 8-11 = row kernel + 2 * table at base + guard-free
                     static const int mode = getenv("EPPM_REFINE_MODE") ? atoi(getenv("EPPM_REFINE_MODE")) : 19;
                     static const CUtensorMap dummy_map = {};
-                    const int md = (v & EPPM_VAR_REFINE_COLUMN) ? 0 : (mode == 19 && (v & EPPM_VAR_REFINE_NOFASTW)) ? 18 : mode;
+                    const int md = (v & EPPM_VAR_REFINE_COLUMN) ? 0 : (v & EPPM_VAR_REFINE_VOLUME) ? 20 : (mode == 19 && (v & EPPM_VAR_REFINE_NOFASTW)) ? 18 : mode;
 #define EPPM_RT(MB, AR, WD) k_c2f_refine_tab<true, 3, MB, 2, AR, WD><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp)
                     switch (md) {
 #define EPPM_RR(L0, FP) k_c2f_refine_row<7, 2, L0, FP><<<grd, blk, (16 + 9 * RF_PIX) * sizeof(float), c->stream>>>(a, c->cost_lut, *tabp, dummy_map)
                     case 8: EPPM_RR(false, false); break;
                     case 9: EPPM_RR(false, true); break;
+                    case 20: case 21: case 22: {   // shared AD + census volume (6 / 7 / 5 CTAs per SM); needs everything mode 19 needs
+                        int lvl = -1;
+                        for (int l = 0; l < c->n_levels; l++)
+                            if (pix1 == c->pix[0][l] && c->tmap_refine_ok[l]) lvl = l;
+                        if (lvl >= 0 && c->vol_ok && lut0_window_base_ok(c->device)) {
+                            static bool attr_v[64] = {};
+                            if (!attr_v[c->device & 63]) {
+                                cudaFuncSetAttribute(k_c2f_refine_vol<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_VOL_SMEM);
+                                cudaFuncSetAttribute(k_c2f_refine_vol<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_VOL_SMEM);
+                                cudaFuncSetAttribute(k_c2f_refine_vol<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_VOL_SMEM);
+                                attr_v[c->device & 63] = true;
+                            }
+                            if (md == 21) k_c2f_refine_vol<7><<<grd, blk, RF_VOL_SMEM, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl], c->vol_tab);
+                            else if (md == 22) k_c2f_refine_vol<5><<<grd, blk, RF_VOL_SMEM, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl], c->vol_tab);
+                            else k_c2f_refine_vol<6><<<grd, blk, RF_VOL_SMEM, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl], c->vol_tab);
+                            break;
+                        }
+                    }
+                    // fall through
                     case 19:     // default: mode 18 + fix-up-free loop behind an exact first patch row (FASTW)
                     case 18: {   // image-1 tile staged by TMA (needs the level's refine tensor map and the table-at-base addressing); else mode 10
                         int lvl = -1;

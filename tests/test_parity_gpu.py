@@ -920,12 +920,13 @@ def test_variant_switches_compute_the_same_bits():
     refine, grouped vs per-sample __expf fix-up, joint vs serial random search, work-queue vs CTA-local propagation with and without
     skipping / compaction, four-row packed vs two-row smoothing, three- vs nine-warp refine, texture vs LSU gathers and one vs three
     passes in the random search, scalar vs packed-pair refine, warp-per-evaluation vs thread-per-evaluation scoring of the propagation
-    queue and of the random search, barrier-free segment chains.  All of them must produce the flow of the default build bit for bit."""
+    queue and of the random search, barrier-free segment chains, the refine with its fix-up-free loop switched off and with a shared AD +
+    census volume.  All of them must produce the flow of the default build bit for bit."""
     h, w = 270, 480
     a, b, _, _ = synth.make_batch(h, w, 2, first_idx=11, distinct=2)
     flows = {}
     try:
-        for v in (0, 1, 2, 4, 8, 16, 32, 64, 127, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 131072, 262144, 524288, 524288 + 8192, 1048576, 2097152, 4194304):
+        for v in (0, 1, 2, 4, 8, 16, 32, 64, 127, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 131072, 262144, 524288, 524288 + 8192, 1048576, 2097152, 4194304, 8388608):
             os.environ["EPPM_VARIANT"] = str(v)
             ctx = E.EppmContext(h, w, 2)
             if v == 0:
