@@ -38,6 +38,7 @@ enum {
     EPPM_VAR_PROP_Q = 2097152,         // propagation: the warp-per-evaluation scoring kernel reads the parity-split planes (dense sample rows; measured slower: 4.45 vs 4.24 ms per pair)
     EPPM_VAR_PROP_WARP_FULL = 131072,  // propagation queue scored by one warp per evaluation with ALL samples staged in shared memory (13 KB per warp starves the L1)
     EPPM_VAR_REFINE_VOLUME = 8388608,  // refine with the AD + census terms of a CTA computed once per (image-1 column, displacement) into shared memory (k_c2f_refine_vol; measured slower: 8.75 vs 7.54 ms per pair at level 0, bound by L1 wavefronts)
+    EPPM_VAR_CENSUS_NOTMA = 16777216,  // census + pack: nine clamped loads and nine luminances per thread (round 1) instead of a TMA-staged tile whose luminances are formed once
     EPPM_VAR_REFINE_NOFASTW = 4194304, // refine: every patch row with the __expf fix-up test (default: only the first row, then a test-free loop where that provably changes no bit)
     EPPM_VAR_PROP_NOSKIP = 8,      // propagation: evaluate candidates that equal the current target (the reference does)
 };
@@ -81,6 +82,7 @@ struct AffineTab {
 // for the CTA's 50 image-1 columns.  T[q][s] is the byte offset of (model q, sample s) inside the volume for the centre candidate (m = 1,
 // n = 1) of a lane whose flow is the CTA minimum, column of lane 0; used[r][sx + 2 sy] marks the lines some lane can read when the flows
 // spread by sx / sy.
+constexpr unsigned CEN_TILE_W = 40, CEN_TILE_H = 10;   // census kernel: 32 x 8 pixels + halo = 34 x 10, fetched from 3 pixels further left: a TMA box must start on a 16-byte boundary (probed: tools/probe_tma_u32.cu)
 constexpr int VOL_COLS = 32 + 2 * PATCH_R;   // image-1 columns of a CTA of 32 pixels
 constexpr int VOL_MAX_LINES = 104;           // >= max over rows of bx * by (98 for the reference's coefficient sets; checked by build_vol_tab)
 struct VolTab {
@@ -156,6 +158,8 @@ struct eppm_context {
     int tmap_ok[eppm::MAX_LEVELS] = {};
     CUtensorMap tmap_refine[eppm::MAX_LEVELS];   // ... and of the refine kernel's image-1 tile (default refine: EPPM_REFINE_MODE=18)
     int tmap_refine_ok[eppm::MAX_LEVELS] = {};
+    CUtensorMap tmap_rgba[2][eppm::MAX_LEVELS];  // ... and of the dense RGBA levels (tile + halo of the census kernel)
+    int tmap_rgba_ok[2][eppm::MAX_LEVELS] = {};
     int tmap_box_h = 0;                          // tile height the tensor maps were encoded for
     void* tile_comm = nullptr;                   // ncclComm_t of the tiling group (tiled.cu); rank / size below
     int tile_rank = 0, tile_world = 0;

@@ -217,6 +217,91 @@ __global__ void __launch_bounds__(256) k_census_pack(const uchar4* __restrict__ 
     pix[(size_t)blockIdx.z * pw * ph + (size_t)py * pw + px] = o;
 }
 
+// The same with the CTA's 32 x 8 source pixels and their one-pixel halo staged in shared memory by ONE TMA copy (cp.async.bulk.tensor + mbarrier,
+// box 40 x 10 uchar4: the 34 x 10 pixels it needs plus three to the left, because the box of a non-interleaved map must start on a 16-byte
+// boundary -- an unaligned start is an illegal instruction, tools/probe_tma_u32.cu) and every luminance formed once per tile entry instead of
+// nine times per pixel.  A tensor map's out-of-bounds fill is zero,
+// not clamp-to-edge, so only CTAs whose tile lies inside the image take this path; the CTAs of the replicated border and of the image rim keep
+// the per-thread clamped loads.  Same comparisons on the same floats: the same bits.
+__global__ void __launch_bounds__(256) k_census_pack_tile(const uchar4* __restrict__ rgba, size_t pitch_px, size_t img_stride_px, float4* __restrict__ pix,
+                                                          int w, int h, int pw, int ph, const __grid_constant__ CUtensorMap tmap) {
+    __shared__ __align__(128) uchar4 s_px[CEN_TILE_H][CEN_TILE_W];
+    __shared__ float s_lum[CEN_TILE_H][CEN_TILE_W];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int px0 = blockIdx.x * 32, py0 = blockIdx.y * 8;
+    const int sx0 = px0 - PAD - 1, sy0 = py0 - PAD - 1;   // source pixel of tile entry (0, 0)
+    const bool interior = sx0 >= 0 && sy0 >= 0 && sx0 + 34 <= w && sy0 + 10 <= h && px0 + 32 <= pw && py0 + 8 <= ph;   // CTA-uniform
+    const int px = px0 + threadIdx.x, py = py0 + threadIdx.y;
+    if (interior) {
+        const int tid = threadIdx.y * 32 + threadIdx.x;
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_expect_tx(&s_bar, CEN_TILE_W * CEN_TILE_H * (unsigned)sizeof(uchar4));
+            tma_load_3d(&s_px[0][0], &tmap, sx0 - 3, sy0, blockIdx.z, &s_bar);   // sx0 - 3 = px0 - 20: a multiple of 4 pixels
+        }
+        __syncthreads();   // the barrier object is initialised before anyone polls it
+        mbar_wait(&s_bar, 0);
+        for (int i = tid; i < (int)(CEN_TILE_H * CEN_TILE_W); i += 256) (&s_lum[0][0])[i] = lum_of((&s_px[0][0])[i]);
+        __syncthreads();
+        const int tx = threadIdx.x + 4, ty = threadIdx.y + 1;   // tile column of source pixel sx0 + k is k + 3
+        const uchar4 c = s_px[ty][tx];
+        const float lc = s_lum[ty][tx];
+        unsigned cen = 0;
+        cen |= (s_lum[ty - 1][tx - 1] > lc) << 0;
+        cen |= (s_lum[ty - 1][tx] > lc) << 1;
+        cen |= (s_lum[ty - 1][tx + 1] > lc) << 2;
+        cen |= (s_lum[ty][tx - 1] > lc) << 3;
+        cen |= (s_lum[ty][tx + 1] > lc) << 4;
+        cen |= (s_lum[ty + 1][tx - 1] > lc) << 5;
+        cen |= (s_lum[ty + 1][tx] > lc) << 6;
+        cen |= (s_lum[ty + 1][tx + 1] > lc) << 7;
+        float4 o;
+        o.x = __fdiv_rn((float)c.x, 255.f);
+        o.y = __fdiv_rn((float)c.y, 255.f);
+        o.z = __fdiv_rn((float)c.z, 255.f);
+        o.w = __uint_as_float(pack_census(cen));
+        pix[(size_t)blockIdx.z * pw * ph + (size_t)py * pw + px] = o;
+        return;
+    }
+    if (px >= pw || py >= ph) return;
+    const uchar4* src = rgba + (size_t)blockIdx.z * img_stride_px;
+    const int x = max(0, min(w - 1, px - PAD)), y = max(0, min(h - 1, py - PAD));
+    const int xm = max(0, x - 1), xp = min(w - 1, x + 1), ym = max(0, y - 1), yp = min(h - 1, y + 1);
+    const uchar4* r0 = src + (size_t)ym * pitch_px;
+    const uchar4* r1 = src + (size_t)y * pitch_px;
+    const uchar4* r2 = src + (size_t)yp * pitch_px;
+    const uchar4 c = r1[x];
+    const float lc = lum_of(c);
+    unsigned cen = 0;
+    cen |= (lum_of(r0[xm]) > lc) << 0;
+    cen |= (lum_of(r0[x]) > lc) << 1;
+    cen |= (lum_of(r0[xp]) > lc) << 2;
+    cen |= (lum_of(r1[xm]) > lc) << 3;
+    cen |= (lum_of(r1[xp]) > lc) << 4;
+    cen |= (lum_of(r2[xm]) > lc) << 5;
+    cen |= (lum_of(r2[x]) > lc) << 6;
+    cen |= (lum_of(r2[xp]) > lc) << 7;
+    float4 o;
+    o.x = __fdiv_rn((float)c.x, 255.f);
+    o.y = __fdiv_rn((float)c.y, 255.f);
+    o.z = __fdiv_rn((float)c.z, 255.f);
+    o.w = __uint_as_float(pack_census(cen));
+    pix[(size_t)blockIdx.z * pw * ph + (size_t)py * pw + px] = o;
+}
+
+// census + pack of one of the context's own RGBA levels: the TMA-staged kernel when the level has a tensor map (16-byte row stride)
+static void op_census_pack(eppm_context* c, int img, int level, int n_img) {
+    const LevelGeom& g = c->lv[level];
+    if (c->tmap_rgba_ok[img][level] && !(c->variant & EPPM_VAR_CENSUS_NOTMA)) {
+        dim3 blk(32, 8), grd((g.pw + 31) / 32, (g.ph + 7) / 8, n_img);
+        k_census_pack_tile<<<grd, blk, 0, c->stream>>>(c->rgba[img][level], (size_t)g.w, (size_t)g.w * g.h, c->pix[img][level], g.w, g.h, g.pw, g.ph,
+                                                      c->tmap_rgba[img][level]);
+        EPPM_LAUNCH_COUNT(1);
+        return;
+    }
+    k_pack_planes(c->stream, c->rgba[img][level], (size_t)g.w * 4, (size_t)g.w * g.h * 4, c->pix[img][level], g, n_img);
+}
+
 void k_pack_planes(cudaStream_t s, const uchar4* rgba, size_t rgba_pitch_bytes, size_t rgba_img_stride_bytes, float4* pix, const LevelGeom& g,
                    int n_img) {
     dim3 blk(32, 8), grd((g.pw + 31) / 32, (g.ph + 7) / 8, n_img);
@@ -349,8 +434,7 @@ void op_pyramid_and_pack(eppm_context* c, int n, int two) {
     }
     for (int i = 0; i < c->n_levels; i++) {
         const LevelGeom& g = c->lv[i];
-        for (int img = 0; img < two; img++)
-            k_pack_planes(s, c->rgba[img][i], (size_t)g.w * 4, (size_t)g.w * g.h * 4, c->pix[img][i], g, n);
+        for (int img = 0; img < two; img++) op_census_pack(c, img, i, n);
     }
     const int L = c->n_levels - 1;
     for (int img = 0; img < two; img++) op_transpose_plane(s, c->pix[img][L], c->pixT[img], c->lv[L], n);

@@ -356,27 +356,6 @@ EPPM_PRAGMA(unroll RF_JUNROLL)
     }
 }
 
-// mbarrier / TMA helpers (PTX, sm_90+): one thread arms the barrier with the byte count, issues the bulk tensor copy, everyone waits.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
-                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // ---- table-driven refine, warp = candidate ROW ----
 // k_c2f_refine_tab gives warp m the candidate COLUMN m and a thread its three candidate rows: the twelve image-2 sites of a sample are
 // twelve 64-bit address computations (two ALU instructions each: 2.3 of the 30.9 issued instructions per sample).  Here warp n owns the
@@ -1647,6 +1626,18 @@ bool build_smooth_tensor_maps(eppm_context* c) {
         r = ((encode_fn)fn)(&c->tmap_refine[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->pix[0][l], dims, strides, rbox, restr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         c->tmap_refine_ok[l] = r == CUDA_SUCCESS;
+        // census + pack: 32 x 8 output pixels + a one-pixel halo of the dense RGBA level (uchar4 as one 32-bit element); the box is 40 wide because it
+        // must start on a 16-byte boundary (see k_census_pack_tile).  Needs 16-byte row and plane strides.
+        for (int img = 0; img < 2; img++) {
+            c->tmap_rgba_ok[img][l] = 0;
+            if (g.w % 4 || ((size_t)g.w * g.h) % 4 || !c->rgba[img][l]) continue;
+            const cuuint64_t cdims[3] = {(cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)c->max_batch};
+            const cuuint64_t cstrides[2] = {(cuuint64_t)g.w * 4, (cuuint64_t)g.w * g.h * 4};
+            const cuuint32_t cbox[3] = {CEN_TILE_W, CEN_TILE_H, 1};
+            r = ((encode_fn)fn)(&c->tmap_rgba[img][l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, c->rgba[img][l], cdims, cstrides, cbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            c->tmap_rgba_ok[img][l] = r == CUDA_SUCCESS;
+        }
     }
     return true;
 }

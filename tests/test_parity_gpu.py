@@ -868,8 +868,8 @@ def test_reference_host_class_on_this_library(tmp_path):
 
 @needs_ref
 def test_flow_colour_coding_vs_reference(ref, mine):
-    """bao_cuda_convert_flow_to_colorshow (C++ linkage; compute_flow's optional colour output): visualisation, compared per channel --
-    libdevice atan2f and a float->double->int chain leave room for one 8-bit level at a rounding boundary."""
+    """bao_cuda_convert_flow_to_colorshow (C++ linkage; compute_flow's optional colour output): the same libdevice atan2f and the same
+    float -> double -> int chain as the reference (read from its SASS) -> every byte identical."""
     sym = "_Z34bao_cuda_convert_flow_to_colorshowP6uchar4P6float2iiff"
     h, w = 120, 160
     g = torch.Generator(device="cpu").manual_seed(3)
@@ -886,10 +886,7 @@ def test_flow_colour_coding_vs_reference(ref, mine):
         torch.cuda.synchronize()
         outs.append(out.cpu().numpy()[..., :3].astype(np.int32))
     d = np.abs(outs[0] - outs[1])
-    print(f"colour coding: max |diff| {d.max()}, identical {(d == 0).mean():.6f}, differing bytes {(d != 0).sum()}")
-    if os.environ.get("EPPM_TEST_COLOUR_EXACT"):
-        assert d.max() == 0, (d.max(), (d != 0).sum())
-    assert d.max() <= 1 and (d == 0).mean() >= 0.999, (d.max(), (d == 0).mean())
+    assert d.max() == 0, (d.max(), (d != 0).sum())
     assert (outs[0][:10, :20] == 0).all() and outs[0].std() > 20
 
 
@@ -921,12 +918,12 @@ def test_variant_switches_compute_the_same_bits():
     skipping / compaction, four-row packed vs two-row smoothing, three- vs nine-warp refine, texture vs LSU gathers and one vs three
     passes in the random search, scalar vs packed-pair refine, warp-per-evaluation vs thread-per-evaluation scoring of the propagation
     queue and of the random search, barrier-free segment chains, the refine with its fix-up-free loop switched off and with a shared AD +
-    census volume.  All of them must produce the flow of the default build bit for bit."""
+    census volume, the census kernel without its TMA-staged tile.  All of them must produce the flow of the default build bit for bit."""
     h, w = 270, 480
     a, b, _, _ = synth.make_batch(h, w, 2, first_idx=11, distinct=2)
     flows = {}
     try:
-        for v in (0, 1, 2, 4, 8, 16, 32, 64, 127, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 131072, 262144, 524288, 524288 + 8192, 1048576, 2097152, 4194304, 8388608):
+        for v in (0, 1, 2, 4, 8, 16, 32, 64, 127, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 131072, 262144, 524288, 524288 + 8192, 1048576, 2097152, 4194304, 8388608, 16777216):
             os.environ["EPPM_VARIANT"] = str(v)
             ctx = E.EppmContext(h, w, 2)
             if v == 0:
