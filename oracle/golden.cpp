@@ -58,6 +58,7 @@ struct golden_ctx {
     std::vector<Level> lv;
     std::vector<S2> nnf[2], rng_init, rng_search;
     std::vector<float> cost[2];
+    std::vector<float> scale, rng_init_scale, rng_search_scale;   // baoCudaPatchMatch_Scaled only (patchmatch_scaled)
     float G[PATCH_R + 1], census_lut[9], wmf_g[5], blf_g[11];
 };
 
@@ -234,12 +235,18 @@ inline uint32_t xw_next(Xorwow& s) {
 
 // Random tables: d_setup_randgen + d_gen_rand_field (bao_pmflow_kernel.cu:50-109) and the draws of d_update_random_guess
 // (:1537-1551); one stream per 16x16 block id, same for both directions and every pair.
+// patch scale of the scaled PatchMatch from the SECOND draw of a pixel: float((10 + ((rdn2 % PM_SCALE_RANGE) - PM_SCALE_MIN)) / float(10.0f))
+// in unsigned arithmetic (bao_pmflow_kernel.cu:138, :1631; defs.h:40-41: 9 and 4) = (r % 9 + 6) / 10 in [0.6, 1.4]
+inline float scale_of_draw(uint32_t r2) { return (float)(r2 % 9u + 6u) / 10.0f; }
+
 void build_rng(golden_ctx* c) {
     const Level& L = c->lv[c->n_levels - 1];
     const int gx = (L.w + 15) / 16, gy = (L.h + 15) / 16;
     const size_t n = (size_t)L.w * L.h;
     c->rng_init.assign(n, S2{0, 0});
     c->rng_search.assign(n * c->num_iter * c->num_guess, S2{0, 0});
+    c->rng_init_scale.assign(n, 0.f);
+    c->rng_search_scale.assign(n * c->num_iter * c->num_guess, 0.f);
     for (int bid = 0; bid < gx * gy; bid++) {
         Xorwow st = xw_init(1234ull, (unsigned long long)bid);
         const int bx = bid % gx, by = bid / gx;
@@ -247,7 +254,10 @@ void build_rng(golden_ctx* c) {
             for (int j = 0; j < 16; j++) {
                 const uint32_t r1 = xw_next(st), r2 = xw_next(st);
                 const int x = bx * 16 + j, y = by * 16 + i;
-                if (x < L.w && y < L.h) c->rng_init[(size_t)y * L.w + x] = S2{(int16_t)(r1 % (uint32_t)(L.w + 1)), (int16_t)(r2 % (uint32_t)(L.h + 1))};
+                if (x < L.w && y < L.h) {
+                    c->rng_init[(size_t)y * L.w + x] = S2{(int16_t)(r1 % (uint32_t)(L.w + 1)), (int16_t)(r2 % (uint32_t)(L.h + 1))};
+                    c->rng_init_scale[(size_t)y * L.w + x] = scale_of_draw(r2);
+                }
             }
         for (int it = 0; it < c->num_iter; it++)
             for (int k = 0; k < c->num_guess; k++)
@@ -255,7 +265,10 @@ void build_rng(golden_ctx* c) {
                     for (int j = 0; j < 16; j++) {
                         const uint32_t r1 = xw_next(st), r2 = xw_next(st);
                         const int x = bx * 16 + j, y = by * 16 + i;
-                        if (x < L.w && y < L.h) c->rng_search[((size_t)(it * c->num_guess + k) * L.h + y) * L.w + x] = S2{(int16_t)r1, (int16_t)r2};
+                        if (x < L.w && y < L.h) {
+                            c->rng_search[((size_t)(it * c->num_guess + k) * L.h + y) * L.w + x] = S2{(int16_t)r1, (int16_t)r2};
+                            c->rng_search_scale[((size_t)(it * c->num_guess + k) * L.h + y) * L.w + x] = scale_of_draw(r2);
+                        }
                     }
     }
 }
@@ -411,6 +424,102 @@ void patchmatch(golden_ctx* c, int n_steps) {
 }
 
 // ------------------------------------------------------------------------------------------------ consistency
+// ------------------------------------------------------------------------------------------------ scaled PatchMatch
+// baoCudaPatchMatch_Scaled (bao_pmflow_kernel.cu:1828-1895): forward direction over (target, patch scale).  Unfinished upstream and restated AS
+// IT STANDS: _d_compute_patch_dist_scaled (:588-634) is the bilateral AD term alone (census lines commented out), image-2 samples at
+// (x2 + float(j)*scale, y2 + float(i)*scale) -- contracted by nvcc to fma(scale, float(j), float(x2)) -- through a point-filtered clamped
+// fetch; d_row_propagate_seg_scaled stores the winning candidate's SCALE into the cost plane (:1207); nothing may be skipped.
+float patch_cost_scaled(const golden_ctx* c, const Level& L, int x1, int y1, int x2, int y2, float scale) {
+    const F3 c1 = L.C(0, x1, y1), c2 = L.C(1, x2, y2);
+    const float neg = -(0.1f * 0.1f);
+    float cs = 0.f, ws = 0.f;
+    for (int i = -PATCH_R; i <= PATCH_R; i += 2)
+        for (int j = -PATCH_R; j <= PATCH_R; j += 2) {
+            const int sx = (int)floorf(fmaf(scale, (float)j, (float)x2)), sy = (int)floorf(fmaf(scale, (float)i, (float)y2));
+            const F3 p1 = L.C(0, x1 + j, y1 + i), p2 = L.C(1, sx, sy);
+            const float cc = max3abs(p1, p2);
+            const float cost = 1.0f - expf_dev((cc * cc) / neg);                                   // :610-611
+            const float d1 = max3abs(c1, p1), d2 = max3abs(c2, p2);
+            const float w = expf_dev(fmaf(d1, d1, d2 * d2) / neg) * (c->G[abs(j)] * c->G[abs(i)]);  // :613-618
+            cs = fmaf(cost, w, cs);
+            ws = ws + w;
+        }
+    return cs / ws;
+}
+
+void patchmatch_scaled(golden_ctx* c) {
+    const Level& L = c->lv[c->n_levels - 1];
+    const size_t n = (size_t)L.w * L.h;
+    std::vector<S2>& nnf = c->nnf[0];
+    std::vector<float>& cost = c->cost[0];
+    std::vector<float>& scl = c->scale;
+    nnf = c->rng_init;            // baoGenerateRandomField_Scaled (:167-178)
+    scl = c->rng_init_scale;
+    cost.resize(n);
+    for (int y = 0; y < L.h; y++)  // baoComputeCostField_Scaled (:647-656)
+        for (int x = 0; x < L.w; x++) {
+            const size_t id = (size_t)y * L.w + x;
+            cost[id] = patch_cost_scaled(c, L, x, y, nnf[id].x, nnf[id].y, scl[id]);
+        }
+    const int sl = c->seg_len;
+    for (int it = 0; it < c->num_iter; it++) {
+        for (int pass = 0; pass < 4; pass++) {   // baoSegPropagate_Scaled (:1318-1331): row, column, row reverse, column reverse; lock-step like pm_propagate
+            const bool row = (pass == 0 || pass == 2), fwd = pass < 2;
+            const int n_line = row ? L.h : L.w, len = row ? L.w : L.h;
+            const int n_seg = (len + sl - 1) / sl;
+            std::vector<S2> prev((size_t)n_line * n_seg);
+            std::vector<float> prev_s((size_t)n_line * n_seg);
+            std::vector<int> start((size_t)n_seg), steps((size_t)n_seg);
+            for (int s = 0; s < n_seg; s++) {
+                if (fwd) { start[s] = s == 0 ? 0 : s * sl - 1; steps[s] = (len - 1 < start[s] + sl ? len - 1 : start[s] + sl) - start[s]; }   // :1189-1192
+                else { start[s] = (s + 1) * sl >= len ? len - 1 : (s + 1) * sl; steps[s] = start[s] - s * sl; }                               // :1225-1227
+            }
+            auto idx = [&](int line, int i) -> size_t { return row ? (size_t)line * L.w + i : (size_t)i * L.w + line; };
+            for (int line = 0; line < n_line; line++)
+                for (int s = 0; s < n_seg; s++) {
+                    prev[(size_t)line * n_seg + s] = nnf[idx(line, start[s])];
+                    prev_s[(size_t)line * n_seg + s] = scl[idx(line, start[s])];
+                }
+            for (int t = 1; t <= sl; t++)
+                for (int line = 0; line < n_line; line++)
+                    for (int s = 0; s < n_seg; s++) {
+                        if (t > steps[s]) continue;
+                        const int i = fwd ? start[s] + t : start[s] - t;
+                        S2& p = prev[(size_t)line * n_seg + s];
+                        float& ps = prev_s[(size_t)line * n_seg + s];
+                        if (pass == 0) p.x = (int16_t)(p.x + 1 < L.w - 1 ? p.x + 1 : L.w - 1);
+                        if (pass == 1) p.y = (int16_t)(p.y + 1 < L.h - 1 ? p.y + 1 : L.h - 1);
+                        if (pass == 2) p.x = (int16_t)(p.x - 1 > 0 ? p.x - 1 : 0);
+                        if (pass == 3) p.y = (int16_t)(p.y - 1 > 0 ? p.y - 1 : 0);
+                        const size_t id = idx(line, i);
+                        const float cv = patch_cost_scaled(c, L, row ? i : line, row ? line : i, p.x, p.y, ps);
+                        if (cv < cost[id]) { nnf[id] = p; scl[id] = ps; cost[id] = pass == 0 ? ps : cv; }   // :1207: the forward row pass stores the scale
+                        else { p = nnf[id]; ps = scl[id]; }
+                    }
+        }
+        for (int y = 0; y < L.h; y++)   // d_update_random_guess_scaled (:1596-1671)
+            for (int x = 0; x < L.w; x++) {
+                const size_t id = (size_t)y * L.w + x;
+                S2 best = nnf[id];
+                const S2 entry = best;
+                float best_s = scl[id], best_cost = cost[id];
+                int mag = c->search_range;
+                for (int k = 0; k < c->num_guess; k++) {
+                    const S2 rr = c->rng_search[(size_t)(it * c->num_guess + k) * n + id];
+                    const float gs = c->rng_search_scale[(size_t)(it * c->num_guess + k) * n + id];
+                    const uint32_t r1 = (uint32_t)(int32_t)rr.x, r2 = (uint32_t)(int32_t)rr.y;
+                    const int16_t xmin = (int16_t)(entry.x - mag > 0 ? entry.x - mag : 0), xmax = (int16_t)(entry.x + mag + 1 < L.w + 1 ? entry.x + mag + 1 : L.w + 1);
+                    const int16_t ymin = (int16_t)(entry.y - mag > 0 ? entry.y - mag : 0), ymax = (int16_t)(entry.y + mag + 1 < L.h + 1 ? entry.y + mag + 1 : L.h + 1);
+                    const int16_t gx = (int16_t)(xmin + r1 % (uint32_t)(xmax - xmin)), gy = (int16_t)(ymin + r2 % (uint32_t)(ymax - ymin));
+                    if (mag / 2 >= c->radius_min) mag /= 2;
+                    const float cv = patch_cost_scaled(c, L, x, y, gx, gy, gs);
+                    if (cv < best_cost) { best = S2{gx, gy}; best_s = gs; best_cost = cv; }
+                }
+                nnf[id] = best; scl[id] = best_s; cost[id] = best_cost;
+            }
+    }
+}
+
 void lr_check(golden_ctx* c, int dir) {  // d_left_right_check (bao_pmflow_refine_kernel.cu:53-76)
     const Level& L = c->lv[c->n_levels - 1];
     for (int y = 0; y < L.h; y++)
@@ -632,6 +741,7 @@ void golden_level_dims(const golden_ctx* c, int level, int* h, int* w) { *h = c-
 
 void golden_prepare(golden_ctx* c, const uint8_t* rgb1, const uint8_t* rgb2) { prepare(c, rgb1, rgb2); }
 void golden_patchmatch(golden_ctx* c, int n_steps) { patchmatch(c, n_steps); }
+void golden_patchmatch_scaled(golden_ctx* c) { patchmatch_scaled(c); }   // forward field in planes nnf_fwd / cost_fwd, scales in plane 9
 void golden_consistency(golden_ctx* c) { consistency(c); }
 void golden_c2f(golden_ctx* c, float* flow_uv) {
     for (int l = c->n_levels - 2; l >= 0; l--) {  // bao_flow_patchmatch_multiscale_cuda.cpp:275-282
@@ -658,6 +768,7 @@ long golden_read_plane(golden_ctx* c, int which, int level, void* out) {
     case 4: case 5: if (c->nnf[which - 4].size() != nc) return -1; memcpy(out, c->nnf[which - 4].data(), nc * 4); return (long)nc * 4;
     case 6: case 7: if (c->cost[which - 6].size() != nc) return -1; memcpy(out, c->cost[which - 6].data(), nc * 4); return (long)nc * 4;
     case 8: if (L.flow.size() != n) return -1; memcpy(out, L.flow.data(), n * 8); return (long)n * 8;
+    case 9: if (c->scale.size() != nc) return -1; memcpy(out, c->scale.data(), nc * 4); return (long)nc * 4;
     }
     return -1;
 }

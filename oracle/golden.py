@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libeppm_golden.so")
 _lib = None
 
-PLANES = {"rgba1": 0, "rgba2": 1, "census1": 2, "census2": 3, "nnf_fwd": 4, "nnf_bwd": 5, "cost_fwd": 6, "cost_bwd": 7, "flow": 8}
+PLANES = {"rgba1": 0, "rgba2": 1, "census1": 2, "census2": 3, "nnf_fwd": 4, "nnf_bwd": 5, "cost_fwd": 6, "cost_bwd": 7, "flow": 8, "scale": 9}
 
 
 def lib():
@@ -27,6 +27,7 @@ def lib():
         l.golden_level_dims.argtypes = [P, I, C.POINTER(I), C.POINTER(I)]
         l.golden_prepare.argtypes = [P, P, P]
         l.golden_patchmatch.argtypes = [P, I]
+        l.golden_patchmatch_scaled.argtypes = [P]
         l.golden_consistency.argtypes = [P]
         l.golden_c2f.argtypes = [P, P]
         l.golden_compute.argtypes = [P, P, P, P]
@@ -150,6 +151,10 @@ class Golden:
         self.l.golden_patchmatch(self.ctx, n_steps)
         self.l.golden_set_pf_cost(self.ctx, 0)
 
+    def patchmatch_scaled(self):
+        """baoCudaPatchMatch_Scaled (bao_pmflow_kernel.cu:1828-1895), forward direction: planes nnf_fwd, cost_fwd and scale."""
+        self.l.golden_patchmatch_scaled(self.ctx)
+
     def consistency(self):
         self.l.golden_consistency(self.ctx)
 
@@ -166,10 +171,10 @@ class Golden:
 
     def _shape(self, which, level):
         h, w = self.level_dims(level)
-        if 4 <= which <= 7:
+        if 4 <= which <= 7 or which == 9:
             h, w = self.level_dims(self.num_levels - 1)
         return {0: ((h, w, 4), np.uint8), 1: ((h, w, 4), np.uint8), 2: ((h, w), np.uint8), 3: ((h, w), np.uint8), 4: ((h, w, 2), np.int16),
-                5: ((h, w, 2), np.int16), 6: ((h, w), np.float32), 7: ((h, w), np.float32), 8: ((h, w, 2), np.float32)}[which]
+                5: ((h, w, 2), np.int16), 6: ((h, w), np.float32), 7: ((h, w), np.float32), 8: ((h, w, 2), np.float32), 9: ((h, w), np.float32)}[which]
 
     def plane(self, name, level=0):
         which = PLANES[name]

@@ -229,6 +229,24 @@ def test_oracle_uncalled_stage_functions_against_reference_fixture(golden, path)
         assert np.abs(cg[same] - z["pf_cost"][same]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "refscaled_*.npz"))))
+def test_oracle_scaled_patchmatch_against_reference_fixture(golden, path):
+    """oracle/golden.cpp patchmatch_scaled (baoCudaPatchMatch_Scaled restated with its quirks: AD-only cost, scale from the second draw, the
+    forward row pass storing the scale into the cost plane) against the reference build's output (tools/gen_golden_scaled.py).  Targets and
+    scales are discrete: measured identical on both fixtures; the bound leaves room for an exp2f-vs-MUFU.EX2 near-tie that propagates."""
+    z = np.load(path)
+    h, w = int(z["h"]), int(z["w"])
+    a, b, _, _ = synth.make_pair(h, w, int(z["pair_idx"]), scale_to=float(z["scale_to"]))
+    g = golden.Golden(h, w)
+    g.prepare(a, b)
+    assert np.array_equal(g.plane("rgba1", 2), z["rgba1_L2"]) and np.array_equal(g.plane("rgba2", 2), z["rgba2_L2"])
+    g.patchmatch_scaled()
+    same = (g.plane("nnf_fwd") == z["sc_nnf"]).all(-1) & (g.plane("scale") == z["sc_scale"])
+    assert same.mean() >= 0.99, same.mean()
+    assert np.abs(g.plane("cost_fwd")[same] - z["sc_cost"][same]).max() <= 1e-5
+    assert np.array_equal(np.unique(z["sc_scale"]), (np.arange(6, 15, dtype=np.float32) / np.float32(10.0)))   # (r % 9 + 6) / 10
+
+
 def test_oracle_stage_injection_is_deterministic(golden):
     """LR check / outlier removal / hole filling / NNF->flow given the reference's own PatchMatch output.  The backward field after
     the LR check is deterministic in the reference and must match bit for bit.  In the forward field, pixels that survive the

@@ -351,6 +351,23 @@ def test_patchmatch_scaled_bit_exact(ref, mine, chain):
     assert (outs["ref"][0] != nf.cpu().numpy()).any()   # and it is not the plain PatchMatch
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "refscaled_*.npz"))))
+def test_patchmatch_scaled_against_committed_reference_fixture(mine, path):
+    """baoCudaPatchMatch_Scaled against the reference build's output committed under tests/golden (tools/gen_golden_scaled.py): targets, scales and
+    cost plane bit-exact; runs without oracle/_ref.  The census planes are passed as NULL: the scaled cost never reads them."""
+    z = np.load(path)
+    S, I, V = C.c_size_t, C.c_int, C.c_void_p
+    mine.baoCudaPatchMatch_Scaled.argtypes = [V] * 7 + [I, I, S, S, S, S, S]; mine.baoCudaPatchMatch_Scaled.restype = None
+    hc, wc = z["rgba1_L2"].shape[:2]
+    i1, pitch = refharness.pitched(z["rgba1_L2"]); i2, _ = refharness.pitched(z["rgba2_L2"])
+    nn = torch.zeros((hc, wc, 2), dtype=torch.int16, device="cuda")
+    sc = torch.zeros((hc, wc), dtype=torch.float32, device="cuda"); co = torch.zeros((hc, wc), dtype=torch.float32, device="cuda")
+    mine.baoCudaPatchMatch_Scaled(P(nn), P(sc), P(co), P(i1), P(i2), None, None, wc, hc, pitch, wc * 4, wc * 4, wc * 4, 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(nn.cpu().numpy(), z["sc_nnf"]), f"{(nn.cpu().numpy() != z['sc_nnf']).any(-1).sum()} targets differ"
+    assert same_bits(sc.cpu().numpy(), z["sc_scale"]) and same_bits(co.cpu().numpy(), z["sc_cost"])
+
+
 @needs_ref
 def test_subpixel_refine_and_bicubic_census_vs_reference(mine, chain, tmp_path):
     """baoCudaCensusTransform_Bicubic + baoCudaSubpixRefine (declared by the reference's host class, not called by
