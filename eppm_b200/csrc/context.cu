@@ -255,6 +255,11 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
     }
     c->vol_ok = p.patch_stride == 2 && build_vol_tab(c->vol_tab);
     for (int l = 0; l + 1 < c->n_levels; l++) c->aff_ok[l] = build_affine_tab(c->aff_tab[l], c->lv[l].pw, c->lv[l].w, c->lv[l].h, p.patch_stride, true);
+    for (int l = 0; l + 1 < c->n_levels; l++) {   // spatial weights by sample index (stride-2 sample order: i outer, j inner)
+        int s2 = 0;
+        for (int i = -PATCH_R; i <= PATCH_R; i += 2)
+            for (int j = -PATCH_R; j <= PATCH_R; j += 2, s2++) c->aff_tab[l].gs[s2] = c->cost_lut.gg[i < 0 ? -i : i][j < 0 ? -j : j];
+    }
     build_gauss_tables(c);
     // the random tables are expanded on the first PatchMatch of the context (ensure_rng_tables): the legacy stage functions create
     // contexts for levels that never run PatchMatch

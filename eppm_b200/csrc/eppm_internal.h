@@ -73,6 +73,7 @@ struct AffineTab {
     int exc_s;         // sample index of that site, -1 = none
     int exc_q;         // its model (0..2)
     float exc_cj, exc_ci;
+    float gs[100];     // stride 2: spatial weight G[|j|] * G[|i|] of sample s (CostLut::gg by sample index: one constant load, no index arithmetic)
 };
 
 // Shared AD + census volume of the refine kernel (k_c2f_refine_vol, stride 2).  The AD + census half of a patch sample depends only on the

@@ -382,7 +382,7 @@ EPPM_PRAGMA(unroll RF_JUNROLL)
             const float4 p1 = TILE ? tile[((i + PATCH_R) / STRIDE) * RF_TILE_W + (j + PATCH_R)] : ldpix(a0 + irow + j);
             const PixPk p1k = pack_pix(p1);
             const float d1 = max3abs_diff(c1k, p1k);
-            const float gg = lut.gg[ai][j < 0 ? -j : j];
+            const float gg = (STRIDE == 2 && TILE) ? tab.gs[s] : lut.gg[ai][j < 0 ? -j : j];
             int off[4];
             off[0] = irow + j;  // identity model: the exact integer site (cx + j, cy + i)
 #pragma unroll
@@ -506,9 +506,10 @@ __global__ void __launch_bounds__(RF_PIX * 3, MINB)
 #pragma unroll
                 for (int q = 0; q < 4; q++)
                     if (valid[m]) lo = fminf(lo, fminf(cs[m][q], ws[m][q]));
-            if (__all_sync(any_mask, lo >= 1.57772181e-30f))   // 2^-99; any_mask: lanes outside this branch (image border, unknown flow) do not vote
-                refine_row_loop<STRIDE, true, Lut0, true, false>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl, -PATCH_R + STRIDE, PATCH_R);
-            else
+            if (__all_sync(any_mask, lo >= 1.57772181e-30f)) {   // 2^-99; any_mask: lanes outside this branch (image border, unknown flow) do not vote
+                if (warp_all) refine_row_loop<STRIDE, false, Lut0, true, false>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl, -PATCH_R + STRIDE, PATCH_R);
+                else refine_row_loop<STRIDE, true, Lut0, true, false>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl, -PATCH_R + STRIDE, PATCH_R);
+            } else
                 refine_row_loop<STRIDE, true, Lut0, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl, -PATCH_R + STRIDE, PATCH_R);
         } else if (TMA1) {
             refine_row_loop<STRIDE, true, Lut0, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl);
@@ -1368,16 +1369,16 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                 else if (v & EPPM_VAR_REFINE_PK_BRANCH) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, false><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else if (v & EPPM_VAR_REFINE_PK) k_c2f_refine_pk<RF_PK_MINBLOCKS, 2, true><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp);
                 else {
-                    // Default (mode 19): warp = candidate row, census table at the shared-window base, the CTA's image-1 samples staged in shared memory by ONE
+                    // Default (mode 23): warp = candidate row, census table at the shared-window base, the CTA's image-1 samples staged in shared memory by ONE
                     // TMA copy (50 pixels x every second of 19 rows; 7.75 ms per 1080p pair at level 0 against 7.85 for mode 10, which reads them through L1), and the
                     // __expf fix-up test dropped behind an exact first patch row where that provably changes no bit (FASTW: 7.75 -> 7.54).  Measured per 1080p pair at level 0 (round 2,
                     // tools/variant_times.py, 16 pairs): column kernel 8.28 ms; its knobs allrows 9.72, wide address 8.78, 6 CTAs 8.54; row kernel
                     // 8.06-8.12, + fixed-address census table 7.85, + guard-free loop for interior warps 7.92 (spills), warp-uniform guards (mode 16) 7.88,
                     // census table indexed by the XOR byte instead of POPC (modes 12-15: plain 7.94, replicated x8 / x16 / x32 8.23 / 8.27 / 12.3).
                     // Tuning knob EPPM_REFINE_MODE: 0-7 = column kernel with allrows + 2 * wide + 4 * (6 CTAs per SM), 8-11 = row kernel + 2 * table at base + guard-free
-                    static const int mode = getenv("EPPM_REFINE_MODE") ? atoi(getenv("EPPM_REFINE_MODE")) : 19;
+                    static const int mode = getenv("EPPM_REFINE_MODE") ? atoi(getenv("EPPM_REFINE_MODE")) : 23;
                     static const CUtensorMap dummy_map = {};
-                    const int md = (v & EPPM_VAR_REFINE_COLUMN) ? 0 : (v & EPPM_VAR_REFINE_VOLUME) ? 20 : (mode == 19 && (v & EPPM_VAR_REFINE_NOFASTW)) ? 18 : mode;
+                    const int md = (v & EPPM_VAR_REFINE_COLUMN) ? 0 : (v & EPPM_VAR_REFINE_VOLUME) ? 20 : ((mode == 19 || mode == 23) && (v & EPPM_VAR_REFINE_NOFASTW)) ? 18 : mode;
 #define EPPM_RT(MB, AR, WD) k_c2f_refine_tab<true, 3, MB, 2, AR, WD><<<grd, blk, 0, c->stream>>>(a, c->cost_lut, *tabp)
                     switch (md) {
 #define EPPM_RR(L0, FP) k_c2f_refine_row<7, 2, L0, FP><<<grd, blk, (16 + 9 * RF_PIX) * sizeof(float), c->stream>>>(a, c->cost_lut, *tabp, dummy_map)
@@ -1402,13 +1403,15 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                         }
                     }
                     // fall through
-                    case 19:     // default: mode 18 + fix-up-free loop behind an exact first patch row (FASTW)
+                    case 23:     // default: mode 19 + no validity guards in the fix-up-free loop of warps whose 96 candidates are all valid (7.54 -> 7.37 ms)
+                    case 19:     // mode 18 + fix-up-free loop behind an exact first patch row (FASTW)
                     case 18: {   // image-1 tile staged by TMA (needs the level's refine tensor map and the table-at-base addressing); else mode 10
                         int lvl = -1;
                         for (int l = 0; l < c->n_levels; l++)
                             if (pix1 == c->pix[0][l] && c->tmap_refine_ok[l]) lvl = l;
                         if (lvl >= 0 && lut0_window_base_ok(c->device)) {
-                            if (md == 19) k_c2f_refine_row<7, 2, true, false, 0, 0, true, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
+                            if (md == 23) k_c2f_refine_row<7, 2, true, true, 0, 0, true, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
+                            else if (md == 19) k_c2f_refine_row<7, 2, true, false, 0, 0, true, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
                             else k_c2f_refine_row<7, 2, true, false, 0, 0, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
                             break;
                         }
