@@ -258,7 +258,11 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
     for (int l = 0; l + 1 < c->n_levels; l++) {   // spatial weights by sample index (stride-2 sample order: i outer, j inner)
         int s2 = 0;
         for (int i = -PATCH_R; i <= PATCH_R; i += 2)
-            for (int j = -PATCH_R; j <= PATCH_R; j += 2, s2++) c->aff_tab[l].gs[s2] = c->cost_lut.gg[i < 0 ? -i : i][j < 0 ? -j : j];
+            for (int j = -PATCH_R; j <= PATCH_R; j += 2, s2++) {
+                c->aff_tab[l].gs[s2] = c->cost_lut.gg[i < 0 ? -i : i][j < 0 ? -j : j];
+                c->aff_tab[l].boff[0][s2] = ((long long)i * c->lv[l].pw + j) * (long long)sizeof(float4);
+                for (int q = 0; q < 3; q++) c->aff_tab[l].boff[q + 1][s2] = (long long)c->aff_tab[l].off[q][s2] * (long long)sizeof(float4);
+            }
     }
     build_gauss_tables(c);
     // the random tables are expanded on the first PatchMatch of the context (ensure_rng_tables): the legacy stage functions create

@@ -73,6 +73,7 @@ struct AffineTab {
     int exc_s;         // sample index of that site, -1 = none
     int exc_q;         // its model (0..2)
     float exc_cj, exc_ci;
+    long long boff[4][100];   // stride 2: BYTE offset of the site of model 0..3 (0 = identity) at sample s: the 64-bit add takes it straight from the constant bank
     float gs[100];     // stride 2: spatial weight G[|j|] * G[|i|] of sample s (CostLut::gg by sample index: one constant load, no index arithmetic)
 };
 

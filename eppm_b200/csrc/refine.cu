@@ -389,7 +389,8 @@ EPPM_PRAGMA(unroll RF_JUNROLL)
             for (int q = 0; q < 3; q++) off[q + 1] = tab.off[q][s];
             const float4* site[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) site[q] = pix_at(Pc, off[q]);
+            for (int q = 0; q < 4; q++)
+                site[q] = (STRIDE == 2 && TILE) ? reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Pc) + tab.boff[q][s]) : pix_at(Pc, off[q]);
 #pragma unroll
             for (int m = 0; m < 3; m++) {
                 if (CHECK && !valid[m]) continue;
