@@ -221,6 +221,9 @@ __device__ __forceinline__ const float4* pix_at_b(const float4* base, int off, i
 #ifndef RF_JUNROLL
 #define RF_JUNROLL 2   // samples of a patch row handled per iteration of the inner loop (tuning knob)
 #endif
+#ifndef RF_ROW_JUNROLL
+#define RF_ROW_JUNROLL 1   // the same for k_c2f_refine_row (default kernel)
+#endif
 #define EPPM_PRAGMA_(x) _Pragma(#x)
 #define EPPM_PRAGMA(x) EPPM_PRAGMA_(x)
 template <bool GROUP_TINY, int NCT, int MINB, int STRIDE, bool ALLROWS = false, bool WIDE = false>
@@ -376,7 +379,9 @@ __device__ __forceinline__ void refine_row_loop(const RefineArgs& a, const CostL
     for (int i = i_lo; i <= i_hi; i += STRIDE) {
         const int ai = i < 0 ? -i : i;
         const int irow = i * a.pw;
-EPPM_PRAGMA(unroll RF_JUNROLL)
+        // one sample per iteration: the kernel is sensitive to its instruction footprint (measured at level 0: 1: 7.12, 2: 7.16, 5: 8.92, 10: 10.95 ms per pair);
+        // hoisting the tile row pointer by hand (7.20) or dropping the scheduling fence below in the guard-free loop (7.43) did not help
+EPPM_PRAGMA(unroll RF_ROW_JUNROLL)
         for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE, s++) {
             // TILE: the image-1 samples of the CTA's 32 pixels (every second row of a (32 + 18)-pixel strip) were staged in shared memory by TMA
             const float4 p1 = TILE ? tile[((i + PATCH_R) / STRIDE) * RF_TILE_W + (j + PATCH_R)] : ldpix(a0 + irow + j);

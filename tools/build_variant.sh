@@ -7,9 +7,9 @@ root=$(cd "$(dirname "$0")/.." && pwd)
 obj=$root/build/ab/obj_$name
 mkdir -p $obj
 cd $root/eppm_b200/csrc
-for f in context prepare patchmatch consistency refine legacy_abi subpix bao_class; do
+for f in context prepare patchmatch consistency refine legacy_abi legacy_inplace eval tiled subpix bao_class; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v $extra -I../../include -c $f.cu -o $obj/$f.o 2> $obj/$f.ptxas.log &
 done
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -Xlinker -Bsymbolic -o $root/build/ab/libeppm_b200_$name.so $obj/*.o 2>/dev/null
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -Xlinker -Bsymbolic -o $root/build/ab/libeppm_b200_$name.so $obj/*.o -ldl 2>/dev/null
 echo built build/ab/libeppm_b200_$name.so
