@@ -401,7 +401,7 @@ EPPM_PRAGMA(unroll RF_ROW_JUNROLL)
                 if (CHECK && !valid[m]) continue;
                 // CHECK = false: wmask is warp-uniform and all ones; the (uniform, never divergent) test keeps the three candidates in separate
                 // basic blocks -- scheduled as one block they need more registers than the kernel has
-                if (!CHECK && !(wmask & (1u << m))) continue;
+                if (!CHECK && !(wmask & (1u << m))) continue;   // (a __syncwarp() as the fence instead: 7.50 vs 7.17 ms per pair at level 0)
                 float ct[4], t2[4], w[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++) sample_eval(p1, p1k, ldpix(site[q] + (m - 1)), c2k[m], d1, lut_ref, ct[q], t2[q]);
@@ -505,7 +505,9 @@ __global__ void __launch_bounds__(RF_PIX * 3, MINB)
 #pragma unroll
         for (int m = 0; m < 3; m++) c2k[m] = pack_pix(ldpix(Pc + (m - 1)));
         if (TMA1 && FASTW) {
-            refine_row_loop<STRIDE, true, Lut0, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl, -PATCH_R, -PATCH_R);
+            // the exact first row, without validity guards in warps whose 96 candidates are all valid (7.17 -> 7.06 ms per pair at level 0)
+            if (warp_all) refine_row_loop<STRIDE, false, Lut0, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl, -PATCH_R, -PATCH_R);
+            else refine_row_loop<STRIDE, true, Lut0, true>(a, lut, tab, a0, Pc, c1k, c2k, valid, wmask, Lut0(), cs, ws, s_tile + pl, -PATCH_R, -PATCH_R);
             float lo = FLT_MAX;   // smallest accumulator among the valid candidates of this lane after the first row
 #pragma unroll
             for (int m = 0; m < 3; m++)
