@@ -1132,7 +1132,12 @@ __global__ void __launch_bounds__(MINB >= 4 ? 128 : 256, MINB) k_pm_search_joint
         for (int i = -PATCH_R; i <= PATCH_R; i += STRIDE) {
             const int ai = i < 0 ? -i : i;
             const unsigned irow = (unsigned)(i * a.pw);
-#pragma unroll 2
+#ifndef PM_SEARCH_JUNROLL
+#define PM_SEARCH_JUNROLL 1   // samples of a patch row per iteration (tuning knob; PatchMatch per pair: 1: 4.001, 2: 4.012, 5: 4.033 ms)
+#endif
+#define PM_PRAGMA_(x) _Pragma(#x)
+#define PM_PRAGMA(x) PM_PRAGMA_(x)
+PM_PRAGMA(unroll PM_SEARCH_JUNROLL)
             for (int j = -PATCH_R; j <= PATCH_R; j += STRIDE) {
                 const unsigned off = irow + (unsigned)j;
                 const float4 p1 = ldpix(A + (oa + off));

@@ -221,6 +221,9 @@ __device__ __forceinline__ const float4* pix_at_b(const float4* base, int off, i
 #ifndef RF_JUNROLL
 #define RF_JUNROLL 2   // samples of a patch row handled per iteration of the inner loop (tuning knob)
 #endif
+#ifndef S4_UNROLL
+#define S4_UNROLL 7     // taps of a tile row per iteration of k_flow_smooth4 (tuning knob; final smoothing per pair: 1: 0.577, 3: 0.515, 7: 0.507 ms)
+#endif
 #ifndef RF_ROW_JUNROLL
 #define RF_ROW_JUNROLL 1   // the same for k_c2f_refine_row (default kernel)
 #endif
@@ -401,7 +404,10 @@ EPPM_PRAGMA(unroll RF_ROW_JUNROLL)
                 if (CHECK && !valid[m]) continue;
                 // CHECK = false: wmask is warp-uniform and all ones; the (uniform, never divergent) test keeps the three candidates in separate
                 // basic blocks -- scheduled as one block they need more registers than the kernel has
-                if (!CHECK && !(wmask & (1u << m))) continue;   // (a __syncwarp() as the fence instead: 7.50 vs 7.17 ms per pair at level 0)
+#ifndef RF_FENCE_FROM
+#define RF_FENCE_FROM 0
+#endif
+                if (!CHECK && m >= RF_FENCE_FROM && !(wmask & (1u << m))) continue;   // (a __syncwarp() as the fence instead: 7.50 vs 7.17 ms per pair at level 0)
                 float ct[4], t2[4], w[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++) sample_eval(p1, p1k, ldpix(site[q] + (m - 1)), c2k[m], d1, lut_ref, ct[q], t2[q]);
@@ -1280,7 +1286,7 @@ __global__ void __launch_bounds__(S4_TX* S4_TY) k_flow_smooth4(SmoothArgs a, con
         const float2* g0 = s_gg + t * (R + 1);
         const float2* g1 = s_gg + (S4_ROWS + t) * (R + 1);
         if (t >= 2 && t <= 2 * R + 1) {
-#pragma unroll 3
+EPPM_PRAGMA(unroll S4_UNROLL)
             for (int dx = -R; dx <= R; dx++) {
                 const float4 p = s_pix[rowb + dx];
                 const float2 fl = s_flow[rowb + dx];
@@ -1290,13 +1296,13 @@ __global__ void __launch_bounds__(S4_TX* S4_TY) k_flow_smooth4(SmoothArgs a, con
                 smooth_tap2<FAST_DIV>(a, cx[1], cy[1], cz[1], p, fl, pk2(gb.x, gb.y), r2, nd2, nx[1], ny[1], ws[1]);
             }
         } else if (t < 2) {
-#pragma unroll 3
+EPPM_PRAGMA(unroll S4_UNROLL)
             for (int dx = -R; dx <= R; dx++) {
                 const float2 ga = g0[dx < 0 ? -dx : dx];
                 smooth_tap2<FAST_DIV>(a, cx[0], cy[0], cz[0], s_pix[rowb + dx], s_flow[rowb + dx], pk2(ga.x, ga.y), r2, nd2, nx[0], ny[0], ws[0]);
             }
         } else {
-#pragma unroll 3
+EPPM_PRAGMA(unroll S4_UNROLL)
             for (int dx = -R; dx <= R; dx++) {
                 const float2 gb = g1[dx < 0 ? -dx : dx];
                 smooth_tap2<FAST_DIV>(a, cx[1], cy[1], cz[1], s_pix[rowb + dx], s_flow[rowb + dx], pk2(gb.x, gb.y), r2, nd2, nx[1], ny[1], ws[1]);
@@ -1411,6 +1417,7 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                         }
                     }
                     // fall through
+                    case 24: case 25:   // mode 23 compiled for 8 / 6 CTAs per SM
                     case 23:     // default: mode 19 + no validity guards in the fix-up-free loop of warps whose 96 candidates are all valid (7.54 -> 7.37 ms)
                     case 19:     // mode 18 + fix-up-free loop behind an exact first patch row (FASTW)
                     case 18: {   // image-1 tile staged by TMA (needs the level's refine tensor map and the table-at-base addressing); else mode 10
@@ -1418,7 +1425,9 @@ void op_refine(eppm_context* c, const float4* pix1, const float4* pix2, const Le
                         for (int l = 0; l < c->n_levels; l++)
                             if (pix1 == c->pix[0][l] && c->tmap_refine_ok[l]) lvl = l;
                         if (lvl >= 0 && lut0_window_base_ok(c->device)) {
-                            if (md == 23) k_c2f_refine_row<7, 2, true, true, 0, 0, true, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
+                            if (md == 24) k_c2f_refine_row<8, 2, true, true, 0, 0, true, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
+                            else if (md == 25) k_c2f_refine_row<6, 2, true, true, 0, 0, true, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
+                            else if (md == 23) k_c2f_refine_row<7, 2, true, true, 0, 0, true, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
                             else if (md == 19) k_c2f_refine_row<7, 2, true, false, 0, 0, true, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
                             else k_c2f_refine_row<7, 2, true, false, 0, 0, true><<<grd, blk, 1280 + RF_TILE_W * RF_TILE_H * sizeof(float4) + 16, c->stream>>>(a, c->cost_lut, *tabp, c->tmap_refine[lvl]);
                             break;
