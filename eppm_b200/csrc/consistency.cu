@@ -150,24 +150,39 @@ __global__ void __launch_bounds__(128) k_wmf(const short2* __restrict__ src, sho
         __syncwarp();
         float best = FLT_MAX;
         int best_k = N;  // N = no candidate
-        for (int k = lane; k < N; k += 32) {
-            const short2 cand = s_d[warp][k];
-            if (cand.x == -32768) continue;
-            float cost_sum = 0.f, weight_sum = 0.f;
-#pragma unroll 9
-            for (int q = 0; q < N; q++) {
-                const short2 cur = s_d[warp][q];
-                if (cur.x == -32768) continue;
-                const float wq = s_w[warp][q];
-                const int dist = max(abs(cand.x - cur.x), abs(cand.y - cur.y));
-                cost_sum = __fmaf_rn(wq, (float)dist, cost_sum);  // :244
-                weight_sum = __fadd_rn(weight_sum, wq);
-            }
-            if (weight_sum > 0.0f && cost_sum < best) {  // lane-local scan is in increasing k: first minimum wins
-                best = cost_sum;
-                best_k = k;
-            }
+        // a lane scores its (up to) NC candidates k = lane, lane + 32, ... in ONE pass over the window: the window entry (displacement, weight) is read
+        // from shared memory once for all of them (the kernel was bound by those broadcast reads), and the weight sum -- the same for every
+        // candidate, same taps in the same order -- is formed once.  Each candidate still adds its taps in window order.
+        constexpr int NC = (N + 31) / 32;
+        short2 cand[NC];
+        bool has[NC];
+        float cost_sum[NC];
+#pragma unroll
+        for (int cI = 0; cI < NC; cI++) {
+            const int k = lane + 32 * cI;
+            cand[cI] = k < N ? s_d[warp][k] : make_short2(-32768, 0);
+            has[cI] = cand[cI].x != -32768;
+            cost_sum[cI] = 0.f;
         }
+        float weight_sum = 0.f;
+#pragma unroll 9
+        for (int q = 0; q < N; q++) {
+            const short2 cur = s_d[warp][q];
+            if (cur.x == -32768) continue;
+            const float wq = s_w[warp][q];
+#pragma unroll
+            for (int cI = 0; cI < NC; cI++) {
+                const int dist = max(abs(cand[cI].x - cur.x), abs(cand[cI].y - cur.y));
+                cost_sum[cI] = __fmaf_rn(wq, (float)dist, cost_sum[cI]);  // :244
+            }
+            weight_sum = __fadd_rn(weight_sum, wq);
+        }
+#pragma unroll
+        for (int cI = 0; cI < NC; cI++)
+            if (has[cI] && weight_sum > 0.0f && cost_sum[cI] < best) {  // lane-local scan is in increasing k: first minimum wins
+                best = cost_sum[cI];
+                best_k = lane + 32 * cI;
+            }
         // warp arg-min with the reference's order: smallest cost, ties -> smallest candidate index
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
