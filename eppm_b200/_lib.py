@@ -15,7 +15,7 @@ class EppmParams(C.Structure):
         ("lambda_ad", C.c_float), ("lambda_census", C.c_float), ("pm_sig_r", C.c_float),
         ("stat_radius", C.c_int), ("stat_sim_thresh", C.c_int), ("wmf_radius", C.c_int), ("wmf_sig_r", C.c_float),
         ("wmf_iters", C.c_int), ("blf_sig_s", C.c_int), ("blf_sig_r", C.c_float), ("rng_mode", C.c_int),
-        ("seed", C.c_ulonglong), ("inplace_filters", C.c_int), ("reserved", C.c_int * 7),
+        ("seed", C.c_ulonglong), ("inplace_filters", C.c_int), ("subpixel_final", C.c_int), ("reserved", C.c_int * 6),
     ]
 
 

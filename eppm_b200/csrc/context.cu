@@ -155,6 +155,11 @@ int eppm_create(eppm_context** out, int device, int h, int w, int max_batch, con
         delete c;
         return EPPM_ERR_ARG;
     }
+    if (p.subpixel_final && (w % 8 != 0 || p.pyr_levels < 2 || p.patch_stride != 2)) {
+        set_error("eppm_create: subpixel_final needs a frame width that is a multiple of 8 (texture pitch), at least two pyramid levels and patch stride 2");
+        delete c;
+        return EPPM_ERR_ARG;
+    }
     // bao_pyr_init_dim (basic/bao_basic.h:196-211): int(double(dim) * pow(double(0.5f), i))
     c->n_levels = p.pyr_levels;
     for (int i = 0; i < c->n_levels; i++) {
@@ -307,6 +312,9 @@ void eppm_destroy(eppm_context* c) {
     for (int img = 0; img < 2; img++)
         if (c->tex_pm[img]) cudaDestroyTextureObject(c->tex_pm[img]);
     if (c->arena.base) cudaFree(c->arena.base);
+    for (int i = 0; i < 2; i++)
+        if (c->subpix_census[i]) cudaFree(c->subpix_census[i]);
+    if (c->subpix_nnf) cudaFree(c->subpix_nnf);
     if (c->pm_arena.base) cudaFree(c->pm_arena.base);
     for (int i = 0; i < 2; i++)
         if (c->h_pinned_in[i]) cudaFreeHost(c->h_pinned_in[i]);

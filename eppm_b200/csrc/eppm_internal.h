@@ -173,6 +173,8 @@ struct eppm_context {
     int variant = 0;                             // EPPM_VARIANT bit mask (A/B switches for measurements, see EPPM_VAR_*)
     int smooth_fast_div = 0;                     // set at create time when the constant-division fast path was verified exact
     int pm_pad_kb = 0;                           // EPPM_PM_PAD_KB: dynamic shared memory (KB) the PatchMatch scoring kernels reserve without using it = residency cap (co-scheduling)
+    unsigned char* subpix_census[2] = {nullptr, nullptr};   // [2h][2w] census planes of the bicubic-upsampled images (subpixel_final; allocated on first use)
+    short2* subpix_nnf = nullptr;                           // [h][w] integer targets of one pair
     int inplace = 0;                             // eppm_params::inplace_filters or EPPM_INPLACE_LEGACY=1: the three racy filters of the reference run in place (legacy_inplace.cu)
     int rng_ready = 0;                           // rng_init / rng_search expanded (lazily, before the first PatchMatch)
 };
@@ -191,6 +193,7 @@ bool run_patchmatch_scaled(eppm_context* c, float* d_scale);   // baoCudaPatchMa
 bool run_patchmatch_planefitting(eppm_context* c);   // baoCudaPatchMatch_PlaneFitting: forward direction of pair 0, coarsest-level planes
 void run_c2f_step(eppm_context* c, int level, int kind, float2* out);
 bool build_smooth_tensor_maps(eppm_context* c);
+void op_subpix_final(eppm_context* c);   // eppm_params::subpixel_final: the reference's sub-pixel stage on flow_tmp (level 0), pair by pair (subpix.cu)
 void band_rows(const eppm_context* c, int level, int* y0, int* y1);
 void run_consistency(eppm_context* c);
 void run_c2f(eppm_context* c, float* d_flow_out);

@@ -1700,6 +1700,7 @@ void run_c2f_step(eppm_context* c, int level, int kind, float2* out) {
 void run_c2f(eppm_context* c, float* d_flow_out) {
     for (int level = c->n_levels - 2; level >= 0; level--) {
         run_c2f_step(c, level, 0, nullptr);
+        if (level == 0 && c->prm.subpixel_final) op_subpix_final(c);   // opt-in: sub-pixel offsets on the integer flow of the level-0 refine
         run_c2f_step(c, level, 1, nullptr);
     }
     // final smoothing at level 0 (…cuda.cpp:289); with a single level the loop above did not run

@@ -373,3 +373,29 @@ void baoCudaSubpixRefine(float2* d_flow, short2* d_disp_vec, uchar4* d_img1, uch
 }
 
 }  // extern "C"
+
+// eppm_params::subpixel_final (opt-in): the two stage functions above applied to the context's own level-0 planes, pair by pair, between the level-0
+// refine (integer flow in flow_tmp) and the level-0 smoothing passes.  The stage functions work on the legacy default stream and synchronise,
+// like the reference's; this path is an accuracy option, not part of the timed pipeline.
+extern "C" void baoCudaFlow2NNF(short2* d_disp_vec, float2* d_flow, int w, int h, size_t disp_pitch, size_t flow_pitch);
+namespace eppm {
+void op_subpix_final(eppm_context* c) {
+    const LevelGeom& g = c->lv[0];
+    const size_t n = (size_t)g.w * g.h;
+    if (!c->subpix_census[0]) {
+        for (int i = 0; i < 2; i++)
+            if (!cuda_ok(cudaMalloc((void**)&c->subpix_census[i], 4 * n), "cudaMalloc(subpix census)")) return;
+        if (!cuda_ok(cudaMalloc((void**)&c->subpix_nnf, n * sizeof(short2)), "cudaMalloc(subpix nnf)")) return;
+    }
+    cudaStreamSynchronize(c->stream);
+    for (int b = 0; b < c->n_cur; b++) {
+        uchar4* i1 = c->rgba[0][0] + (size_t)b * n;
+        uchar4* i2 = c->rgba[1][0] + (size_t)b * n;
+        float2* fl = c->flow_tmp + (size_t)b * n;
+        baoCudaCensusTransform_Bicubic(c->subpix_census[0], c->subpix_census[1], 2 * g.w, 2 * g.h, (size_t)2 * g.w, i1, i2, g.w, g.h, (size_t)g.w * 4);
+        baoCudaFlow2NNF(c->subpix_nnf, fl, g.w, g.h, (size_t)g.w * sizeof(short2), (size_t)g.w * sizeof(float2));
+        baoCudaSubpixRefine(fl, c->subpix_nnf, i1, i2, c->subpix_census[0], c->subpix_census[1], g.w, g.h, (size_t)g.w * 4, (size_t)2 * g.w,
+                            (size_t)g.w * sizeof(short2), (size_t)g.w * sizeof(float2));
+    }
+}
+}  // namespace eppm

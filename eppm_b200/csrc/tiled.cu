@@ -172,6 +172,7 @@ int eppm_tiled_shutdown(eppm_context* c) {
 int eppm_compute_tiled_device(eppm_context* c, const uint8_t* d_img1, const uint8_t* d_img2, float* d_flow) {
     if (!c || !d_img1 || !d_img2 || !d_flow) { set_error("eppm_compute_tiled_device: null pointer"); return EPPM_ERR_ARG; }
     if (!c->tile_comm || c->tile_world < 1) { set_error("eppm_compute_tiled_device before eppm_tiled_init"); return EPPM_ERR_STATE; }
+    if (c->prm.subpixel_final) { set_error("eppm_compute_tiled_device: subpixel_final is not combined with spatial tiling"); return EPPM_ERR_ARG; }
     int prev = -1;
     cudaGetDevice(&prev);
     if (prev != c->device) cudaSetDevice(c->device);

@@ -63,7 +63,12 @@ typedef struct eppm_params {
                                 reference's read-while-write race as far as the hardware schedules it the same way; slower, and
                                 like the reference not guaranteed reproducible across GPUs.  EPPM_INPLACE_LEGACY=1 in the
                                 environment forces 1 for every context. */
-    int reserved[7];
+    int subpixel_final;      /* 0 (default).  1: the reference's optional sub-pixel stage (baoCudaCensusTransform_Bicubic + baoCudaSubpixRefine,
+                                bao_pmflow_refine_kernel.cu:395-634 -- declared by its host class, never placed in its pipeline) runs on the
+                                integer flow of the level-0 refine, in front of the two level-0 smoothing passes, at full resolution as the
+                                reference's buffers are sized (…cuda.cpp:135-136).  Needs w % 8 == 0 (texture pitch) and >= 2 pyramid levels;
+                                costs about three times the rest of the pipeline.  Not combined with spatial tiling. */
+    int reserved[6];
 } eppm_params;
 
 typedef struct eppm_context eppm_context; /* opaque; one per (device, h, w, params) */

@@ -939,6 +939,44 @@ def test_philox_mode_epe_delta(ref):
     ref.destroy(rc); ctx.close()
 
 
+def test_subpixel_final_option(mine):
+    """eppm_params::subpixel_final: the reference's optional sub-pixel stage (baoCudaCensusTransform_Bicubic + baoCudaSubpixRefine; declared by its
+    host class, never placed in its pipeline) between the level-0 refine and the level-0 smoothing passes.  The wiring is checked exactly: the
+    stage functions applied by hand to the default context's level-0 refine output (integer flow, left in FLOW_TMP) must reproduce the option's
+    FLOW_TMP bit for bit; end to end the option must stay as accurate against ground truth as the default."""
+    h, w = 240, 320
+    a, b, gt, valid = synth.make_pair(h, w, 21, scale_to=0.2)
+    ctx0 = E.EppmContext(h, w, 1)
+    f0 = ctx0.compute_batch_host(a[None], b[None])[0].copy()
+    t0 = ctx0.read_plane(E.PLANE_FLOW_TMP, 0)
+    assert np.array_equal(t0, np.round(t0))                     # the refine leaves integer displacements
+    p = E.default_params()
+    p.subpixel_final = 1
+    ctx1 = E.EppmContext(h, w, 1, params=p)
+    f1 = ctx1.compute_batch_host(a[None], b[None])[0].copy()
+    t1 = ctx1.read_plane(E.PLANE_FLOW_TMP, 0)
+    assert np.isfinite(f1).all() and not np.array_equal(t1, t0) and not same_bits(f1, f0)
+    assert np.abs(t1 - t0).max() <= 1.5 + 1e-6                   # offsets of at most 3 half-pixels (:630)
+    # by hand, through the stage ABI, on the default context's planes
+    S, I, V = C.c_size_t, C.c_int, C.c_void_p
+    mine.baoCudaCensusTransform_Bicubic.argtypes = [V, V, I, I, S, V, V, I, I, S]; mine.baoCudaCensusTransform_Bicubic.restype = None
+    mine.baoCudaFlow2NNF.argtypes = [V, V, I, I, S, S]; mine.baoCudaFlow2NNF.restype = None
+    mine.baoCudaSubpixRefine.argtypes = [V, V, V, V, V, V, I, I, S, S, S, S]; mine.baoCudaSubpixRefine.restype = None
+    i1, i2 = dev(ctx0.read_plane(E.PLANE_RGBA1, 0)), dev(ctx0.read_plane(E.PLANE_RGBA2, 0))
+    c1 = torch.zeros((2 * h, 2 * w), dtype=torch.uint8, device="cuda"); c2 = torch.zeros_like(c1)
+    mine.baoCudaCensusTransform_Bicubic(P(c1), P(c2), 2 * w, 2 * h, 2 * w, P(i1), P(i2), w, h, w * 4)
+    fl = dev(t0); nn = torch.zeros((h, w, 2), dtype=torch.int16, device="cuda")
+    mine.baoCudaFlow2NNF(P(nn), P(fl), w, h, w * 4, w * 8)
+    mine.baoCudaSubpixRefine(P(fl), P(nn), P(i1), P(i2), P(c1), P(c2), w, h, w * 4, 2 * w, w * 4, w * 8)
+    torch.cuda.synchronize()
+    assert same_bits(fl.cpu().numpy(), t1)
+    e0, e1 = synth.epe(f0, gt, valid), synth.epe(f1, gt, valid)
+    assert e1 <= e0 + 0.05, (e0, e1)
+    with pytest.raises(E.EppmError):                             # the texture pitch needs w % 8 == 0
+        E.EppmContext(h, 324, 1, params=p)
+    ctx0.close(); ctx1.close()
+
+
 def test_variant_switches_compute_the_same_bits():
     """Every tuned kernel has its plain predecessor behind EPPM_VARIANT (eppm_internal.h): site-table vs computed coordinates in the
     refine, grouped vs per-sample __expf fix-up, joint vs serial random search, work-queue vs CTA-local propagation with and without
