@@ -61,6 +61,7 @@ EPPM_SYMBOLS = {
     "eppm_smooth_uses_tma": (C.c_int, [C.c_void_p]),
     "eppm_selftest_affine_sites": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "eppm_selftest_affine_sites_stride": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "eppm_selftest_volume_tables": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint)]),
     "eppm_refine_uses_site_table": (C.c_int, [C.c_void_p, C.c_int]),
     "eppm_eval_flow": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.POINTER(EppmFlowError)]),
     "eppm_write_flo": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),

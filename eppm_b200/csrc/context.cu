@@ -644,6 +644,15 @@ int eppm_selftest_affine_sites_stride(int w, int h, int pw, int stride, int* tab
         for (int q = 0; q < 3; q++) memcpy(table_out + q * n * n, t.off[q], (size_t)n * n * sizeof(int));
     return ok ? 1 : 0;
 }
+int eppm_selftest_volume_tables(int* box_out, int* t_out, unsigned* used_out) {
+    static VolTab v;
+    const bool ok = build_vol_tab(v);
+    if (ok && box_out)
+        for (int r = 0; r < 10; r++) { box_out[4 * r] = v.xlo[r]; box_out[4 * r + 1] = v.ylo[r]; box_out[4 * r + 2] = v.bx[r]; box_out[4 * r + 3] = v.by[r]; }
+    if (ok && t_out) memcpy(t_out, v.T, sizeof(v.T));
+    if (ok && used_out) memcpy(used_out, v.used, sizeof(v.used));
+    return ok ? 1 : 0;
+}
 int eppm_refine_uses_site_table(eppm_context* c, int level) {
     if (!c || level < 0 || level >= c->n_levels) return EPPM_ERR_ARG;
     return c->aff_ok[level] && !(c->variant & EPPM_VAR_REFINE_GENERIC);

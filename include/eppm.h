@@ -195,6 +195,11 @@ int eppm_selftest_affine_sites(int w, int h, int pw, int* table_out);
  * context at stride 1 tabulates the other 1082 sites and computes that one per thread with the reference's arithmetic. */
 int eppm_selftest_affine_sites_stride(int w, int h, int pw, int stride, int* table_out);
 int eppm_refine_uses_site_table(eppm_context* ctx, int level);
+/* Tables of the refine variant with a shared AD + census volume (EPPM_VARIANT bit 8388608): per patch row r = 0..9 the box of
+ * displacement "lines" (box_out: 10 x {xlo, ylo, bx, by}), the byte offset of (model q, sample s) inside the volume for the centre candidate
+ * of a lane at the CTA's minimum flow (t_out: 4 x 100) and the lines some lane can read when the CTA's flows spread by sx / sy
+ * (used_out: 10 x 4 x 4 words, index [r][sx + 2 sy]).  Host only (no CUDA call); returns 1 when the boxes fit the kernel's volume. */
+int eppm_selftest_volume_tables(int* box_out, int* t_out, unsigned* used_out);
 
 /* Evaluation against ground truth on the device (d_flow, d_gt: [n][h][w][2] f32 device arrays; out: n host records; synchronises).
  *   epe / aae_deg : bao_calc_flow_error (basic/bao_flow_tools.cpp:64-111): mean end-point error and mean angular error (degrees) over the

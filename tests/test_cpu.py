@@ -58,6 +58,50 @@ def test_scaled_patchmatch_rejects_bad_arguments_loudly(capfd):
     assert "baoCudaPatchMatch_Scaled" in capfd.readouterr().err
 
 
+def test_volume_tables_of_the_refine_variant():
+    """Host tables of the refine variant with a shared AD + census volume (eppm_selftest_volume_tables) against an independent restatement:
+    for every patch row the box must contain every displacement a lane can ask for -- site offset of the model (floor of the reference's two
+    FMAs) + candidate column / row (-1..1) + flow spread (0..1) -- T must address the line of the centre candidate, and the used masks must
+    mark exactly the lines that can be read."""
+    lib = _lib.load()
+    box = (C.c_int * 40)(); T = (C.c_int * 400)(); used = (C.c_uint * 160)()
+    assert lib.eppm_selftest_volume_tables(box, T, used) == 1
+    box = np.array(box).reshape(10, 4); T = np.array(T).reshape(4, 100); used = np.array(used, dtype=np.uint64).reshape(10, 4, 4)
+    coef = [(0.177, -0.011, -0.003, 0.301), (0.125, -0.357, 0.009, 0.308), (0.205, 0.370, 0.011, 0.296)]
+    f32 = np.float32
+    def site(i, j, cj, ci):   # floor(fma(i, ci, fma(j, cj, X))) - X; the fma results are exact enough at X = 1000 for a plain float64 restatement
+        return int(np.floor(np.float64(f32(i)) * np.float64(f32(ci)) + np.float64(f32(j)) * np.float64(f32(cj)) + 1000.0)) - 1000
+    cols = 32 + 18
+    assert (box[:, 2] * box[:, 3]).max() <= 104
+    for r in range(10):
+        i = -9 + 2 * r
+        xlo, ylo, bx, by = box[r]
+        offs = {(0, 0)}
+        for jj in range(10):
+            j = -9 + 2 * jj
+            s = r * 10 + jj
+            for q in range(4):
+                ox, oy = (0, 0) if q == 0 else (site(i, j, coef[q - 1][0], coef[q - 1][1]), site(i, j, coef[q - 1][2], coef[q - 1][3]))
+                offs.add((ox, oy))
+                line = (oy - ylo) * bx + (ox - xlo)
+                assert T[q, s] == 4 * (line * cols + 2 * jj), (r, jj, q)
+                for m in (-1, 0, 1):            # every reachable displacement lies inside the box, also with the flow spread
+                    for n in (-1, 0, 1):
+                        for ddx in (0, 1):
+                            for ddy in (0, 1):
+                                assert 0 <= ox + m + ddx - xlo < bx and 0 <= oy + n + ddy - ylo < by
+        for sxy in range(4):
+            want = set()
+            for (ox, oy) in offs:
+                for m in (-1, 0, 1):
+                    for n in (-1, 0, 1):
+                        for ddx in range((sxy & 1) + 1):
+                            for ddy in range((sxy >> 1) + 1):
+                                want.add((oy + n + ddy - ylo) * bx + (ox + m + ddx - xlo))
+            got = {L for L in range(bx * by) if (int(used[r, sxy, L >> 5]) >> (L & 31)) & 1}
+            assert got == want, (r, sxy)
+
+
 def test_default_params_are_the_reference_macros():
     p = E.default_params()  # defs.h:31-76
     assert (p.pyr_levels, p.num_iter, p.patch_r, p.patch_stride) == (3, 10, 9, 2)
