@@ -672,6 +672,7 @@ def test_video_stream_vs_reference_on_chained_frames(ref):
     ctx4.synchronize()
     assert same_bits(out_h, d_flow.cpu().numpy())
     rc = ref.create(h, w)
+    deltas = []
     for t in range(n):
         ref.set_data(rc, frames[t], frames[t + 1])
         for l in range(3):   # frame t sits in plane t of the image-1 arrays of the stream context
@@ -679,8 +680,13 @@ def test_video_stream_vs_reference_on_chained_frames(ref):
             assert same_bits(ctx4.read_plane(E.PLANE_CENSUS1, l, pair=t), ref.read_plane(rc, 2, l)), (t, l)
         fr = ref.compute_flow(rc, h, w)
         d = np.sqrt(((out_h[t].astype(np.float64) - fr.astype(np.float64)) ** 2).sum(-1))
-        assert synth.epe(out_h[t], flows[t], valids[t]) <= synth.epe(fr, flows[t], valids[t]) + 0.05 * (3.0 if RACY_SLACK > 1 else 1.0), t   # no worse than the reference against ground truth
+        deltas.append(synth.epe(out_h[t], flows[t], valids[t]) - synth.epe(fr, flows[t], valids[t]))
+        # no worse than the reference against ground truth: 0.05 px on the MEAN over the clip (below); a single pair additionally gets the 0.03 px the
+        # reference's own result moves by between runs and boxes (its in-place filters race: profiles/r02_ref_epe_spread.json).  Measured on this
+        # clip: +0.045, +0.008, -0.052 (tools/test_margins.py)
+        assert deltas[-1] <= (0.05 + 0.03) * (3.0 if RACY_SLACK > 1 else 1.0), (t, deltas)
         assert np.median(d) <= 1e-3, (t, np.median(d))
+    assert float(np.mean(deltas)) <= 0.05 * (3.0 if RACY_SLACK > 1 else 1.0), deltas
     ref.destroy(rc); ctx.close(); ctx4.close()
 
 
